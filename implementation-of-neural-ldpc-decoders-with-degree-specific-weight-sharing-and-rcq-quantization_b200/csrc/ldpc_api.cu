@@ -1,0 +1,811 @@
+// C-ABI layer (include/ldpc_b200.h): Tanner-graph re-layout, decoder objects, device workspace,
+// the per-iteration launch sequence, the chunked host<->device pipeline and the Monte-Carlo round.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_b200.h"
+#include "ldpc_internal.h"
+
+using namespace ldpc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? LDPC_ERR_NOMEM : LDPC_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(T** dptr, const std::vector<T>& h) {
+    *dptr = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CU(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) CU(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+constexpr int kCnChunk = 8;   // checks per work item
+constexpr int kVnChunk = 8;   // variables per work item
+constexpr int64_t kFrameAlign = 128;
+
+}  // namespace
+
+// =================================================================================================
+// Graph
+// =================================================================================================
+struct ldpc_graph {
+    int device = 0;
+    int32_t n = 0, m = 0;
+    int64_t E = 0;
+    int max_dc = 0, max_dv = 0;
+    int n_cclass = 0, n_vclass = 0;
+    // host copies (layout + tests)
+    std::vector<int32_t> slot_of_edge;   // [E] check-major edge id -> slot
+    std::vector<int32_t> slot_var;       // [E] slot -> variable
+    std::vector<int32_t> vslots;         // slot lists by degree-sorted variable position
+    std::vector<int32_t> vpos_var;       // [n] position -> variable
+    std::vector<int32_t> var_vpos;       // [n] variable -> position
+    std::vector<WorkItem> cn_items, vn_items;
+    // device copies
+    int32_t* d_slot_var = nullptr;
+    int32_t* d_vslots = nullptr;
+    int32_t* d_vpos_var = nullptr;
+    WorkItem* d_cn_items = nullptr;
+    WorkItem* d_vn_items = nullptr;
+};
+
+extern "C" int ldpc_version(void) { return LDPC_B200_VERSION; }
+extern "C" const char* ldpc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ldpc_device_count(int* count) {
+    if (!count) return fail(LDPC_ERR_INVALID, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(LDPC_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = c;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(LDPC_ERR_INVALID, "bad arguments");
+    CU(cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return LDPC_OK;
+}
+extern "C" int ldpc_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return LDPC_OK;
+}
+
+// K6 graph_relayout: replaces the dense-H neighbour scans (ldpc_decoder.py:85,92,124,136).
+extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t* check_ptr,
+                                 const int32_t* check_var, ldpc_graph** out) {
+    if (!out) return fail(LDPC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || m < 0 || !check_ptr || (m > 0 && check_ptr[m] > 0 && !check_var))
+        return fail(LDPC_ERR_INVALID, "bad graph arguments");
+    if (check_ptr[0] != 0) return fail(LDPC_ERR_INVALID, "check_ptr[0] must be 0");
+    const int64_t E = check_ptr[m];
+    if (E >= (int64_t)1 << 31) return fail(LDPC_ERR_UNSUPPORTED, "more than 2^31-1 edges");
+    std::vector<int32_t> dv(n, 0);
+    int max_dc = 0;
+    for (int32_t i = 0; i < m; ++i) {
+        int64_t a = check_ptr[i], b = check_ptr[i + 1];
+        if (b < a) return fail(LDPC_ERR_INVALID, "check_ptr not monotone at %d", i);
+        max_dc = std::max<int64_t>(max_dc, b - a);
+        for (int64_t e = a; e < b; ++e) {
+            int32_t j = check_var[e];
+            if (j < 0 || j >= n) return fail(LDPC_ERR_INVALID, "variable index %d out of range", j);
+            if (e > a && check_var[e - 1] >= j)
+                return fail(LDPC_ERR_INVALID, "check %d: variables must be strictly ascending", i);
+            dv[j]++;
+        }
+    }
+    int max_dv = 0;
+    for (int32_t j = 0; j < n; ++j) max_dv = std::max(max_dv, dv[j]);
+
+    ldpc_graph* g = new (std::nothrow) ldpc_graph();
+    if (!g) return fail(LDPC_ERR_NOMEM, "host allocation failed");
+    g->device = device;
+    g->n = n;
+    g->m = m;
+    g->E = E;
+    g->max_dc = max_dc;
+    g->max_dv = max_dv;
+
+    // ---- check side: stable sort of non-empty checks by degree -> slots ----
+    std::vector<int32_t> corder;
+    corder.reserve(m);
+    for (int32_t i = 0; i < m; ++i)
+        if (check_ptr[i + 1] > check_ptr[i]) corder.push_back(i);
+    std::stable_sort(corder.begin(), corder.end(), [&](int32_t a, int32_t b) {
+        return (check_ptr[a + 1] - check_ptr[a]) < (check_ptr[b + 1] - check_ptr[b]);
+    });
+    g->slot_of_edge.assign((size_t)E, -1);
+    g->slot_var.assign((size_t)E, 0);
+    {
+        int32_t slot = 0;
+        int prev_deg = -1;
+        size_t pos = 0;
+        while (pos < corder.size()) {
+            int deg = (int)(check_ptr[corder[pos] + 1] - check_ptr[corder[pos]]);
+            if (deg != prev_deg) {
+                g->n_cclass++;
+                prev_deg = deg;
+            }
+            size_t end = pos;
+            while (end < corder.size() && (int)(check_ptr[corder[end] + 1] - check_ptr[corder[end]]) == deg) ++end;
+            for (size_t c = pos; c < end; c += kCnChunk) {
+                WorkItem it;
+                it.deg = deg;
+                it.count = (int32_t)std::min<size_t>(kCnChunk, end - c);
+                it.first_node = (int32_t)c;
+                it.first_slot = slot + (int32_t)((c - pos) * (size_t)deg);
+                g->cn_items.push_back(it);
+            }
+            for (size_t c = pos; c < end; ++c) {
+                int32_t i = corder[c];
+                for (int k = 0; k < deg; ++k) {
+                    int64_t e = check_ptr[i] + k;
+                    g->slot_of_edge[(size_t)e] = slot;
+                    g->slot_var[(size_t)slot] = check_var[e];
+                    ++slot;
+                }
+            }
+            pos = end;
+        }
+    }
+    // ---- variable side: stable sort by degree; slot lists in ascending check index ----
+    std::vector<int32_t> vorder(n);
+    for (int32_t j = 0; j < n; ++j) vorder[j] = j;
+    std::stable_sort(vorder.begin(), vorder.end(), [&](int32_t a, int32_t b) { return dv[a] < dv[b]; });
+    g->vpos_var = vorder;
+    g->var_vpos.assign(n, 0);
+    std::vector<int64_t> lbase(n, 0);
+    {
+        int64_t off = 0;
+        for (int32_t p = 0; p < n; ++p) {
+            g->var_vpos[vorder[p]] = p;
+            lbase[vorder[p]] = off;
+            off += dv[vorder[p]];
+        }
+    }
+    g->vslots.assign((size_t)E, 0);
+    {
+        std::vector<int32_t> fill(n, 0);
+        for (int32_t i = 0; i < m; ++i)  // ascending check index => ascending inside every variable list
+            for (int64_t e = check_ptr[i]; e < check_ptr[i + 1]; ++e) {
+                int32_t j = check_var[e];
+                g->vslots[(size_t)(lbase[j] + fill[j]++)] = g->slot_of_edge[(size_t)e];
+            }
+        int prev_deg = -1;
+        int32_t pos = 0;
+        while (pos < n) {
+            int deg = dv[vorder[pos]];
+            if (deg != prev_deg) {
+                g->n_vclass++;
+                prev_deg = deg;
+            }
+            int32_t end = pos;
+            while (end < n && dv[vorder[end]] == deg) ++end;
+            for (int32_t c = pos; c < end; c += kVnChunk) {
+                WorkItem it;
+                it.deg = deg;
+                it.count = std::min<int32_t>(kVnChunk, end - c);
+                it.first_node = c;
+                it.first_slot = (int32_t)lbase[vorder[c]];
+                g->vn_items.push_back(it);
+            }
+            pos = end;
+        }
+    }
+    // ---- upload ----
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete g;
+        return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", device);
+    }
+    int rc = upload(&g->d_slot_var, g->slot_var);
+    if (!rc) rc = upload(&g->d_vslots, g->vslots);
+    if (!rc) rc = upload(&g->d_vpos_var, g->vpos_var);
+    if (!rc) rc = upload(&g->d_cn_items, g->cn_items);
+    if (!rc) rc = upload(&g->d_vn_items, g->vn_items);
+    if (rc) {
+        ldpc_graph_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
+    if (!g) return LDPC_OK;
+    DeviceGuard guard(g->device);
+    cudaFree(g->d_slot_var);
+    cudaFree(g->d_vslots);
+    cudaFree(g->d_vpos_var);
+    cudaFree(g->d_cn_items);
+    cudaFree(g->d_vn_items);
+    delete g;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_query(const ldpc_graph* g, int what, int64_t* value) {
+    if (!g || !value) return fail(LDPC_ERR_INVALID, "NULL argument");
+    switch (what) {
+        case LDPC_GRAPH_N: *value = g->n; break;
+        case LDPC_GRAPH_M: *value = g->m; break;
+        case LDPC_GRAPH_E: *value = g->E; break;
+        case LDPC_GRAPH_CHECK_CLASSES: *value = g->n_cclass; break;
+        case LDPC_GRAPH_VAR_CLASSES: *value = g->n_vclass; break;
+        case LDPC_GRAPH_MAX_DC: *value = g->max_dc; break;
+        case LDPC_GRAPH_MAX_DV: *value = g->max_dv; break;
+        case LDPC_GRAPH_DEVICE: *value = g->device; break;
+        default: return fail(LDPC_ERR_INVALID, "unknown query %d", what);
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_slot_of_edge(const ldpc_graph* g, int32_t* slot_of_edge) {
+    if (!g || !slot_of_edge) return fail(LDPC_ERR_INVALID, "NULL argument");
+    std::memcpy(slot_of_edge, g->slot_of_edge.data(), (size_t)g->E * sizeof(int32_t));
+    return LDPC_OK;
+}
+
+// =================================================================================================
+// Decoder
+// =================================================================================================
+namespace {
+
+struct Workspace {
+    int64_t cap = 0;  // frames (multiple of kFrameAlign)
+    void* llrT = nullptr;
+    void* v2c = nullptr;
+    void* c2v = nullptr;
+    uint32_t* hardw = nullptr;
+    uint32_t* unsat = nullptr;  // [2][Wn]
+    uint8_t* done = nullptr;
+    int32_t* iters = nullptr;
+    uint8_t* success = nullptr;
+    void release() {
+        cudaFree(llrT); cudaFree(v2c); cudaFree(c2v); cudaFree(hardw); cudaFree(unsat);
+        cudaFree(done); cudaFree(iters); cudaFree(success);
+        *this = Workspace();
+    }
+};
+
+struct HostLane {            // one lane of the host pipeline: its own stream, staging and workspace
+    cudaStream_t stream = nullptr;
+    cudaEvent_t free_ev = nullptr;
+    Workspace ws;
+    void* d_llr = nullptr;
+    uint8_t* d_bits = nullptr;
+    void* d_post = nullptr;
+    int64_t cap = 0;
+    bool post_cap = false;
+};
+
+}  // namespace
+
+struct ldpc_decoder {
+    ldpc_graph* g = nullptr;
+    int dtype = LDPC_F32;
+    int V = 4;
+    size_t rsz = 4;
+    int T = 0;
+    int early_stop = 1;
+    int n_beta = 0, n_alpha = 0, bc = 0, Q = 0, nth = 0;
+    std::vector<int> mono;                 // per quantiser
+    std::vector<int32_t> q_of_iter;        // host copy
+    int32_t* d_bidx = nullptr;             // per slot
+    int32_t* d_aidx = nullptr;             // per vpos
+    void* d_beta = nullptr;                // [T][n_beta]
+    void* d_alpha = nullptr;               // [T][n_alpha]
+    float* d_thr = nullptr;                // [Q][nth]
+    float* d_lut = nullptr;                // [Q][2^bc]
+    int32_t* d_q_of_iter = nullptr;        // [T]
+    Workspace ws;
+    HostLane lanes[2];
+    int64_t host_chunk = 0;
+    // instrumentation
+    int prof_mode = 0;
+    ldpc_profile prof{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    struct Pending { int kind; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    size_t ev_next = 0;
+};
+
+namespace {
+
+int64_t pad_frames(int64_t B) { return (B + kFrameAlign - 1) / kFrameAlign * kFrameAlign; }
+
+int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
+    if (ws.cap >= Bp) return LDPC_OK;
+    ws.release();
+    const ldpc_graph* g = d->g;
+    const size_t rows_v2c = (size_t)std::max<int64_t>(std::max<int64_t>(g->E, g->n), 1);
+    const size_t rows_c2v = (size_t)std::max<int64_t>(g->E, 1);
+    const size_t c2v_elt = d->bc ? 1 : d->rsz;
+    const int64_t Wn = Bp / 32;
+    CU(cudaMalloc(&ws.llrT, (size_t)g->n * Bp * d->rsz));
+    CU(cudaMalloc(&ws.v2c, rows_v2c * Bp * d->rsz));
+    CU(cudaMalloc(&ws.c2v, rows_c2v * Bp * c2v_elt));
+    CU(cudaMalloc((void**)&ws.hardw, (size_t)g->n * Wn * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&ws.unsat, (size_t)2 * Wn * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&ws.done, (size_t)Bp));
+    CU(cudaMalloc((void**)&ws.iters, (size_t)Bp * sizeof(int32_t)));
+    CU(cudaMalloc((void**)&ws.success, (size_t)Bp));
+    ws.cap = Bp;
+    return LDPC_OK;
+}
+
+// ---- instrumentation helpers ----
+enum { K_CN = 0, K_VN = 1, K_OTHER = 2 };
+
+struct Timed {
+    ldpc_decoder* d;
+    int kind;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timed(ldpc_decoder* d_, int kind_, cudaStream_t s_) : d(d_), kind(kind_), s(s_) {
+        d->prof.launches++;
+        if (kind == K_CN) d->prof.cn_launches++;
+        if (kind == K_VN) d->prof.vn_launches++;
+        if (d->prof_mode == 1) {
+            if (d->ev_next >= d->ev_pool.size()) {
+                cudaEvent_t x, y;
+                if (cudaEventCreate(&x) == cudaSuccess && cudaEventCreate(&y) == cudaSuccess)
+                    d->ev_pool.emplace_back(x, y);
+            }
+            if (d->ev_next < d->ev_pool.size()) {
+                a = d->ev_pool[d->ev_next].first;
+                b = d->ev_pool[d->ev_next].second;
+                d->ev_next++;
+                cudaEventRecord(a, s);
+            }
+        }
+    }
+    ~Timed() {
+        if (a) {
+            cudaEventRecord(b, s);
+            d->pending.push_back({kind, a, b});
+        }
+    }
+};
+
+#define LAUNCH(kind, expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t le_;                                                                       \
+        {                                                                                      \
+            Timed t_(d, kind, stream);                                                         \
+            le_ = (expr);                                                                      \
+        }                                                                                      \
+        if (le_ != cudaSuccess)                                                                \
+            return fail(LDPC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(le_));              \
+    } while (0)
+
+// The flooding schedule on frames already resident as llrT [n][Bp] in `ws`.
+// After it returns (stream order): ws.hardw holds the final hard decisions of every frame,
+// ws.iters / ws.success the per-frame results, and ws.v2c holds postT [n][Bp] if want_post.
+int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
+    const ldpc_graph* g = d->g;
+    const int64_t Wn = Bp / 32;
+    LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
+    for (int t = 0; t < d->T; ++t) {
+        const int q = d->bc ? d->q_of_iter[t] : 0;
+        CnLaunch cn{};
+        cn.src = (t == 0) ? ws.llrT : ws.v2c;
+        cn.dst = ws.c2v;
+        cn.row_map = (t == 0) ? g->d_slot_var : nullptr;
+        cn.bidx = d->d_bidx;
+        cn.beta_t = d->d_beta ? (const char*)d->d_beta + (size_t)t * d->n_beta * d->rsz : nullptr;
+        cn.thr = d->bc ? d->d_thr + (size_t)q * d->nth : nullptr;
+        cn.nth = d->nth;
+        cn.bc = d->bc;
+        cn.mono = d->bc ? d->mono[q] : 1;
+        cn.done = ws.done;
+        cn.items = g->d_cn_items;
+        cn.n_items = (int)g->cn_items.size();
+        cn.Bp = Bp;
+        LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
+
+        const bool last = (t == d->T - 1);
+        VnLaunch vn{};
+        vn.c2v = ws.c2v;
+        vn.v2c = ws.v2c;
+        vn.llrT = ws.llrT;
+        vn.postT = (last && want_post) ? ws.v2c : nullptr;  // v2c is dead after the last check pass
+        vn.vslots = g->d_vslots;
+        vn.vpos_var = g->d_vpos_var;
+        vn.aidx = d->d_aidx;
+        vn.alpha_t = d->d_alpha ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
+        vn.lut = d->d_lut;
+        vn.bc = d->bc;
+        vn.n_quant = d->Q;
+        vn.q_now = q;
+        vn.q_of_iter = d->d_q_of_iter;
+        vn.iters = ws.iters;
+        vn.hardw = ws.hardw;
+        vn.Wn = Wn;
+        vn.done = ws.done;
+        vn.items = g->d_vn_items;
+        vn.n_items = (int)g->vn_items.size();
+        vn.Bp = Bp;
+        vn.final_pass = last ? 1 : 0;
+        // The last pass recomputes posterior + decision of EVERY frame from its frozen c2v (frames that
+        // stopped at iteration t kept c2v(t)); the dead v2c update of iteration T-1 is not written.
+        LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
+
+        if (d->early_stop || last) {
+            uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
+            uint32_t* nxt = ws.unsat + (size_t)((t + 1) & 1) * Wn;
+            SynLaunch sy{};
+            sy.hardw = ws.hardw;
+            sy.Wn = Wn;
+            sy.slot_var = g->d_slot_var;
+            sy.items = g->d_cn_items;
+            sy.n_items = (int)g->cn_items.size();
+            sy.unsat = cur;
+            LAUNCH(K_OTHER, launch_syndrome(sy, stream));
+            LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
+        }
+    }
+    return LDPC_OK;
+}
+
+int emit_outputs(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, uint8_t* bits, void* post, int32_t* iters,
+                 uint8_t* success, cudaStream_t stream) {
+    const ldpc_graph* g = d->g;
+    if (bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, bits, B, g->n, stream));
+    if (post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, post, B, Bp, g->n, stream));
+    if (iters) CU(cudaMemcpyAsync(iters, ws.iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    if (success) CU(cudaMemcpyAsync(success, ws.success, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+    return LDPC_OK;
+}
+
+int decode_on_device(ldpc_decoder* d, Workspace& ws, const void* llr, int64_t B, uint8_t* bits, void* post,
+                     int32_t* iters, uint8_t* success, cudaStream_t stream) {
+    const int64_t Bp = pad_frames(B);
+    int rc = ws_ensure(d, ws, Bp);
+    if (rc) return rc;
+    d->prof.frames_padded = Bp;
+    LAUNCH(K_OTHER, launch_pack(d->dtype, llr, ws.llrT, B, Bp, d->g->n, ws.done, ws.iters, ws.success, d->T, stream));
+    rc = run_iterations(d, ws, B, Bp, post != nullptr, stream);
+    if (rc) return rc;
+    return emit_outputs(d, ws, B, Bp, bits, post, iters, success, stream);
+}
+
+}  // namespace
+
+extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg, ldpc_decoder** out) {
+    if (!out) return fail(LDPC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!g || !cfg) return fail(LDPC_ERR_INVALID, "NULL argument");
+    if (cfg->struct_size != (int32_t)sizeof(ldpc_decoder_config))
+        return fail(LDPC_ERR_INVALID, "config struct_size %d != %d", cfg->struct_size, (int)sizeof(ldpc_decoder_config));
+    if (cfg->dtype != LDPC_F32 && cfg->dtype != LDPC_F64) return fail(LDPC_ERR_INVALID, "bad dtype");
+    if (cfg->max_iterations < 1) return fail(LDPC_ERR_INVALID, "max_iterations must be >= 1");
+    if (cfg->n_beta < 0 || cfg->n_alpha < 0) return fail(LDPC_ERR_INVALID, "negative table width");
+    if (cfg->n_beta > 0 && !cfg->beta) return fail(LDPC_ERR_INVALID, "beta is NULL");
+    if (cfg->n_alpha > 0 && !cfg->alpha) return fail(LDPC_ERR_INVALID, "alpha is NULL");
+    if (cfg->bc != 0) {
+        if (cfg->bc < 2 || cfg->bc > 8) return fail(LDPC_ERR_UNSUPPORTED, "bc must be 0 or 2..8");
+        if (cfg->dtype != LDPC_F32) return fail(LDPC_ERR_UNSUPPORTED, "quantised decoding is float32 only");
+        if (cfg->n_quantizers < 1 || !cfg->thresholds || !cfg->quantizer_of_iter)
+            return fail(LDPC_ERR_INVALID, "quantiser tables missing");
+        if (((int64_t)cfg->n_quantizers << cfg->bc) > kMaxLutFloats)
+            return fail(LDPC_ERR_UNSUPPORTED, "too many quantiser levels");
+    }
+    if (cfg->dtype == LDPC_F64 && g->max_dv > 129)
+        return fail(LDPC_ERR_UNSUPPORTED, "float64 path models np.sum up to 128 terms (max variable degree 129)");
+    const int T = cfg->max_iterations;
+    const int64_t E = g->E;
+    if (cfg->beta_index)
+        for (int64_t e = 0; e < E; ++e)
+            if (cfg->beta_index[e] < 0 || cfg->beta_index[e] >= std::max(cfg->n_beta, 1))
+                return fail(LDPC_ERR_INVALID, "beta_index[%lld] out of range", (long long)e);
+    if (cfg->alpha_index)
+        for (int32_t j = 0; j < g->n; ++j)
+            if (cfg->alpha_index[j] < 0 || cfg->alpha_index[j] >= std::max(cfg->n_alpha, 1))
+                return fail(LDPC_ERR_INVALID, "alpha_index[%d] out of range", j);
+
+    ldpc_decoder* d = new (std::nothrow) ldpc_decoder();
+    if (!d) return fail(LDPC_ERR_NOMEM, "host allocation failed");
+    d->g = g;
+    d->dtype = cfg->dtype;
+    d->V = cfg->dtype == LDPC_F32 ? 4 : 2;
+    d->rsz = cfg->dtype == LDPC_F32 ? 4 : 8;
+    d->T = T;
+    d->early_stop = cfg->early_stop ? 1 : 0;
+    d->n_beta = cfg->n_beta;
+    d->n_alpha = cfg->n_alpha;
+    d->bc = cfg->bc;
+    d->Q = cfg->bc ? cfg->n_quantizers : 0;
+    d->nth = cfg->bc ? (1 << (cfg->bc - 1)) : 0;
+
+    DeviceGuard guard(g->device);
+    if (!guard.ok) {
+        delete d;
+        return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", g->device);
+    }
+    int rc = LDPC_OK;
+    if (cfg->n_beta > 0 && cfg->beta_index) {
+        std::vector<int32_t> bidx((size_t)E);
+        for (int64_t e = 0; e < E; ++e) bidx[(size_t)g->slot_of_edge[(size_t)e]] = cfg->beta_index[e];
+        rc = upload(&d->d_bidx, bidx);
+    }
+    if (!rc && cfg->n_alpha > 0 && cfg->alpha_index) {
+        std::vector<int32_t> aidx((size_t)g->n);
+        for (int32_t p = 0; p < g->n; ++p) aidx[(size_t)p] = cfg->alpha_index[g->vpos_var[(size_t)p]];
+        rc = upload(&d->d_aidx, aidx);
+    }
+    if (!rc && cfg->n_beta > 0) {
+        size_t bytes = (size_t)T * cfg->n_beta * d->rsz;
+        cudaError_t e = cudaMalloc(&d->d_beta, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(d->d_beta, cfg->beta, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(LDPC_ERR_CUDA, "beta upload: %s", cudaGetErrorString(e));
+    }
+    if (!rc && cfg->n_alpha > 0) {
+        size_t bytes = (size_t)T * cfg->n_alpha * d->rsz;
+        cudaError_t e = cudaMalloc(&d->d_alpha, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(d->d_alpha, cfg->alpha, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(LDPC_ERR_CUDA, "alpha upload: %s", cudaGetErrorString(e));
+    }
+    if (!rc && cfg->bc) {
+        const int nth = d->nth, nl = 1 << cfg->bc;
+        std::vector<float> thr(cfg->thresholds, cfg->thresholds + (size_t)d->Q * nth);
+        std::vector<float> lut((size_t)d->Q * nl);
+        d->mono.assign(d->Q, 1);
+        for (int q = 0; q < d->Q; ++q) {
+            for (int j = 1; j < nth; ++j)
+                if (!(thr[(size_t)q * nth + j] >= thr[(size_t)q * nth + j - 1])) d->mono[q] = 0;
+            for (int code = 0; code < nl; ++code) {
+                // rcq_decoder.py:106-119: sign = 1 - 2*sign_bit, value = sign * threshold[idx]
+                int sb = code >= nth;
+                float sign = 1.f - 2.f * (float)sb;
+                lut[(size_t)q * nl + code] = sign * thr[(size_t)q * nth + (code % nth)];
+            }
+        }
+        d->q_of_iter.assign(cfg->quantizer_of_iter, cfg->quantizer_of_iter + T);
+        for (int t = 0; t < T && !rc; ++t)
+            if (d->q_of_iter[t] < 0 || d->q_of_iter[t] >= d->Q) rc = fail(LDPC_ERR_INVALID, "quantizer_of_iter[%d] out of range", t);
+        if (!rc) rc = upload(&d->d_thr, thr);
+        if (!rc) rc = upload(&d->d_lut, lut);
+        if (!rc) rc = upload(&d->d_q_of_iter, d->q_of_iter);
+    }
+    if (rc) {
+        ldpc_decoder_destroy(d);
+        return rc;
+    }
+    *out = d;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decoder_set_weights(ldpc_decoder* d, const void* beta, const void* alpha) {
+    if (!d) return fail(LDPC_ERR_INVALID, "NULL decoder");
+    DeviceGuard guard(d->g->device);
+    if (beta) {
+        if (!d->d_beta) return fail(LDPC_ERR_INVALID, "decoder was created without beta");
+        CU(cudaMemcpy(d->d_beta, beta, (size_t)d->T * d->n_beta * d->rsz, cudaMemcpyHostToDevice));
+    }
+    if (alpha) {
+        if (!d->d_alpha) return fail(LDPC_ERR_INVALID, "decoder was created without alpha");
+        CU(cudaMemcpy(d->d_alpha, alpha, (size_t)d->T * d->n_alpha * d->rsz, cudaMemcpyHostToDevice));
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
+    if (!d) return LDPC_OK;
+    DeviceGuard guard(d->g->device);
+    cudaDeviceSynchronize();
+    d->ws.release();
+    for (auto& ln : d->lanes) {
+        ln.ws.release();
+        cudaFree(ln.d_llr);
+        cudaFree(ln.d_bits);
+        cudaFree(ln.d_post);
+        if (ln.free_ev) cudaEventDestroy(ln.free_ev);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    for (auto& ev : d->ev_pool) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    cudaFree(d->d_bidx);
+    cudaFree(d->d_aidx);
+    cudaFree(d->d_beta);
+    cudaFree(d->d_alpha);
+    cudaFree(d->d_thr);
+    cudaFree(d->d_lut);
+    cudaFree(d->d_q_of_iter);
+    delete d;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decoder_reserve(ldpc_decoder* d, int64_t frames) {
+    if (!d || frames < 1) return fail(LDPC_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(d->g->device);
+    return ws_ensure(d, d->ws, pad_frames(frames));
+}
+
+extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
+                                  int32_t* iterations, uint8_t* success, void* stream) {
+    if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
+    if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
+    DeviceGuard guard(d->g->device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    return decode_on_device(d, d->ws, llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
+}
+
+// Host-buffer entry point: chunked, double-buffered H2D -> decode -> D2H on two private streams.
+extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
+                                int32_t* iterations, uint8_t* success) {
+    if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
+    if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
+    DeviceGuard guard(d->g->device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    const ldpc_graph* g = d->g;
+    const int64_t n = g->n;
+    // chunk: big enough to fill the GPU (>= 8192 frames when available), two chunks in flight
+    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : 8192;
+    if (B <= chunk) chunk = B;
+    const int nl = (B > chunk) ? 2 : 1;
+    for (int l = 0; l < nl; ++l) {
+        HostLane& ln = d->lanes[l];
+        if (!ln.stream) CU(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        if (ln.cap < chunk || (posterior && !ln.post_cap)) {
+            cudaFree(ln.d_llr); cudaFree(ln.d_bits); cudaFree(ln.d_post);
+            ln.d_llr = nullptr; ln.d_bits = nullptr; ln.d_post = nullptr;
+            CU(cudaMalloc(&ln.d_llr, (size_t)chunk * n * d->rsz));
+            CU(cudaMalloc((void**)&ln.d_bits, (size_t)chunk * n));
+            if (posterior) CU(cudaMalloc(&ln.d_post, (size_t)chunk * n * d->rsz));
+            ln.cap = chunk;
+            ln.post_cap = posterior != nullptr;
+        }
+        int rc = ws_ensure(d, ln.ws, pad_frames(chunk));
+        if (rc) return rc;
+    }
+    int rc = LDPC_OK;
+    int64_t done_frames = 0;
+    int l = 0;
+    while (done_frames < B && !rc) {
+        const int64_t b = std::min<int64_t>(chunk, B - done_frames);
+        HostLane& ln = d->lanes[l];
+        cudaStream_t stream = ln.stream;
+        const char* src = (const char*)llr + (size_t)done_frames * n * d->rsz;
+        CU(cudaMemcpyAsync(ln.d_llr, src, (size_t)b * n * d->rsz, cudaMemcpyHostToDevice, stream));
+        int32_t* d_it = ln.ws.iters;
+        uint8_t* d_su = ln.ws.success;
+        rc = decode_on_device(d, ln.ws, ln.d_llr, b, bits ? ln.d_bits : nullptr, posterior ? ln.d_post : nullptr,
+                              nullptr, nullptr, stream);
+        if (rc) break;
+        if (bits) CU(cudaMemcpyAsync(bits + (size_t)done_frames * n, ln.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, stream));
+        if (posterior)
+            CU(cudaMemcpyAsync((char*)posterior + (size_t)done_frames * n * d->rsz, ln.d_post, (size_t)b * n * d->rsz,
+                               cudaMemcpyDeviceToHost, stream));
+        if (iterations) CU(cudaMemcpyAsync(iterations + done_frames, d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        if (success) CU(cudaMemcpyAsync(success + done_frames, d_su, (size_t)b, cudaMemcpyDeviceToHost, stream));
+        done_frames += b;
+        l = (l + 1) % nl;
+    }
+    for (int k = 0; k < nl; ++k) {
+        cudaError_t e = cudaStreamSynchronize(d->lanes[k].stream);
+        if (e != cudaSuccess && !rc) rc = fail(LDPC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+// =================================================================================================
+// Monte-Carlo leg
+// =================================================================================================
+extern "C" int ldpc_awgn_llr(int device, int32_t n, int64_t B, uint64_t frame0, uint64_t seed, float snr_db,
+                             int32_t llr_sign, const uint8_t* codeword, float* llr_out, void* stream) {
+    if (n < 1 || B < 1 || !llr_out) return fail(LDPC_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", device);
+    cudaError_t e = launch_awgn(LDPC_F32, 1, llr_out, n, B, B, frame0, seed, snr_db, llr_sign, codeword, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(LDPC_ERR_CUDA, "awgn launch: %s", cudaGetErrorString(e));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, uint64_t seed, uint64_t frame0, int64_t B,
+                             const uint8_t* codeword, int64_t* counters, int32_t* frame_bit_errors,
+                             int32_t* frame_iterations, void* stream_) {
+    if (!d || !counters) return fail(LDPC_ERR_INVALID, "NULL argument");
+    if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
+    DeviceGuard guard(d->g->device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t Bp = pad_frames(B);
+    int rc = ws_ensure(d, d->ws, Bp);
+    if (rc) return rc;
+    d->prof.frames_padded = Bp;
+    Workspace& ws = d->ws;
+    LAUNCH(K_OTHER, launch_awgn(d->dtype, 0, ws.llrT, d->g->n, B, Bp, frame0, seed, snr_db, llr_sign, codeword, stream));
+    rc = run_iterations(d, ws, B, Bp, false, stream);
+    if (rc) return rc;
+    LAUNCH(K_OTHER, launch_count_packed(d->V, ws.hardw, Bp / 32, d->g->n, B, codeword, ws.iters, counters,
+                                        frame_bit_errors, frame_iterations, stream));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_count_errors(int device, int32_t n, int64_t B, const uint8_t* bits, const uint8_t* codeword,
+                                 const int32_t* iterations, int64_t* counters, int32_t* frame_bit_errors, void* stream) {
+    if (n < 1 || B < 1 || !bits || !counters) return fail(LDPC_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", device);
+    cudaError_t e = launch_count_bits(bits, n, B, codeword, iterations, counters, frame_bit_errors, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(LDPC_ERR_CUDA, "count launch: %s", cudaGetErrorString(e));
+    return LDPC_OK;
+}
+
+// =================================================================================================
+// Instrumentation
+// =================================================================================================
+extern "C" int ldpc_decoder_profile_mode(ldpc_decoder* d, int32_t mode) {
+    if (!d || mode < 0 || mode > 1) return fail(LDPC_ERR_INVALID, "bad arguments");
+    d->prof_mode = mode;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decoder_profile_read(ldpc_decoder* d, ldpc_profile* out, int32_t reset) {
+    if (!d || !out) return fail(LDPC_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(d->g->device);
+    if (!d->pending.empty()) {
+        CU(cudaDeviceSynchronize());
+        for (auto& p : d->pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+                if (p.kind == K_CN) d->prof.cn_ms += ms;
+                else if (p.kind == K_VN) d->prof.vn_ms += ms;
+                else d->prof.other_ms += ms;
+            }
+        }
+        d->pending.clear();
+        d->ev_next = 0;
+    }
+    *out = d->prof;
+    if (reset) {
+        int64_t fp = d->prof.frames_padded;
+        d->prof = ldpc_profile{};
+        d->prof.frames_padded = fp;
+    }
+    return LDPC_OK;
+}

@@ -1,0 +1,105 @@
+// Host-visible declarations shared between the kernel translation unit and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldpc {
+
+// One unit of grid work: `count` consecutive nodes of one degree class.
+//   check side : `first_slot` = message slot of the first check's first edge; the next check
+//                starts `deg` slots later (degree-sorted, check-major slot layout).
+//   variable side: `first_node` = position (vpos) of the first variable in degree-sorted order;
+//                `first_slot` = offset of its slot list inside vslots; next variable += deg.
+struct WorkItem {
+    int32_t deg;
+    int32_t count;
+    int32_t first_node;
+    int32_t first_slot;
+};
+
+constexpr int kMaxQuantLevels = 128;   // 2^(bc-1) for bc <= 8
+constexpr int kMaxLutFloats = 4096;    // Q * 2^bc
+
+struct CnLaunch {
+    const void* src;            // v2c [E][Bp], or llrT [n][Bp] for iteration 0
+    void* dst;                  // c2v: Real [E][Bp] or uint8 codes [E][Bp]
+    const int32_t* row_map;     // iteration 0: variable of each slot; else nullptr
+    const int32_t* bidx;        // per-slot column of beta, or nullptr (column 0)
+    const void* beta_t;         // beta row of this iteration, or nullptr (beta == 1)
+    const float* thr;           // device thresholds of this iteration's quantiser [nth]
+    int nth;                    // 2^(bc-1), 0 = float messages
+    int bc;
+    int mono;                   // thresholds non-decreasing
+    const uint8_t* done;        // [Bp]
+    const WorkItem* items;
+    int n_items;
+    int64_t Bp;
+};
+
+struct VnLaunch {
+    const void* c2v;            // Real [E][Bp] or uint8 codes
+    void* v2c;                  // Real [E][Bp] (ignored by the final pass)
+    const void* llrT;           // Real [n][Bp]
+    void* postT;                // final pass: Real [n][Bp] or nullptr
+    const int32_t* vslots;      // slot lists, ascending check index inside a variable
+    const int32_t* vpos_var;    // variable id at each degree-sorted position
+    const int32_t* aidx;        // per-position column of alpha, or nullptr (column 0)
+    const void* alpha_t;        // alpha row of this iteration, or nullptr
+    const float* lut;           // device LUT [Q][2^bc] (value of every code), or nullptr
+    int bc;
+    int n_quant;
+    int q_now;                  // quantiser of this iteration (non-final)
+    const int32_t* q_of_iter;   // final pass: quantiser by iteration, selected through iters[]
+    const int32_t* iters;       // [Bp] iterations executed per frame (final pass)
+    uint32_t* hardw;            // [n][Wn] packed hard decisions
+    int64_t Wn;                 // Bp / 32
+    const uint8_t* done;
+    const WorkItem* items;
+    int n_items;
+    int64_t Bp;
+    int final_pass;
+};
+
+struct SynLaunch {
+    const uint32_t* hardw;
+    int64_t Wn;
+    const int32_t* slot_var;
+    const WorkItem* items;      // check-side items
+    int n_items;
+    uint32_t* unsat;            // [Wn] OR-accumulated syndrome words
+};
+
+// All launchers enqueue on `stream` and return the CUDA launch status.
+cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream);
+cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream);
+cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream);
+// frames with done == 0 whose syndrome word bit is clear become done with iterations = t1;
+// also clears `unsat_next`.  V = frames per lane of the decoder's dtype.
+cudaError_t launch_commit(int V, const uint32_t* unsat, uint32_t* unsat_next, uint8_t* done,
+                          int32_t* iters, uint8_t* success, int32_t t1, int64_t Bp, cudaStream_t stream);
+// llr [B][n] row-major -> llrT [n][Bp]; also resets done / iters / success for a new decode.
+cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64_t Bp, int32_t n,
+                        uint8_t* done, int32_t* iters, uint8_t* success, int32_t T, cudaStream_t stream);
+cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, uint32_t* unsat2,
+                               int64_t B, int64_t Bp, int32_t T, cudaStream_t stream);
+// hardw -> bits [B][n] uint8
+cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B,
+                               int32_t n, cudaStream_t stream);
+// postT [n][Bp] -> post [B][n]
+cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp,
+                               int32_t n, cudaStream_t stream);
+cudaError_t launch_copy_frames(const int32_t* iters_src, const uint8_t* succ_src, int32_t* iters_dst,
+                               uint8_t* succ_dst, int64_t B, cudaStream_t stream);
+// AWGN LLRs.  row_major != 0: out is float [B][n]; else out is Real [n][Bp] of `dtype`.
+cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t B, int64_t Bp,
+                        uint64_t frame0, uint64_t seed, float snr_db, int32_t llr_sign,
+                        const uint8_t* codeword, cudaStream_t stream);
+// counters += {frame_errors, bit_errors, total_iterations, total_frames}
+cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B,
+                                const uint8_t* codeword, const int32_t* iters, int64_t* counters,
+                                int32_t* frame_bit_errors, int32_t* frame_iters, cudaStream_t stream);
+cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const uint8_t* codeword,
+                              const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
+                              cudaStream_t stream);
+
+}  // namespace ldpc

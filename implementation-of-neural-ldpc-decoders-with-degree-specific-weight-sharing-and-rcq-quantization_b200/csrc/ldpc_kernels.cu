@@ -1,0 +1,818 @@
+// Hand-written sm_100a kernels of the flooding min-sum / RCQ hot path.
+//
+// Data layout: every per-edge message array is [slot][Bp] with the FRAME index
+// fastest, slots numbered check-major over degree-sorted checks.  One lane owns V consecutive frames
+// (V = 4 for float, 2 for double), so a warp moves 512 contiguous bytes per message row and the
+// graph indices / weights are warp-uniform broadcast loads.  The work is gather / min / add on
+// streaming data: HBM-bound, no tensor cores (it is not a contraction).
+//
+//   cn_kernel   check-node half iteration      reads v2c [E][Bp]     writes c2v [E][Bp] (float or code)
+//   vn_kernel   variable-node half iteration   reads c2v, llrT       writes v2c, packed hard decisions
+//   syn_kernel  parity checks on the bit-packed hard decisions (32 frames per word)
+//   commit      per-frame early stop bookkeeping
+//   pack/unpack row-major user buffers <-> interleaved layout, Philox AWGN, error counting
+#include "ldpc_device.cuh"
+#include "ldpc_internal.h"
+
+namespace ldpc {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int V>
+__device__ __forceinline__ uint32_t load_done_mask(const uint8_t* __restrict__ done, int64_t f0) {
+    uint32_t m = 0;
+    if constexpr (V == 4) {
+        uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(done + f0));
+#pragma unroll
+        for (int v = 0; v < 4; ++v) m |= ((w >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
+    } else {
+        uint16_t w = __ldg(reinterpret_cast<const uint16_t*>(done + f0));
+#pragma unroll
+        for (int v = 0; v < 2; ++v) m |= ((w >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
+    }
+    return m;
+}
+
+// Store V frames of one row; frames whose done bit is set keep their old (frozen) value.
+template <typename T, int V>
+__device__ __forceinline__ void store_masked(T* __restrict__ rowptr, const Pack<T, V>& val, uint32_t dmask) {
+    if (dmask == 0) {
+        st_stream<Pack<T, V>>(rowptr, val);
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (!((dmask >> v) & 1u)) rowptr[v] = val.v[v];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Check node (ldpc_decoder.py:91-120; neural_2d_decoder.py:161-191; rcq_decoder.py:211-246, :526-563)
+//
+// Per frame: m1 = min |x|, k0 = its first index, m2 = min over the others; for edge k
+//   raw = (k == k0) ? m2 : m1,   c2v = fl(beta_k * raw) with the sign of prod_{k' != k} sign(x_k').
+// The product of the other signs is applied as an XOR of IEEE sign bits: whenever an input is +-0 the
+// magnitudes force every affected output to +-0 (appendix A2), so three-valued sign() never shows.
+// The same expression covers (beta*raw)*sp [N-MS] and (beta*sp)*raw [W-RCQ]: sp = +-1 is exact.
+// ---------------------------------------------------------------------------------------------
+template <typename Real, bool QUANT>
+struct CnOut { using type = Real; };
+template <typename Real>
+struct CnOut<Real, true> { using type = uint8_t; };
+
+template <typename Real, int V>
+struct MinState {
+    Real m1, m2;
+    int k0;
+    uint32_t par;
+    __device__ __forceinline__ void init() {
+        m1 = Arith<Real>::inf();
+        m2 = Arith<Real>::inf();
+        k0 = 0;
+        par = 0;
+    }
+    __device__ __forceinline__ void push(Real x, int k) {
+        Real a = Arith<Real>::abs(x);
+        m2 = Arith<Real>::fmin_(m2, Arith<Real>::fmax_(m1, a));
+        if (a < m1) k0 = k;  // strict: first index wins ties
+        m1 = Arith<Real>::fmin_(m1, a);
+        par ^= Arith<Real>::hi(x);
+    }
+};
+
+template <typename Real, bool QUANT>
+__device__ __forceinline__ typename CnOut<Real, QUANT>::type cn_emit(Real raw, Real beta, bool has_beta,
+                                                                      uint32_t signbits, const float* s_thr,
+                                                                      int nth, int bc, bool mono) {
+    Real val = has_beta ? Arith<Real>::mul(beta, raw) : raw;
+    val = Arith<Real>::flip(val, signbits);
+    if constexpr (QUANT) {
+        float x = (float)val;
+        int idx = quant_index(fabsf(x), s_thr, nth, mono);
+        int code = ((x < 0.f) ? (1 << (bc - 1)) : 0) | idx;
+        return (uint8_t)code;
+    } else {
+        return val;
+    }
+}
+
+template <typename Real, bool QUANT, int DC>
+__device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask,
+                                               const float* s_thr) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using OutT = typename CnOut<Real, QUANT>::type;
+    const Real* __restrict__ src = static_cast<const Real*>(p.src);
+    OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
+    Pack<Real, V> x[DC];
+    Real beta[DC];
+    const bool has_beta = p.beta_t != nullptr;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+        beta[k] = Real(1);
+        if (has_beta) {
+            int col = p.bidx ? __ldg(p.bidx + slot0 + k) : 0;
+            beta[k] = __ldg(static_cast<const Real*>(p.beta_t) + col);
+        }
+    }
+    Pack<OutT, V> out[DC];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        MinState<Real, V> st;
+        st.init();
+#pragma unroll
+        for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
+        if (DC == 1) st.m2 = st.m1;  // ldpc_decoder.py:112-113
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            Real raw = (k == st.k0) ? st.m2 : st.m1;
+            out[k].v[v] = cn_emit<Real, QUANT>(raw, beta[k], has_beta, st.par ^ Arith<Real>::hi(x[k].v[v]),
+                                               s_thr, p.nth, p.bc, p.mono != 0);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+}
+
+template <typename Real, bool QUANT>
+__device__ void cn_check_generic(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
+                                 const float* s_thr) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using OutT = typename CnOut<Real, QUANT>::type;
+    const Real* __restrict__ src = static_cast<const Real*>(p.src);
+    OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
+    const bool has_beta = p.beta_t != nullptr;
+    MinState<Real, V> st[V];
+    uint64_t neg[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        st[v].init();
+        neg[v] = 0;
+    }
+    const bool use_mask = dc <= 64;
+#pragma unroll 4
+    for (int k = 0; k < dc; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        Pack<Real, V> x = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            st[v].push(x.v[v], k);
+            neg[v] |= (uint64_t)(Arith<Real>::hi(x.v[v]) >> 31) << (k & 63);
+        }
+    }
+    if (dc == 1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].m2 = st[v].m1;
+    }
+#pragma unroll 2
+    for (int k = 0; k < dc; ++k) {
+        Real beta = Real(1);
+        if (has_beta) {
+            int col = p.bidx ? __ldg(p.bidx + slot0 + k) : 0;
+            beta = __ldg(static_cast<const Real*>(p.beta_t) + col);
+        }
+        Pack<Real, V> x;
+        if (!use_mask) {
+            int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+            x = *reinterpret_cast<const Pack<Real, V>*>(src + row * p.Bp + f0);
+        }
+        Pack<OutT, V> out;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            uint32_t sb = use_mask ? ((uint32_t)((neg[v] >> (k & 63)) & 1ull) << 31) : Arith<Real>::hi(x.v[v]);
+            Real raw = (k == st[v].k0) ? st[v].m2 : st[v].m1;
+            out.v[v] = cn_emit<Real, QUANT>(raw, beta, has_beta, st[v].par ^ sb, s_thr, p.nth, p.bc, p.mono != 0);
+        }
+        store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+    }
+}
+
+template <typename Real, bool QUANT>
+__global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const int nfb) {
+    constexpr int V = FramesPerLane<Real>::value;
+    __shared__ float s_thr[kMaxQuantLevels];
+    if (QUANT) {
+        for (int i = threadIdx.x; i < p.nth; i += blockDim.x) s_thr[i] = p.thr[i];
+        __syncthreads();
+    }
+    const int fb = blockIdx.x % nfb;
+    const int item_id = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= p.Bp) return;  // whole warps: Bp is a multiple of 32*V
+    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    const WorkItem it = p.items[item_id];
+    int64_t slot = it.first_slot;
+#define LDPC_CN_CASE(D)                                                                   \
+    case D:                                                                               \
+        for (int c = 0; c < it.count; ++c, slot += D)                                     \
+            cn_check_small<Real, QUANT, D>(p, slot, f0, dmask, s_thr);                    \
+        break;
+    switch (it.deg) {
+        LDPC_CN_CASE(1)
+        LDPC_CN_CASE(2)
+        LDPC_CN_CASE(3)
+        LDPC_CN_CASE(4)
+        LDPC_CN_CASE(5)
+        LDPC_CN_CASE(6)
+        LDPC_CN_CASE(7)
+        LDPC_CN_CASE(8)
+        default:
+            for (int c = 0; c < it.count; ++c, slot += it.deg)
+                cn_check_generic<Real, QUANT>(p, slot, it.deg, f0, dmask, s_thr);
+    }
+#undef LDPC_CN_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable node + posterior + hard decision (ldpc_decoder.py:123-140; neural_2d_decoder.py:194-212)
+//   v2c_d = fl(llr + fl(alpha * S(c2v of the other checks, ascending check index)))
+//   post  = fl(llr + S(all c2v))        -- never alpha-weighted
+//   bit   = post < 0, ballot-packed: one 32-bit word holds the same variable of 32 frames.
+// ---------------------------------------------------------------------------------------------
+template <typename Real, bool QUANT>
+__device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t idx, const float* s_lut,
+                                          int lutbase) {
+    if constexpr (QUANT) {
+        return (Real)s_lut[lutbase + static_cast<const uint8_t*>(c2v)[idx]];
+    } else {
+        return static_cast<const Real*>(c2v)[idx];
+    }
+}
+
+template <typename Real, int V>
+__device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t Wn, int64_t j, int64_t wbase,
+                                           const bool (&bit)[V]) {
+    uint32_t words[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) words[v] = __ballot_sync(0xffffffffu, bit[v]);
+    const int lane = threadIdx.x & 31;
+    if (lane < V) {
+        uint32_t w = words[0];
+#pragma unroll
+        for (int v = 1; v < V; ++v)
+            if (lane == v) w = words[v];
+        hardw[j * Wn + wbase + lane] = w;
+    }
+}
+
+template <typename Real, bool QUANT, bool FINAL, int DV>
+__device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, int64_t lbase, int64_t f0,
+                                              uint32_t dmask, int64_t wbase, const float* s_lut,
+                                              const int (&lutbase)[FramesPerLane<Real>::value]) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using InT = typename CnOut<Real, QUANT>::type;
+    const InT* __restrict__ c2v = static_cast<const InT*>(p.c2v);
+    Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
+    const int64_t j = __ldg(p.vpos_var + vpos);
+    int64_t slot[DV > 0 ? DV : 1];
+    Pack<InT, V> cin[DV > 0 ? DV : 1];
+#pragma unroll
+    for (int d = 0; d < DV; ++d) slot[d] = __ldg(p.vslots + lbase + d);
+#pragma unroll
+    for (int d = 0; d < DV; ++d) cin[d] = ld_stream<Pack<InT, V>>(c2v + slot[d] * p.Bp + f0);
+    const Pack<Real, V> L = ld_stream<Pack<Real, V>>(static_cast<const Real*>(p.llrT) + j * p.Bp + f0);
+    const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
+    Real alpha = Real(1);
+    if (has_alpha) {
+        int col = p.aidx ? __ldg(p.aidx + vpos) : 0;
+        alpha = __ldg(static_cast<const Real*>(p.alpha_t) + col);
+    }
+    Pack<Real, V> out[DV > 0 ? DV : 1];
+    Pack<Real, V> post;
+    bool bit[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        Real c[DV > 0 ? DV : 1];
+#pragma unroll
+        for (int d = 0; d < DV; ++d) {
+            if constexpr (QUANT) c[d] = (Real)s_lut[lutbase[v] + cin[d].v[v]];
+            else c[d] = cin[d].v[v];
+        }
+        if constexpr (!FINAL) {
+#pragma unroll
+            for (int d = 0; d < DV; ++d) {
+                Real s = LibSum<Real>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[i < d ? i : i + 1]; });
+                if (has_alpha) s = Arith<Real>::mul(alpha, s);
+                out[d].v[v] = Arith<Real>::add(L.v[v], s);
+            }
+        }
+        Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
+        Real pv = (DV > 0) ? Arith<Real>::add(L.v[v], tot) : L.v[v];
+        post.v[v] = pv;
+        bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
+    }
+    if constexpr (!FINAL) {
+#pragma unroll
+        for (int d = 0; d < DV; ++d) store_masked<Real, V>(v2c + slot[d] * p.Bp + f0, out[d], dmask);
+    } else {
+        if (p.postT) st_stream<Pack<Real, V>>(static_cast<Real*>(p.postT) + j * p.Bp + f0, post);
+    }
+    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit);
+}
+
+template <typename Real, bool QUANT, bool FINAL>
+__device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, int dv, int64_t f0, uint32_t dmask,
+                                int64_t wbase, const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
+    constexpr int V = FramesPerLane<Real>::value;
+    Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
+    const int64_t j = __ldg(p.vpos_var + vpos);
+    const Pack<Real, V> L = *reinterpret_cast<const Pack<Real, V>*>(static_cast<const Real*>(p.llrT) + j * p.Bp + f0);
+    const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
+    Real alpha = Real(1);
+    if (has_alpha) {
+        int col = p.aidx ? __ldg(p.aidx + vpos) : 0;
+        alpha = __ldg(static_cast<const Real*>(p.alpha_t) + col);
+    }
+    bool bit[V];
+    Pack<Real, V> post;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        auto elem = [&](int i) -> Real {
+            int64_t s = __ldg(p.vslots + lbase + i);
+            return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v]);
+        };
+        Real tot = LibSum<Real>::dyn(elem, dv);
+        Real pv = dv > 0 ? Arith<Real>::add(L.v[v], tot) : L.v[v];
+        post.v[v] = pv;
+        bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
+    }
+    if constexpr (!FINAL) {
+        // all sums are formed from c2v before any v2c of this variable is written (separate arrays)
+        for (int d = 0; d < dv; ++d) {
+            Pack<Real, V> out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                auto others = [&](int i) -> Real {
+                    int64_t s = __ldg(p.vslots + lbase + (i < d ? i : i + 1));
+                    return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v]);
+                };
+                Real s = LibSum<Real>::dyn(others, dv - 1);
+                if (has_alpha) s = Arith<Real>::mul(alpha, s);
+                out.v[v] = Arith<Real>::add(L.v[v], s);
+            }
+            int64_t sd = __ldg(p.vslots + lbase + d);
+            store_masked<Real, V>(v2c + sd * p.Bp + f0, out, dmask);
+        }
+    } else {
+        if (p.postT) *reinterpret_cast<Pack<Real, V>*>(static_cast<Real*>(p.postT) + j * p.Bp + f0) = post;
+    }
+    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit);
+}
+
+template <typename Real, bool QUANT, bool FINAL>
+__global__ void __launch_bounds__(kThreads) vn_kernel(const VnLaunch p, const int nfb) {
+    constexpr int V = FramesPerLane<Real>::value;
+    extern __shared__ float s_lut[];
+    if (QUANT) {
+        const int nl = p.n_quant << p.bc;
+        for (int i = threadIdx.x; i < nl; i += blockDim.x) s_lut[i] = p.lut[i];
+        __syncthreads();
+    }
+    const int fb = blockIdx.x % nfb;
+    const int item_id = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= p.Bp) return;
+    uint32_t dmask = 0;
+    if (!FINAL) {
+        dmask = load_done_mask<V>(p.done, f0);
+        if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    }
+    int lutbase[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        lutbase[v] = 0;
+        if (QUANT) {
+            int q = p.q_now;
+            if (FINAL) {
+                int itv = __ldg(p.iters + f0 + v);
+                q = __ldg(p.q_of_iter + (itv > 0 ? itv - 1 : 0));
+            }
+            lutbase[v] = q << p.bc;
+        }
+    }
+    const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
+    const int64_t wbase = (warp_f0 / (32 * V)) * V;
+    const WorkItem it = p.items[item_id];
+    int64_t lbase = it.first_slot;
+    int32_t vpos = it.first_node;
+#define LDPC_VN_CASE(D)                                                                               \
+    case D:                                                                                           \
+        for (int c = 0; c < it.count; ++c, lbase += D, ++vpos)                                        \
+            vn_node_small<Real, QUANT, FINAL, D>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);   \
+        break;
+    switch (it.deg) {
+        LDPC_VN_CASE(0)
+        LDPC_VN_CASE(1)
+        LDPC_VN_CASE(2)
+        LDPC_VN_CASE(3)
+        LDPC_VN_CASE(4)
+        LDPC_VN_CASE(5)
+        LDPC_VN_CASE(6)
+        LDPC_VN_CASE(7)
+        LDPC_VN_CASE(8)
+        default:
+            for (int c = 0; c < it.count; ++c, lbase += it.deg, ++vpos)
+                vn_node_generic<Real, QUANT, FINAL>(p, vpos, lbase, it.deg, f0, dmask, wbase, s_lut, lutbase);
+    }
+#undef LDPC_VN_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Syndrome on packed hard decisions (ldpc_decoder.py:141): one thread = one 32-frame word,
+// XOR over a check's variables, OR over the item's checks, atomicOr into unsat[w].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) syn_kernel(const SynLaunch p, const int nwb) {
+    const int wb = blockIdx.x % nwb;
+    const int item_id = blockIdx.x / nwb;
+    const int64_t w = (int64_t)wb * blockDim.x + threadIdx.x;
+    if (w >= p.Wn) return;
+    const WorkItem it = p.items[item_id];
+    int64_t slot = it.first_slot;
+    uint32_t acc = 0;
+    for (int c = 0; c < it.count; ++c, slot += it.deg) {
+        uint32_t syn = 0;
+        for (int k = 0; k < it.deg; ++k) {
+            int64_t j = __ldg(p.slot_var + slot + k);
+            syn ^= __ldg(p.hardw + j * p.Wn + w);
+        }
+        acc |= syn;
+    }
+    if (acc) atomicOr(p.unsat + w, acc);
+}
+
+__host__ __device__ __forceinline__ void frame_to_wordbit(int64_t f, int V, int64_t& w, int& bit) {
+    int64_t g = f / (32 * V);
+    int r = (int)(f % (32 * V));
+    bit = r / V;
+    w = g * V + (r % V);
+}
+__host__ __device__ __forceinline__ int64_t wordbit_to_frame(int64_t w, int bit, int V) {
+    return (w / V) * (32 * V) + (int64_t)bit * V + (w % V);
+}
+
+// ldpc_decoder.py:143-144: first iteration whose syndrome is all-zero ends the frame.
+__global__ void commit_kernel(int V, const uint32_t* __restrict__ unsat, uint32_t* __restrict__ unsat_next,
+                              uint8_t* __restrict__ done, int32_t* __restrict__ iters,
+                              uint8_t* __restrict__ success, int32_t t1, int64_t Bp) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Bp) return;
+    int64_t w;
+    int bit;
+    frame_to_wordbit(f, V, w, bit);
+    if (!done[f]) {
+        if (!((unsat[w] >> bit) & 1u)) {
+            done[f] = 1;
+            iters[f] = t1;
+            success[f] = 1;
+        }
+    }
+    if (unsat_next && bit == 0) unsat_next[w] = 0;
+}
+
+__global__ void reset_kernel(uint8_t* __restrict__ done, int32_t* __restrict__ iters, uint8_t* __restrict__ success,
+                             uint32_t* __restrict__ unsat2, int64_t B, int64_t Bp, int32_t T) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Bp) return;
+    done[f] = (f >= B) ? 1 : 0;  // pad frames never run
+    iters[f] = T;
+    success[f] = 0;
+    if (f < 2 * (Bp / 32)) unsat2[f] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout conversion: user [B][n] row-major <-> interleaved [n][Bp]
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void pack_kernel(const Real* __restrict__ llr, Real* __restrict__ llrT, int64_t B, int64_t Bp, int32_t n) {
+    __shared__ Real tile[32][33];
+    const int64_t f_base = (int64_t)blockIdx.x * 32;
+    const int32_t j_base = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t f = f_base + r;
+        int32_t j = j_base + threadIdx.x;
+        tile[r][threadIdx.x] = (f < B && j < n) ? llr[f * n + j] : Real(0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int32_t j = j_base + r;
+        int64_t f = f_base + threadIdx.x;
+        if (j < n && f < Bp) llrT[(int64_t)j * Bp + f] = tile[threadIdx.x][r];
+    }
+}
+
+template <typename Real>
+__global__ void unpack_post_kernel(const Real* __restrict__ postT, Real* __restrict__ post, int64_t B, int64_t Bp,
+                                   int32_t n) {
+    __shared__ Real tile[32][33];
+    const int64_t f_base = (int64_t)blockIdx.x * 32;
+    const int32_t j_base = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int32_t j = j_base + r;
+        int64_t f = f_base + threadIdx.x;
+        tile[r][threadIdx.x] = (j < n && f < Bp) ? postT[(int64_t)j * Bp + f] : Real(0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t f = f_base + r;
+        int32_t j = j_base + threadIdx.x;
+        if (f < B && j < n) post[f * n + j] = tile[threadIdx.x][r];
+    }
+}
+
+// One warp: one hard word (32 frames) x 32 variables per step.
+__global__ void unpack_bits_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, uint8_t* __restrict__ bits,
+                                   int64_t B, int32_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= Wn) return;
+    const int32_t j = blockIdx.x * 32 + lane;
+    const uint32_t word = (j < n) ? __ldg(hardw + (int64_t)j * Wn + w) : 0u;
+    for (int b = 0; b < 32; ++b) {
+        int64_t f = wordbit_to_frame(w, b, V);
+        if (f < B && j < n) bits[f * n + j] = (uint8_t)((word >> b) & 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AWGN channel (ldpc_decoder.py:286-302) with counter-based Philox4x32-10 noise.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
+
+template <typename Real, bool ROW_MAJOR>
+__global__ void awgn_kernel(void* __restrict__ out_, int32_t n, int64_t B, int64_t Bp, uint64_t frame0, uint64_t seed,
+                            float sigma, float inv_sigma2_x2, float llr_sign, const uint8_t* __restrict__ codeword) {
+    const int64_t f0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int32_t jg = blockIdx.y;
+    const int64_t Flim = ROW_MAJOR ? B : Bp;
+    if (f0 >= Flim) return;
+    float val[4][4];  // [variable in group][frame]
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        uint64_t gf = frame0 + (uint64_t)(f0 + v);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)jg, (uint32_t)gf, (uint32_t)(gf >> 32), 0x4c445043u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r);
+        float z[4];
+        {
+            float rad = sqrtf(-2.f * logf(u01(r[0])));
+            float s, c;
+            sincospif(2.f * u01(r[1]), &s, &c);
+            z[0] = rad * c;
+            z[1] = rad * s;
+            rad = sqrtf(-2.f * logf(u01(r[2])));
+            sincospif(2.f * u01(r[3]), &s, &c);
+            z[2] = rad * c;
+            z[3] = rad * s;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int32_t j = 4 * jg + i;
+            float cw = (codeword && j < n) ? (float)codeword[j] : 0.f;
+            float sym = llr_sign * (1.f - 2.f * cw);  // ldpc_decoder.py:289 with the chosen convention
+            float y = __fadd_rn(sym, __fmul_rn(sigma, z[i]));
+            val[i][v] = __fmul_rn(y, inv_sigma2_x2);
+            if (!ROW_MAJOR && (f0 + v) >= B) val[i][v] = 0.f;  // pad frames
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int32_t j = 4 * jg + i;
+        if (j >= n) break;
+        if (ROW_MAJOR) {
+            float* out = static_cast<float*>(out_);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                if (f0 + v < B) out[(f0 + v) * n + j] = val[i][v];
+        } else {
+            Real* out = static_cast<Real*>(out_) + (int64_t)j * Bp + f0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) out[v] = (Real)val[i][v];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Error counting (simulation_framework.py:125-131)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void accumulate_counters(int64_t* counters, int ferr, int berr, int iters, int valid) {
+    unsigned fe = __reduce_add_sync(0xffffffffu, (unsigned)ferr);
+    unsigned be = __reduce_add_sync(0xffffffffu, (unsigned)berr);
+    unsigned it = __reduce_add_sync(0xffffffffu, (unsigned)iters);
+    unsigned nf = __reduce_add_sync(0xffffffffu, (unsigned)valid);
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* c = reinterpret_cast<unsigned long long*>(counters);
+        if (fe) atomicAdd(c + 0, (unsigned long long)fe);
+        if (be) atomicAdd(c + 1, (unsigned long long)be);
+        if (it) atomicAdd(c + 2, (unsigned long long)it);
+        if (nf) atomicAdd(c + 3, (unsigned long long)nf);
+    }
+}
+
+__global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, int32_t n, int64_t B,
+                                    const uint8_t* __restrict__ codeword, const int32_t* __restrict__ iters,
+                                    int64_t* counters, int32_t* __restrict__ frame_bit_errors,
+                                    int32_t* __restrict__ frame_iters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= Wn) return;
+    int cnt = 0;
+    for (int32_t j = 0; j < n; ++j) {
+        uint32_t word = __ldg(hardw + (int64_t)j * Wn + w);
+        uint32_t bit = (word >> lane) & 1u;
+        if (codeword) bit ^= (uint32_t)__ldg(codeword + j);
+        cnt += (int)bit;
+    }
+    const int64_t f = wordbit_to_frame(w, lane, V);
+    const int valid = f < B;
+    const int it = valid ? iters[f] : 0;
+    if (valid) {
+        if (frame_bit_errors) frame_bit_errors[f] = cnt;
+        if (frame_iters) frame_iters[f] = it;
+    }
+    accumulate_counters(counters, valid && cnt > 0, valid ? cnt : 0, it, valid);
+}
+
+__global__ void count_bits_kernel(const uint8_t* __restrict__ bits, int32_t n, int64_t B,
+                                  const uint8_t* __restrict__ codeword, const int32_t* __restrict__ iters,
+                                  int64_t* counters, int32_t* __restrict__ frame_bit_errors) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= B) return;
+    int cnt = 0;
+    for (int32_t j = lane; j < n; j += 32) {
+        uint8_t b = bits[f * n + j];
+        uint8_t c = codeword ? codeword[j] : 0;
+        cnt += (b != c);
+    }
+    cnt = (int)__reduce_add_sync(0xffffffffu, (unsigned)cnt);
+    if (lane == 0) {
+        if (frame_bit_errors) frame_bit_errors[f] = cnt;
+        unsigned long long* c = reinterpret_cast<unsigned long long*>(counters);
+        if (cnt) {
+            atomicAdd(c + 0, 1ull);
+            atomicAdd(c + 1, (unsigned long long)cnt);
+        }
+        if (iters) atomicAdd(c + 2, (unsigned long long)iters[f]);
+        atomicAdd(c + 3, 1ull);
+    }
+}
+
+inline int threads_for(int64_t Bp, int V) {
+    int64_t lanes = Bp / V;
+    int t = (int)(lanes < kThreads ? lanes : kThreads);
+    t = (t + 31) / 32 * 32;
+    return t < 32 ? 32 : t;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
+    if (p.n_items == 0) return cudaSuccess;
+    const int V = dtype == 0 ? 4 : 2;
+    const int threads = threads_for(p.Bp, V);
+    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+    const int64_t grid = nfb * p.n_items;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (dtype == 0) {
+        if (p.nth > 0) cn_kernel<float, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        else cn_kernel<float, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    } else {
+        cn_kernel<double, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream) {
+    if (p.n_items == 0) return cudaSuccess;
+    const int V = dtype == 0 ? 4 : 2;
+    const int threads = threads_for(p.Bp, V);
+    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+    const int64_t grid = nfb * p.n_items;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
+    const unsigned g = (unsigned)grid;
+    const int nf = (int)nfb;
+    if (dtype == 0) {
+        if (p.bc) {
+            if (p.final_pass) vn_kernel<float, true, true><<<g, threads, smem, stream>>>(p, nf);
+            else vn_kernel<float, true, false><<<g, threads, smem, stream>>>(p, nf);
+        } else {
+            if (p.final_pass) vn_kernel<float, false, true><<<g, threads, smem, stream>>>(p, nf);
+            else vn_kernel<float, false, false><<<g, threads, smem, stream>>>(p, nf);
+        }
+    } else {
+        if (p.final_pass) vn_kernel<double, false, true><<<g, threads, smem, stream>>>(p, nf);
+        else vn_kernel<double, false, false><<<g, threads, smem, stream>>>(p, nf);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream) {
+    if (p.n_items == 0) return cudaSuccess;
+    const int threads = 128;
+    const int64_t nwb = (p.Wn + threads - 1) / threads;
+    const int64_t grid = nwb * p.n_items;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    syn_kernel<<<(unsigned)grid, threads, 0, stream>>>(p, (int)nwb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_commit(int V, const uint32_t* unsat, uint32_t* unsat_next, uint8_t* done, int32_t* iters,
+                          uint8_t* success, int32_t t1, int64_t Bp, cudaStream_t stream) {
+    const int threads = 256;
+    commit_kernel<<<(unsigned)((Bp + threads - 1) / threads), threads, 0, stream>>>(V, unsat, unsat_next, done, iters,
+                                                                                      success, t1, Bp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, uint32_t* unsat2, int64_t B,
+                               int64_t Bp, int32_t T, cudaStream_t stream) {
+    const int threads = 256;
+    reset_kernel<<<(unsigned)((Bp + threads - 1) / threads), threads, 0, stream>>>(done, iters, success, unsat2, B, Bp, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64_t Bp, int32_t n, uint8_t* done,
+                        int32_t* iters, uint8_t* success, int32_t T, cudaStream_t stream) {
+    (void)done; (void)iters; (void)success; (void)T;
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((Bp + 31) / 32), (unsigned)((n + 31) / 32));
+    if (dtype == 0) pack_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(llr), static_cast<float*>(llrT), B, Bp, n);
+    else pack_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(llr), static_cast<double*>(llrT), B, Bp, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B, int32_t n,
+                               cudaStream_t stream) {
+    const int warps = 8;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((Wn + warps - 1) / warps));
+    unpack_bits_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, bits, B, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp, int32_t n,
+                               cudaStream_t stream) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((B + 31) / 32), (unsigned)((n + 31) / 32));
+    if (dtype == 0) unpack_post_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n);
+    else unpack_post_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t B, int64_t Bp, uint64_t frame0,
+                        uint64_t seed, float snr_db, int32_t llr_sign, const uint8_t* codeword, cudaStream_t stream) {
+    // ldpc_decoder.py:292-300: noise_power = 1 / 10^(snr/10); llr = 2 * received / noise_power
+    const double sigma2 = 1.0 / pow(10.0, (double)snr_db / 10.0);
+    const float sigma = (float)sqrt(sigma2);
+    const float k = (float)(2.0 / sigma2);
+    const float sgn = llr_sign >= 0 ? 1.f : -1.f;
+    const int64_t F = row_major ? B : Bp;
+    const int threads = 128;
+    dim3 grid((unsigned)((F / 4 + (F % 4 != 0) + threads - 1) / threads), (unsigned)((n + 3) / 4));
+    if (row_major) awgn_kernel<float, true><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
+    else if (dtype == 0) awgn_kernel<float, false><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
+    else awgn_kernel<double, false><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B, const uint8_t* codeword,
+                                const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
+                                int32_t* frame_iters, cudaStream_t stream) {
+    const int warps = 4;
+    count_packed_kernel<<<(unsigned)((Wn + warps - 1) / warps), warps * 32, 0, stream>>>(
+        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const uint8_t* codeword, const int32_t* iters,
+                              int64_t* counters, int32_t* frame_bit_errors, cudaStream_t stream) {
+    const int warps = 8;
+    count_bits_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, stream>>>(bits, n, B, codeword, iters,
+                                                                                       counters, frame_bit_errors);
+    return cudaGetLastError();
+}
+
+}  // namespace ldpc

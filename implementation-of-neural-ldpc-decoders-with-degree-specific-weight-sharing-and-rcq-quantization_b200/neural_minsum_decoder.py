@@ -1,0 +1,77 @@
+"""Neural min-sum decoder with one weight per (iteration, edge) -- B200-native counterpart of the
+reference's ``neural_minsum_decoder.py:19-150``.
+
+``beta_weights`` exposes the dense ``[T, E]`` table under the reference keys ``iter_{t}_c{i}_v{j}``
+(initialised ``0.7 + 0.1 * randn`` in the reference's creation order, neural_minsum_decoder.py:47-53)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._neural_base import DecoderModule, WeightView, seeded_normal
+from .ldpc_decoder import LDPCCode
+
+
+class NeuralMinSumDecoder(DecoderModule):
+    def __init__(self, code: LDPCCode, max_iterations: int = 50):
+        super().__init__()
+        self._init_base(code, max_iterations)
+        g = code.graph
+        T, E = max_iterations, g.E
+        self._beta_table = nn.Parameter(seeded_normal(T * E, 0.1, 0.7).reshape(T, E).clone())
+        self._alpha_table = None
+        self._beta_index = np.arange(E, dtype=np.int32)   # check-major edge order == creation order
+        self._alpha_index = None
+        self._beta_const = None
+        self._edge_check = g.edge_check
+        self._edge_var = g.check_var
+        self.beta_weights = _EdgeKeyView(self._beta_table, T, g)
+
+    def forward(self, llr: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        return self._forward_impl(llr)
+
+
+class _EdgeKeyView(WeightView):
+    """Key view for T*E per-edge weights without materialising T*E strings up front."""
+
+    def __init__(self, table, T, graph):
+        self._table = table
+        self._T = T
+        self._g = graph
+        self._edge = None
+
+    def _edges(self):
+        if self._edge is None:
+            self._edge = {(int(i), int(j)): e for e, (i, j) in enumerate(zip(self._g.edge_check, self._g.check_var))}
+        return self._edge
+
+    def _parse(self, key: str):
+        try:
+            it, c, v = key.split("_")[1:]
+            return int(it), self._edges()[(int(c[1:]), int(v[1:]))]
+        except (ValueError, KeyError, IndexError):
+            raise KeyError(key)
+
+    def __getitem__(self, key):
+        t, e = self._parse(key)
+        if not 0 <= t < self._T:
+            raise KeyError(key)
+        return self._table[t, e:e + 1]
+
+    def __iter__(self):
+        for t in range(self._T):
+            for i, j in zip(self._g.edge_check, self._g.check_var):
+                yield f"iter_{t}_c{int(i)}_v{int(j)}"
+
+    def __len__(self):
+        return self._T * self._g.E
+
+    def __contains__(self, key):
+        try:
+            t, _ = self._parse(key)
+            return 0 <= t < self._T
+        except KeyError:
+            return False

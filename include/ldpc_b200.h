@@ -1,0 +1,186 @@
+/*
+ * ldpc_b200.h -- C ABI of the B200-native batched LDPC flooding min-sum / RCQ decoding engine.
+ *
+ * The reference (Lalwaniamisha789/Implementation-of-Neural-LDPC-Decoders-...) is pure Python and
+ * has NO FFI / plugin boundary of its own: its boundary is the Python
+ * constructor + decode()/forward() surface of five classes.  This header is therefore the boundary
+ * a maintainer would bind *underneath* those classes (ctypes stub in INTEGRATION.md).  Each entry
+ * point names the reference code it replaces (file:line, relative to the reference root).
+ *
+ * Conventions: plain C types only (no torch / CUDA types in signatures; a CUDA stream travels as
+ * void*), every function returns 0 on success or an LDPC_ERR_* code and never throws;
+ * ldpc_last_error() returns a thread-local description of the last failure.  All buffers are
+ * caller-allocated.  Handles are independent objects with no shared mutable state, so different
+ * handles may be driven from different host threads concurrently (the reference runs one decoder
+ * object per thread, simulation_framework.py:192-198).  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with LDPC_ERR_CUDA.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_VERSION 100
+
+enum {
+    LDPC_OK = 0,
+    LDPC_ERR_INVALID = 1,     /* bad argument                                  */
+    LDPC_ERR_CUDA = 2,        /* CUDA runtime failure (incl. no device)        */
+    LDPC_ERR_NOMEM = 3,       /* host or device allocation failed              */
+    LDPC_ERR_UNSUPPORTED = 4  /* valid request this build does not implement   */
+};
+
+enum { LDPC_F32 = 0, LDPC_F64 = 1 };
+
+typedef struct ldpc_graph ldpc_graph;     /* Tanner graph re-laid-out on one device           */
+typedef struct ldpc_decoder ldpc_decoder; /* graph + weights + quantisers + device workspace  */
+
+int ldpc_version(void);
+const char *ldpc_last_error(void);
+int ldpc_device_count(int *count);
+
+/* Pinned host memory for the host-buffer entry points (full PCIe rate needs page-locked memory). */
+int ldpc_host_alloc(void **ptr, int64_t bytes);
+int ldpc_host_free(void *ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph.  Replaces LDPCCode's dense H and the repeated np.where / torch.where neighbour scans
+ * (ldpc_decoder.py:26-54, :85, :92, :124, :136; neural_2d_decoder.py:155, :162, :195).
+ *   check_ptr[m+1], check_var[E]: CSR by check; inside a check the variables MUST be in ascending
+ *   index order (that is the order np.where yields and the order the min-sum argmin tie-break and
+ *   all sums follow).  Only H == 1 entries are edges.  Checks/variables of degree 0 are allowed.
+ * The library derives the variable-side adjacency (ascending check index), the degree classes and
+ * the degree-sorted slot layout itself and uploads them to `device`.
+ * ------------------------------------------------------------------------------------------- */
+int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t *check_ptr,
+                      const int32_t *check_var, ldpc_graph **out);
+int ldpc_graph_destroy(ldpc_graph *g);
+
+enum {
+    LDPC_GRAPH_N = 0,
+    LDPC_GRAPH_M = 1,
+    LDPC_GRAPH_E = 2,
+    LDPC_GRAPH_CHECK_CLASSES = 3, /* number of distinct non-zero check degrees     */
+    LDPC_GRAPH_VAR_CLASSES = 4,   /* number of distinct variable degrees (incl. 0) */
+    LDPC_GRAPH_MAX_DC = 5,
+    LDPC_GRAPH_MAX_DV = 6,
+    LDPC_GRAPH_DEVICE = 7
+};
+int ldpc_graph_query(const ldpc_graph *g, int what, int64_t *value);
+/* Test hook: message-slot id of every edge (check-major edge order in, slot out). */
+int ldpc_graph_slot_of_edge(const ldpc_graph *g, int32_t *slot_of_edge /* [E] */);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decoder.  One configuration struct covers the five reference decoders:
+ *
+ *   BasicMinSumDecoder        (ldpc_decoder.py:56-153)        dtype F64, beta = {factor}, T = code.max_iterations
+ *   NeuralMinSumDecoder       (neural_minsum_decoder.py:19-150) beta[T][E], beta_index[e] = e
+ *   Neural2DMinSumDecoder     (neural_2d_decoder.py:16-225)    types 1-4 through beta_index / alpha_index
+ *   RCQMinSumDecoder flooding (rcq_decoder.py:123-279)         bc > 0, no beta / alpha
+ *   WeightedRCQDecoder        (rcq_decoder.py:352-597)         bc > 0 plus beta / alpha
+ *
+ * Arithmetic (verified against the reference):
+ *   check node   raw_k = min2 if k == first-argmin else min1;  c2v = fl(fl(beta*raw) * sp)
+ *   quantised    code = (x < 0) << (bc-1) | last j with |x| >= float(thr_j);  c2v = +-float(thr_idx)
+ *   variable     v2c = fl(llr + fl(alpha * S(others)));  posterior = fl(llr + S(all))  (no alpha)
+ *   S()          torch.sum order for F32, np.sum (pairwise) order for F64
+ *   stop         bits = posterior < 0; all parity checks zero -> iterations = t+1, success
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ldpc_decoder_config {
+    int32_t struct_size;     /* = sizeof(ldpc_decoder_config)                                    */
+    int32_t dtype;           /* LDPC_F32 | LDPC_F64 (F64 only without quantiser)                 */
+    int32_t max_iterations;  /* T >= 1                                                           */
+    int32_t early_stop;      /* 1: reference behaviour; 0: always run T iterations (benchmarks)  */
+    int32_t n_beta;          /* columns of beta; 0 -> beta == 1                                  */
+    int32_t n_alpha;         /* columns of alpha; 0 -> no alpha multiply (alpha == 1)            */
+    int32_t bc;              /* 0: float c2v; 2..8: c2v stored as bc-bit sign-magnitude codes    */
+    int32_t n_quantizers;    /* Q                                                                */
+    const int32_t *beta_index;        /* [E] column of beta per edge (check-major); NULL -> 0    */
+    const void *beta;                 /* [T][n_beta] of dtype                                    */
+    const int32_t *alpha_index;       /* [n] column of alpha per variable; NULL -> 0             */
+    const void *alpha;                /* [T][n_alpha] of dtype                                   */
+    const float *thresholds;          /* [Q][2^(bc-1)] thresholds rounded to float32             */
+    const int32_t *quantizer_of_iter; /* [T] quantiser used by iteration t (rcq_decoder.py:156-167) */
+} ldpc_decoder_config;
+
+int ldpc_decoder_create(ldpc_graph *g, const ldpc_decoder_config *cfg, ldpc_decoder **out);
+/* Replace the weight tables (same shapes as at creation); host pointers. */
+int ldpc_decoder_set_weights(ldpc_decoder *d, const void *beta, const void *alpha);
+int ldpc_decoder_destroy(ldpc_decoder *d);
+/* Pre-size the device workspace for batches of up to `frames` frames (otherwise grown on demand). */
+int ldpc_decoder_reserve(ldpc_decoder *d, int64_t frames);
+
+/*
+ * Decode B frames.  Replaces decode()/forward() of the classes above, batched:
+ *   llr      [B][n] of dtype, row-major (one reference call per row)
+ *   bits     [B][n] uint8   hard decisions (posterior < 0)
+ *   posterior[B][n] of dtype, may be NULL  (forward() returns it, decode() does not)
+ *   iterations[B] int32, success[B] uint8 (either may be NULL)
+ * _device: all pointers are device pointers on the graph's device; work is enqueued on `stream`
+ *          (a cudaStream_t, NULL = default stream) and NOT synchronised.
+ * _host:   all pointers are host pointers (pinned for full speed); the call copies in, decodes and
+ *          copies out through an internal chunked double-buffered pipeline and returns when the
+ *          outputs are valid.
+ */
+int ldpc_decode_device(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bits, void *posterior,
+                       int32_t *iterations, uint8_t *success, void *stream);
+int ldpc_decode_host(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bits, void *posterior,
+                     int32_t *iterations, uint8_t *success);
+
+/* ---------------------------------------------------------------------------------------------
+ * Monte-Carlo leg.  Replaces simulate_awgn_channel (ldpc_decoder.py:286-302) and the per-frame
+ * body of LDPSimulator.simulate_single_snr (simulation_framework.py:110-131).
+ *
+ * Noise: z(frame, variable) is a pure function of (seed, global frame index, variable index):
+ * Philox4x32-10, key = seed, counter = (variable/4, frame_lo, frame_hi, 0x4c445043), Box-Muller on
+ * the four outputs.  y = s + sigma*z, sigma^2 = 10^(-snr_db/10), llr = 2*y/sigma^2 in float32
+ * (then widened for F64 decoders).  s = +1 for codeword bit 0 when llr_sign = +1 (decisions then
+ * converge to the all-zero word) and -1 when llr_sign = -1 (the reference's own convention,
+ * ldpc_decoder.py:289 -- see SURVEY appendix C1).
+ * ------------------------------------------------------------------------------------------- */
+/* llr_out: device [B][n] float32 row-major.  codeword: device uint8 [n] or NULL (all-zero). */
+int ldpc_awgn_llr(int device, int32_t n, int64_t B, uint64_t frame0, uint64_t seed, float snr_db,
+                  int32_t llr_sign, const uint8_t *codeword, float *llr_out, void *stream);
+
+/*
+ * One Monte-Carlo round on frames [frame0, frame0+B): generate LLRs straight into the decoder's
+ * interleaved layout, decode, compare with `codeword` (device uint8[n] or NULL = all-zero) and
+ * ACCUMULATE into counters (device int64[4]):
+ *   {frame_errors, bit_errors (of erroneous frames), total_iterations, total_frames}
+ * i.e. the four sums of simulation_framework.py:125-131.  Optional per-frame outputs (device,
+ * may be NULL): frame_bit_errors[B] int32, frame_iterations[B] int32 -- used for the exact
+ * sequential max_errors stop rule.  Enqueued on `stream`, not synchronised.
+ */
+int ldpc_mc_round(ldpc_decoder *d, float snr_db, int32_t llr_sign, uint64_t seed, uint64_t frame0,
+                  int64_t B, const uint8_t *codeword, int64_t *counters, int32_t *frame_bit_errors,
+                  int32_t *frame_iterations, void *stream);
+
+/* Stand-alone error counting on decoded bits (device uint8 [B][n]), same counter semantics. */
+int ldpc_count_errors(int device, int32_t n, int64_t B, const uint8_t *bits, const uint8_t *codeword,
+                      const int32_t *iterations, int64_t *counters, int32_t *frame_bit_errors,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Instrumentation (bench.py / tests).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ldpc_profile {
+    int64_t launches;         /* kernels of this library launched by the handle since reset        */
+    int64_t cn_launches;      /* check-node kernel launches                                        */
+    int64_t vn_launches;      /* variable-node kernel launches (incl. the final posterior pass)    */
+    double cn_ms;             /* device time of those launches, CUDA events (profiling mode only)  */
+    double vn_ms;
+    double other_ms;          /* pack / unpack / syndrome / commit / awgn / count                  */
+    int64_t frames_padded;    /* Bp of the last call                                               */
+} ldpc_profile;
+/* mode 0: count launches only (no overhead); mode 1: also bracket every kernel with CUDA events. */
+int ldpc_decoder_profile_mode(ldpc_decoder *d, int32_t mode);
+int ldpc_decoder_profile_read(ldpc_decoder *d, ldpc_profile *out, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */
