@@ -34,15 +34,21 @@ METRIC = "info_gbps_at_10_iters"
 UNIT = "info Gb/s"
 T_ITERS = 10
 SNR_DB = 2.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed
-# `ncu --set full` capture (profiles/); None until a capture exists for the current kernel.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per FRAME of one launch, from the committed `ncu --set full`
+# captures (profiles/r01_ncu_full_*_8192frames.csv: bytes of one launch / 8192 frames); scaled by the
+# frames of the benchmarked launch.  Only the captured (decoder, code, kernel) pairs have an entry.
+NCU_TRAFFIC_BYTES_PER_FRAME = {
+    ("n2d2", "dvbs2", "vn_kernel"): (2.123935e9 + 1.572802e9) / 8192,
+    ("n2d2", "dvbs2", "cn_kernel"): (1.592792e9 + 1.542397e9) / 8192,
+    ("rcq", "dvbs2", "vn_kernel"): (0.929394e9 + 1.550779e9) / 8192,
+    ("rcq", "dvbs2", "cn_kernel"): (1.592605e9 + 0.370780e9) / 8192,
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU per step")
@@ -328,7 +334,10 @@ def run_ours(args):
     step_bytes = T_ITERS * ab["frame_iter"] * B
     roofline = {
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": dominant, "peak_source": peak_src,
+        "traffic": (NCU_TRAFFIC_BYTES_PER_FRAME[(kind, args.code, dominant)] * Bp
+                    if (kind, args.code, dominant) in NCU_TRAFFIC_BYTES_PER_FRAME else None),
+        "traffic_source": "ncu --set full at 8192 frames per launch, scaled per frame (profiles/README.md)",
+        "kernel": dominant, "peak_source": peak_src,
         "bytes_per_launch": vn_bytes if dominant == "vn_kernel" else cn_bytes,
         "avg_launch_ms": vn_ms if dominant == "vn_kernel" else cn_ms,
         "vn_kernel": {"gbs": vn_gbs, "frac": vn_gbs / peak, "ms_total": prof["vn_ms"], "launches": prof["vn_launches"]},

@@ -333,6 +333,7 @@ struct ldpc_decoder {
     std::vector<int> mono;                 // per quantiser
     std::vector<int32_t> q_of_iter;        // host copy
     int32_t* d_bidx = nullptr;             // per slot
+    int beta_per_edge = 0;                 // some check mixes beta columns
     int32_t* d_aidx = nullptr;             // per vpos
     void* d_beta = nullptr;                // [T][n_beta]
     void* d_alpha = nullptr;               // [T][n_alpha]
@@ -434,6 +435,7 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
         cn.dst = ws.c2v;
         cn.row_map = (t == 0) ? g->d_slot_var : nullptr;
         cn.bidx = d->d_bidx;
+        cn.beta_per_edge = d->beta_per_edge;
         cn.beta_t = d->d_beta ? (const char*)d->d_beta + (size_t)t * d->n_beta * d->rsz : nullptr;
         cn.thr = d->bc ? d->d_thr + (size_t)q * d->nth : nullptr;
         cn.nth = d->nth;
@@ -568,6 +570,13 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (cfg->n_beta > 0 && cfg->beta_index) {
         std::vector<int32_t> bidx((size_t)E);
         for (int64_t e = 0; e < E; ++e) bidx[(size_t)g->slot_of_edge[(size_t)e]] = cfg->beta_index[e];
+        for (const WorkItem& it : g->cn_items)   // does any check mix columns?
+            for (int c = 0; c < it.count && !d->beta_per_edge; ++c)
+                for (int k = 1; k < it.deg; ++k)
+                    if (bidx[(size_t)it.first_slot + (size_t)c * it.deg + k] != bidx[(size_t)it.first_slot + (size_t)c * it.deg]) {
+                        d->beta_per_edge = 1;
+                        break;
+                    }
         rc = upload(&d->d_bidx, bidx);
     }
     if (!rc && cfg->n_alpha > 0 && cfg->alpha_index) {

@@ -25,6 +25,7 @@ struct CnLaunch {
     void* dst;                  // c2v: Real [E][Bp] or uint8 codes [E][Bp]
     const int32_t* row_map;     // iteration 0: variable of each slot; else nullptr
     const int32_t* bidx;        // per-slot column of beta, or nullptr (column 0)
+    int beta_per_edge;          // 0: every edge of a check uses the column of its first slot; 1: per edge
     const void* beta_t;         // beta row of this iteration, or nullptr (beta == 1)
     const float* thr;           // device thresholds of this iteration's quantiser [nth]
     int nth;                    // 2^(bc-1), 0 = float messages

@@ -61,7 +61,10 @@ struct CnOut { using type = Real; };
 template <typename Real>
 struct CnOut<Real, true> { using type = uint8_t; };
 
-template <typename Real, int V>
+// Running min1 / min2 / sign parity of one check for one frame.  TRACK_K0 also keeps the first index of
+// the minimum; it is only needed where the inputs are not kept (sign-mask path of wide checks) -- where
+// they are, "|x_k| == m1" selects the same outputs: with a tie m2 == m1, so both choices coincide.
+template <typename Real, bool TRACK_K0>
 struct MinState {
     Real m1, m2;
     int k0;
@@ -75,130 +78,266 @@ struct MinState {
     __device__ __forceinline__ void push(Real x, int k) {
         Real a = Arith<Real>::abs(x);
         m2 = Arith<Real>::fmin_(m2, Arith<Real>::fmax_(m1, a));
-        if (a < m1) k0 = k;  // strict: first index wins ties
+        if (TRACK_K0) {
+            if (a < m1) k0 = k;  // strict: first index wins ties
+        }
         m1 = Arith<Real>::fmin_(m1, a);
         par ^= Arith<Real>::hi(x);
     }
 };
 
-template <typename Real, bool QUANT>
-__device__ __forceinline__ typename CnOut<Real, QUANT>::type cn_emit(Real raw, Real beta, bool has_beta,
-                                                                      uint32_t signbits, const float* s_thr,
-                                                                      int nth, int bc, bool mono) {
-    Real val = has_beta ? Arith<Real>::mul(beta, raw) : raw;
-    val = Arith<Real>::flip(val, signbits);
+// RCQ magnitude index (rcq_decoder.py:76-84).  NTH > 0: non-decreasing thresholds held in registers,
+// index = number of thresholds j >= 1 that the magnitude reaches (== "last j reached").  NTH == 0:
+// any table, read from shared memory.
+template <int NTH>
+struct Quantizer {
+    float t[NTH > 0 ? NTH : 1];
+    const float* s_thr;
+    int nth;
+    bool mono;
+    __device__ __forceinline__ void load(const float* s_thr_, int nth_, bool mono_) {
+        s_thr = s_thr_;
+        nth = nth_;
+        mono = mono_;
+        if constexpr (NTH > 0) {
+#pragma unroll
+            for (int j = 0; j < NTH; ++j) t[j] = (j < nth_) ? s_thr_[j] : __int_as_float(0x7f800000);
+        }
+    }
+    __device__ __forceinline__ uint32_t index(float mag) const {
+        if constexpr (NTH > 0) {
+            uint32_t idx = 0;
+#pragma unroll
+            for (int j = 1; j < NTH; ++j) idx += (mag >= t[j]) ? 1u : 0u;
+            return idx;
+        } else {
+            return (uint32_t)quant_index(mag, s_thr, nth, mono);
+        }
+    }
+};
+
+// One edge whose beta is its own (type-1 weights over mixed variable degrees, per-edge N-NMS weights).
+template <typename Real, bool QUANT, int NTH>
+__device__ __forceinline__ typename CnOut<Real, QUANT>::type cn_emit(Real raw, Real beta, uint32_t signbits,
+                                                                      const Quantizer<NTH>& qz, int bc) {
+    Real val = Arith<Real>::flip(Arith<Real>::mul(beta, raw), signbits);
     if constexpr (QUANT) {
         float x = (float)val;
-        int idx = quant_index(fabsf(x), s_thr, nth, mono);
-        int code = ((x < 0.f) ? (1 << (bc - 1)) : 0) | idx;
+        uint32_t code = ((x < 0.f) ? (1u << (bc - 1)) : 0u) | qz.index(fabsf(x));
         return (uint8_t)code;
     } else {
         return val;
     }
 }
 
-template <typename Real, bool QUANT, int DC>
+// When every edge of the check shares one beta (Basic, RCQ, N-2D types 2-4, type 1 where a check sees
+// one variable degree) a check has only TWO output magnitudes per frame, A = fl(beta*m1) for the edges
+// other than the minimum and B = fl(beta*m2) for the minimum edge, so the multiply -- and for RCQ the
+// threshold search -- runs twice per check instead of once per edge.
+template <typename Real, bool QUANT>
+struct CheckOut {
+    using OutT = typename CnOut<Real, QUANT>::type;
+    Real A, B;
+    uint32_t ia, ib, ma, mb;  // RCQ: magnitude indices and sign-bit masks (0 when the value is +-0)
+    uint32_t par;             // XOR of the input sign words (RCQ: also of beta's sign)
+    int sh;
+    template <int NTH>
+    __device__ __forceinline__ void prepare(Real m1, Real m2, uint32_t par_, Real beta, bool has_beta,
+                                            const Quantizer<NTH>& qz, int bc) {
+        A = has_beta ? Arith<Real>::mul(beta, m1) : m1;
+        B = has_beta ? Arith<Real>::mul(beta, m2) : m2;
+        par = par_;
+        if constexpr (QUANT) {
+            const float a = (float)A, b = (float)B;
+            const uint32_t S = 1u << (bc - 1);
+            ia = qz.index(fabsf(a));
+            ib = qz.index(fabsf(b));
+            // code sign bit = (x < 0) needs a non-zero magnitude (rcq_decoder.py:87); A and B carry
+            // beta's sign whenever they are non-zero, and B == 0 implies A == 0
+            ma = (a != 0.f) ? S : 0u;
+            mb = (b != 0.f) ? S : 0u;
+            par = par_ ^ __float_as_uint(b);
+            sh = 32 - bc;
+        }
+    }
+    // is_min: this edge carries the check's minimum magnitude; sx: sign word of its own input
+    __device__ __forceinline__ OutT emit(bool is_min, uint32_t sx) const {
+        if constexpr (QUANT) {
+            const uint32_t idx = is_min ? ib : ia, mask = is_min ? mb : ma;
+            return (uint8_t)(idx | (((par ^ sx) >> sh) & mask));
+        } else {
+            return Arith<Real>::flip(is_min ? B : A, par ^ sx);
+        }
+    }
+};
+
+template <typename Real, bool QUANT, int NTH, int DC>
 __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask,
-                                               const float* s_thr) {
+                                               const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
     const Real* __restrict__ src = static_cast<const Real*>(p.src);
     OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
     Pack<Real, V> x[DC];
-    Real beta[DC];
     const bool has_beta = p.beta_t != nullptr;
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
         int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
         x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
     }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-        beta[k] = Real(1);
-        if (has_beta) {
-            int col = p.bidx ? __ldg(p.bidx + slot0 + k) : 0;
-            beta[k] = __ldg(static_cast<const Real*>(p.beta_t) + col);
-        }
-    }
     Pack<OutT, V> out[DC];
+    if (!p.beta_per_edge) {
+        Real beta = Real(1);
+        if (has_beta) beta = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        MinState<Real, V> st;
-        st.init();
+        for (int v = 0; v < V; ++v) {
+            MinState<Real, false> st;
+            st.init();
 #pragma unroll
-        for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
-        if (DC == 1) st.m2 = st.m1;  // ldpc_decoder.py:112-113
+            for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
+            if (DC == 1) st.m2 = st.m1;  // ldpc_decoder.py:112-113
+            CheckOut<Real, QUANT> co;
+            co.prepare(st.m1, st.m2, st.par, beta, has_beta, qz, p.bc);
 #pragma unroll
-        for (int k = 0; k < DC; ++k) {
-            Real raw = (k == st.k0) ? st.m2 : st.m1;
-            out[k].v[v] = cn_emit<Real, QUANT>(raw, beta[k], has_beta, st.par ^ Arith<Real>::hi(x[k].v[v]),
-                                               s_thr, p.nth, p.bc, p.mono != 0);
+            for (int k = 0; k < DC; ++k)
+                out[k].v[v] = co.emit(Arith<Real>::abs(x[k].v[v]) == st.m1, Arith<Real>::hi(x[k].v[v]));
+        }
+    } else {
+        Real beta[DC];
+#pragma unroll
+        for (int k = 0; k < DC; ++k) beta[k] = __ldg(static_cast<const Real*>(p.beta_t) + __ldg(p.bidx + slot0 + k));
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            MinState<Real, false> st;
+            st.init();
+#pragma unroll
+            for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
+            if (DC == 1) st.m2 = st.m1;
+#pragma unroll
+            for (int k = 0; k < DC; ++k) {
+                Real raw = (Arith<Real>::abs(x[k].v[v]) == st.m1) ? st.m2 : st.m1;
+                out[k].v[v] = cn_emit<Real, QUANT, NTH>(raw, beta[k], st.par ^ Arith<Real>::hi(x[k].v[v]), qz, p.bc);
+            }
         }
     }
 #pragma unroll
     for (int k = 0; k < DC; ++k) store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
 }
 
-template <typename Real, bool QUANT>
-__device__ void cn_check_generic(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
-                                 const float* s_thr) {
+// Checks of degree 9..32: stream the inputs once, keeping min1/min2/first-argmin/parity and one sign
+// bit per edge in a 32-bit shift register (funnel shift: one instruction per edge and frame).
+template <typename Real, bool QUANT, int NTH>
+__device__ void cn_check_mask32(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
+                                const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
     const Real* __restrict__ src = static_cast<const Real*>(p.src);
     OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
     const bool has_beta = p.beta_t != nullptr;
-    MinState<Real, V> st[V];
-    uint64_t neg[V];
+    MinState<Real, true> st[V];
+    uint32_t neg[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         st[v].init();
         neg[v] = 0;
     }
-    const bool use_mask = dc <= 64;
-#pragma unroll 4
+#pragma unroll 6
     for (int k = 0; k < dc; ++k) {
         int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
         Pack<Real, V> x = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             st[v].push(x.v[v], k);
-            neg[v] |= (uint64_t)(Arith<Real>::hi(x.v[v]) >> 31) << (k & 63);
+            neg[v] = __funnelshift_l(Arith<Real>::hi(x.v[v]), neg[v], 1);  // (neg << 1) | sign(x)
         }
     }
-    if (dc == 1) {
+    CheckOut<Real, QUANT> co[V];
+    if (!p.beta_per_edge) {
+        Real beta = Real(1);
+        if (has_beta) beta = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
 #pragma unroll
-        for (int v = 0; v < V; ++v) st[v].m2 = st[v].m1;
+        for (int v = 0; v < V; ++v) co[v].prepare(st[v].m1, st[v].m2, st[v].par, beta, has_beta, qz, p.bc);
     }
-#pragma unroll 2
+#pragma unroll
+    for (int v = 0; v < V; ++v) neg[v] <<= (32 - dc);  // bit 31 = sign of edge 0
+#pragma unroll 6
     for (int k = 0; k < dc; ++k) {
         Real beta = Real(1);
-        if (has_beta) {
-            int col = p.bidx ? __ldg(p.bidx + slot0 + k) : 0;
-            beta = __ldg(static_cast<const Real*>(p.beta_t) + col);
-        }
-        Pack<Real, V> x;
-        if (!use_mask) {
-            int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
-            x = *reinterpret_cast<const Pack<Real, V>*>(src + row * p.Bp + f0);
-        }
+        if (p.beta_per_edge) beta = __ldg(static_cast<const Real*>(p.beta_t) + __ldg(p.bidx + slot0 + k));
         Pack<OutT, V> out;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            uint32_t sb = use_mask ? ((uint32_t)((neg[v] >> (k & 63)) & 1ull) << 31) : Arith<Real>::hi(x.v[v]);
-            Real raw = (k == st[v].k0) ? st[v].m2 : st[v].m1;
-            out.v[v] = cn_emit<Real, QUANT>(raw, beta, has_beta, st[v].par ^ sb, s_thr, p.nth, p.bc, p.mono != 0);
+            const uint32_t sb = neg[v] & 0x80000000u;
+            neg[v] <<= 1;
+            if (!p.beta_per_edge) {
+                out.v[v] = co[v].emit(k == st[v].k0, sb);
+            } else {
+                Real raw = (k == st[v].k0) ? st[v].m2 : st[v].m1;
+                out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
+            }
         }
         store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
     }
 }
 
-template <typename Real, bool QUANT>
+// Checks of degree > 32: same streaming pass, then the inputs are read again (they were just fetched)
+// for their signs and for the "is the minimum" test.
+template <typename Real, bool QUANT, int NTH>
+__device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
+                                const Quantizer<NTH>& qz) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using OutT = typename CnOut<Real, QUANT>::type;
+    const Real* __restrict__ src = static_cast<const Real*>(p.src);
+    OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
+    const bool has_beta = p.beta_t != nullptr;
+    MinState<Real, false> st[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) st[v].init();
+#pragma unroll 4
+    for (int k = 0; k < dc; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        Pack<Real, V> x = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].push(x.v[v], k);
+    }
+    CheckOut<Real, QUANT> co[V];
+    if (!p.beta_per_edge) {
+        Real beta = Real(1);
+        if (has_beta) beta = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+#pragma unroll
+        for (int v = 0; v < V; ++v) co[v].prepare(st[v].m1, st[v].m2, st[v].par, beta, has_beta, qz, p.bc);
+    }
+#pragma unroll 4
+    for (int k = 0; k < dc; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        Pack<Real, V> x = *reinterpret_cast<const Pack<Real, V>*>(src + row * p.Bp + f0);
+        Real beta = Real(1);
+        if (p.beta_per_edge) beta = __ldg(static_cast<const Real*>(p.beta_t) + __ldg(p.bidx + slot0 + k));
+        Pack<OutT, V> out;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const bool is_min = Arith<Real>::abs(x.v[v]) == st[v].m1;
+            const uint32_t sb = Arith<Real>::hi(x.v[v]);
+            if (!p.beta_per_edge) {
+                out.v[v] = co[v].emit(is_min, sb);
+            } else {
+                Real raw = is_min ? st[v].m2 : st[v].m1;
+                out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
+            }
+        }
+        store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+    }
+}
+
+template <typename Real, bool QUANT, int NTH>
 __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const int nfb) {
     constexpr int V = FramesPerLane<Real>::value;
     __shared__ float s_thr[kMaxQuantLevels];
+    Quantizer<NTH> qz;
     if (QUANT) {
         for (int i = threadIdx.x; i < p.nth; i += blockDim.x) s_thr[i] = p.thr[i];
         __syncthreads();
+        qz.load(s_thr, p.nth, p.mono != 0);
     }
     const int fb = blockIdx.x % nfb;
     const int item_id = blockIdx.x / nfb;
@@ -211,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
 #define LDPC_CN_CASE(D)                                                                   \
     case D:                                                                               \
         for (int c = 0; c < it.count; ++c, slot += D)                                     \
-            cn_check_small<Real, QUANT, D>(p, slot, f0, dmask, s_thr);                    \
+            cn_check_small<Real, QUANT, NTH, D>(p, slot, f0, dmask, qz);                  \
         break;
     switch (it.deg) {
         LDPC_CN_CASE(1)
@@ -223,8 +362,13 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
         LDPC_CN_CASE(7)
         LDPC_CN_CASE(8)
         default:
-            for (int c = 0; c < it.count; ++c, slot += it.deg)
-                cn_check_generic<Real, QUANT>(p, slot, it.deg, f0, dmask, s_thr);
+            if (it.deg <= 32) {
+                for (int c = 0; c < it.count; ++c, slot += it.deg)
+                    cn_check_mask32<Real, QUANT, NTH>(p, slot, it.deg, f0, dmask, qz);
+            } else {
+                for (int c = 0; c < it.count; ++c, slot += it.deg)
+                    cn_check_reread<Real, QUANT, NTH>(p, slot, it.deg, f0, dmask, qz);
+            }
     }
 #undef LDPC_CN_CASE
 }
@@ -237,9 +381,9 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
 // ---------------------------------------------------------------------------------------------
 template <typename Real, bool QUANT>
 __device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t idx, const float* s_lut,
-                                          int lutbase) {
+                                          int lutbase, uint32_t lutmask) {
     if constexpr (QUANT) {
-        return (Real)s_lut[lutbase + static_cast<const uint8_t*>(c2v)[idx]];
+        return (Real)s_lut[lutbase + (static_cast<const uint8_t*>(c2v)[idx] & lutmask)];
     } else {
         return static_cast<const Real*>(c2v)[idx];
     }
@@ -261,59 +405,93 @@ __device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t
     }
 }
 
-template <typename Real, bool QUANT, bool FINAL, int DV>
+// U consecutive variables of degree DV at once: all loads of the group are issued before the first use,
+// which is what keeps enough bytes in flight for the low-degree classes (a degree-2 variable on its own
+// has only 3 loads to overlap; RCQ code rows are just 128 bytes per warp).
+template <typename Real, bool QUANT, bool FINAL, int DV, int U>
 __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, int64_t lbase, int64_t f0,
                                               uint32_t dmask, int64_t wbase, const float* s_lut,
                                               const int (&lutbase)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
+    constexpr int D1 = DV > 0 ? DV : 1;
     using InT = typename CnOut<Real, QUANT>::type;
     const InT* __restrict__ c2v = static_cast<const InT*>(p.c2v);
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
-    const int64_t j = __ldg(p.vpos_var + vpos);
-    int64_t slot[DV > 0 ? DV : 1];
-    Pack<InT, V> cin[DV > 0 ? DV : 1];
+    const uint32_t lutmask = (1u << p.bc) - 1u;  // pad frames hold unwritten codes: keep the LUT index in range
+    int64_t j[U];
+    int64_t slot[U][D1];
+    Pack<InT, V> cin[U][D1];
+    Pack<Real, V> L[U];
 #pragma unroll
-    for (int d = 0; d < DV; ++d) slot[d] = __ldg(p.vslots + lbase + d);
+    for (int u = 0; u < U; ++u) {
+        j[u] = __ldg(p.vpos_var + vpos + u);
 #pragma unroll
-    for (int d = 0; d < DV; ++d) cin[d] = ld_stream<Pack<InT, V>>(c2v + slot[d] * p.Bp + f0);
-    const Pack<Real, V> L = ld_stream<Pack<Real, V>>(static_cast<const Real*>(p.llrT) + j * p.Bp + f0);
-    const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
-    Real alpha = Real(1);
-    if (has_alpha) {
-        int col = p.aidx ? __ldg(p.aidx + vpos) : 0;
-        alpha = __ldg(static_cast<const Real*>(p.alpha_t) + col);
+        for (int d = 0; d < DV; ++d) slot[u][d] = __ldg(p.vslots + lbase + u * DV + d);
     }
-    Pack<Real, V> out[DV > 0 ? DV : 1];
-    Pack<Real, V> post;
-    bool bit[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        Real c[DV > 0 ? DV : 1];
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int d = 0; d < DV; ++d) {
-            if constexpr (QUANT) c[d] = (Real)s_lut[lutbase[v] + cin[d].v[v]];
-            else c[d] = cin[d].v[v];
+        for (int d = 0; d < DV; ++d) cin[u][d] = ld_stream<Pack<InT, V>>(c2v + slot[u][d] * p.Bp + f0);
+        L[u] = ld_stream<Pack<Real, V>>(static_cast<const Real*>(p.llrT) + j[u] * p.Bp + f0);
+    }
+    const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        Real alpha = Real(1);
+        if (has_alpha) {
+            int col = p.aidx ? __ldg(p.aidx + vpos + u) : 0;
+            alpha = __ldg(static_cast<const Real*>(p.alpha_t) + col);
+        }
+        Pack<Real, V> out[D1];
+        Pack<Real, V> post;
+        bool bit[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            Real c[D1];
+#pragma unroll
+            for (int d = 0; d < DV; ++d) {
+                if constexpr (QUANT) c[d] = (Real)s_lut[lutbase[v] + (cin[u][d].v[v] & lutmask)];
+                else c[d] = cin[u][d].v[v];
+            }
+            if constexpr (!FINAL) {
+#pragma unroll
+                for (int d = 0; d < DV; ++d) {
+                    Real s = LibSum<Real>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[i < d ? i : i + 1]; });
+                    if (has_alpha) s = Arith<Real>::mul(alpha, s);
+                    out[d].v[v] = Arith<Real>::add(L[u].v[v], s);
+                }
+            }
+            Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
+            Real pv = (DV > 0) ? Arith<Real>::add(L[u].v[v], tot) : L[u].v[v];
+            post.v[v] = pv;
+            bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
         }
         if constexpr (!FINAL) {
 #pragma unroll
-            for (int d = 0; d < DV; ++d) {
-                Real s = LibSum<Real>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[i < d ? i : i + 1]; });
-                if (has_alpha) s = Arith<Real>::mul(alpha, s);
-                out[d].v[v] = Arith<Real>::add(L.v[v], s);
-            }
+            for (int d = 0; d < DV; ++d) store_masked<Real, V>(v2c + slot[u][d] * p.Bp + f0, out[d], dmask);
+        } else {
+            if (p.postT) st_stream<Pack<Real, V>>(static_cast<Real*>(p.postT) + j[u] * p.Bp + f0, post);
         }
-        Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
-        Real pv = (DV > 0) ? Arith<Real>::add(L.v[v], tot) : L.v[v];
-        post.v[v] = pv;
-        bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
+        write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit);
     }
-    if constexpr (!FINAL) {
-#pragma unroll
-        for (int d = 0; d < DV; ++d) store_masked<Real, V>(v2c + slot[d] * p.Bp + f0, out[d], dmask);
-    } else {
-        if (p.postT) st_stream<Pack<Real, V>>(static_cast<Real*>(p.postT) + j * p.Bp + f0, post);
+}
+
+// All variables of one work item, in groups of U (remainder one by one).
+template <typename Real, bool QUANT, bool FINAL, int DV>
+__device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem& it, int64_t f0, uint32_t dmask,
+                                              int64_t wbase, const float* s_lut,
+                                              const int (&lutbase)[FramesPerLane<Real>::value]) {
+    // byte-wide RCQ code rows need more rows in flight than 16-byte float rows
+    constexpr int U = QUANT ? ((DV <= 2) ? 4 : ((DV <= 4) ? 2 : 1)) : ((DV <= 2) ? 2 : 1);
+    int64_t lbase = it.first_slot;
+    int32_t vpos = it.first_node;
+    int c = 0;
+    if constexpr (U > 1) {
+        for (; c + U <= it.count; c += U, lbase += U * DV, vpos += U)
+            vn_node_small<Real, QUANT, FINAL, DV, U>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);
     }
-    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit);
+    for (; c < it.count; ++c, lbase += DV, ++vpos)
+        vn_node_small<Real, QUANT, FINAL, DV, 1>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);
 }
 
 template <typename Real, bool QUANT, bool FINAL>
@@ -322,6 +500,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
     constexpr int V = FramesPerLane<Real>::value;
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
     const int64_t j = __ldg(p.vpos_var + vpos);
+    const uint32_t lutmask = (1u << p.bc) - 1u;
     const Pack<Real, V> L = *reinterpret_cast<const Pack<Real, V>*>(static_cast<const Real*>(p.llrT) + j * p.Bp + f0);
     const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
     Real alpha = Real(1);
@@ -335,7 +514,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
     for (int v = 0; v < V; ++v) {
         auto elem = [&](int i) -> Real {
             int64_t s = __ldg(p.vslots + lbase + i);
-            return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v]);
+            return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v], lutmask);
         };
         Real tot = LibSum<Real>::dyn(elem, dv);
         Real pv = dv > 0 ? Arith<Real>::add(L.v[v], tot) : L.v[v];
@@ -350,7 +529,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
             for (int v = 0; v < V; ++v) {
                 auto others = [&](int i) -> Real {
                     int64_t s = __ldg(p.vslots + lbase + (i < d ? i : i + 1));
-                    return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v]);
+                    return c2v_value<Real, QUANT>(p.c2v, s * p.Bp + f0 + v, s_lut, lutbase[v], lutmask);
                 };
                 Real s = LibSum<Real>::dyn(others, dv - 1);
                 if (has_alpha) s = Arith<Real>::mul(alpha, s);
@@ -403,8 +582,7 @@ __global__ void __launch_bounds__(kThreads) vn_kernel(const VnLaunch p, const in
     int32_t vpos = it.first_node;
 #define LDPC_VN_CASE(D)                                                                               \
     case D:                                                                                           \
-        for (int c = 0; c < it.count; ++c, lbase += D, ++vpos)                                        \
-            vn_node_small<Real, QUANT, FINAL, D>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);   \
+        vn_item_small<Real, QUANT, FINAL, D>(p, it, f0, dmask, wbase, s_lut, lutbase);                \
         break;
     switch (it.deg) {
         LDPC_VN_CASE(0)
@@ -696,11 +874,19 @@ cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
     const int64_t nfb = (p.Bp / V + threads - 1) / threads;
     const int64_t grid = nfb * p.n_items;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const unsigned g = (unsigned)grid;
+    const int nf = (int)nfb;
     if (dtype == 0) {
-        if (p.nth > 0) cn_kernel<float, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
-        else cn_kernel<float, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        if (p.nth > 0) {
+            // register-resident thresholds need a non-decreasing table (count == last index reached)
+            if (p.mono && p.nth <= 4) cn_kernel<float, true, 4><<<g, threads, 0, stream>>>(p, nf);
+            else if (p.mono && p.nth <= 8) cn_kernel<float, true, 8><<<g, threads, 0, stream>>>(p, nf);
+            else cn_kernel<float, true, 0><<<g, threads, 0, stream>>>(p, nf);
+        } else {
+            cn_kernel<float, false, 0><<<g, threads, 0, stream>>>(p, nf);
+        }
     } else {
-        cn_kernel<double, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        cn_kernel<double, false, 0><<<g, threads, 0, stream>>>(p, nf);
     }
     return cudaGetLastError();
 }

@@ -1,0 +1,155 @@
+"""C-ABI behaviour on the device: graph re-layout, generic-degree paths, error codes, big-batch
+properties the domain offers (codewords stay codewords, linearity of the syndrome)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_graph_relayout_round_trip(built_lib):
+    L = built_lib
+    from ldpc_b200 import _lib
+    code = L.codes.dvbs2_shaped(scale=20)
+    g = code.graph
+    slot = g.slot_of_edge(0)
+    assert sorted(slot.tolist()) == list(range(g.E)), "slots are a permutation of the edges"
+    dc_of_edge = g.check_degree[g.edge_check]
+    order = np.argsort(slot)
+    assert (np.diff(dc_of_edge[order]) >= 0).all(), "slots are sorted by check degree"
+    # inside a check the slots are consecutive and keep ascending variable order
+    for i in (0, 7, g.m - 1):
+        s = slot[g.check_ptr[i]:g.check_ptr[i + 1]]
+        assert (np.diff(s) == 1).all()
+    assert g.query(0, _lib.GRAPH_E) == g.E and g.query(0, _lib.GRAPH_CHECK_CLASSES) == 4
+    assert g.query(0, _lib.GRAPH_VAR_CLASSES) == 4 and g.query(0, _lib.GRAPH_MAX_DC) == 7
+    assert g.query(0, _lib.GRAPH_MAX_DV) == 8
+
+
+def test_error_codes(built_lib):
+    from ldpc_b200 import _lib
+    lib = _lib.load()
+    out = C.c_void_p()
+    ptr = np.array([0, 2, 3], dtype=np.int64)
+    bad_order = np.array([1, 0, 2], dtype=np.int32)
+    assert lib.ldpc_graph_create(0, 3, 2, ptr.ctypes.data, bad_order.ctypes.data, C.byref(out)) == _lib.LDPC_ERR_INVALID
+    assert b"ascending" in lib.ldpc_last_error()
+    oob = np.array([0, 5, 2], dtype=np.int32)
+    assert lib.ldpc_graph_create(0, 3, 2, ptr.ctypes.data, oob.ctypes.data, C.byref(out)) == _lib.LDPC_ERR_INVALID
+    good = np.array([0, 1, 2], dtype=np.int32)
+    assert lib.ldpc_graph_create(0, 3, 2, ptr.ctypes.data, good.ctypes.data, C.byref(out)) == 0
+    cfg = _lib.DecoderConfig()
+    cfg.struct_size = C.sizeof(_lib.DecoderConfig)
+    cfg.max_iterations = 0
+    dec = C.c_void_p()
+    assert lib.ldpc_decoder_create(out, C.byref(cfg), C.byref(dec)) == _lib.LDPC_ERR_INVALID
+    cfg.max_iterations = 3
+    cfg.bc = 3
+    cfg.dtype = _lib.LDPC_F64
+    assert lib.ldpc_decoder_create(out, C.byref(cfg), C.byref(dec)) == _lib.LDPC_ERR_UNSUPPORTED
+    cfg.bc = 0
+    assert lib.ldpc_decoder_create(out, C.byref(cfg), C.byref(dec)) == 0
+    assert lib.ldpc_decode_host(dec, None, 1, None, None, None, None) == _lib.LDPC_ERR_INVALID
+    assert lib.ldpc_decoder_destroy(dec) == 0 and lib.ldpc_graph_destroy(out) == 0
+    with pytest.raises(IndexError):
+        import ldpc_b200 as L
+        L.BasicMinSumDecoder(L.create_test_ldpc_code()).decode(np.zeros(9))
+
+
+def test_wide_checks_and_wide_variables_generic_paths(built_lib):
+    """dc = 70 (> 64: sign re-read path), dc = 40 (mask path), dv = 20 and dv = 0 (generic sums)."""
+    from oracle import capi as O
+    from oracle.restatement import MODE_RCQ, SparseGraph, quantizer_schedule
+    L = built_lib
+    rng = np.random.default_rng(8)
+    m, n = 24, 96
+    H = np.zeros((m, n), dtype=np.int64)
+    H[0, rng.choice(n, 70, replace=False)] = 1
+    H[1, rng.choice(n, 40, replace=False)] = 1
+    for i in range(2, m):
+        H[i, rng.choice(n, rng.integers(2, 12), replace=False)] = 1
+    H[:, 3] = 0                      # dv = 0
+    H[rng.choice(m, 20, replace=False), 4] = 1   # dv >= 20
+    code = L.LDPCCode(n, n - m, H, max_iterations=7)
+    og = SparseGraph.from_dense(H)
+    llr = (rng.standard_normal((70, n)) * 2.5 + 1.0)
+    T = 7
+    torch.manual_seed(2)
+    dec = L.Neural2DMinSumDecoder(code, 1, T)
+    with torch.no_grad():
+        dec._beta_table.uniform_(0.5, 1.0)
+    b, p, i = dec(torch.from_numpy(llr.astype(np.float32)).cuda())
+    ref = O.decode(og, llr.astype(np.float32), T=T, beta=dec._beta_table.detach().numpy()[:, dec._beta_index])
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+    assert np.array_equal(p.cpu().numpy(), ref.posterior)
+    bb, ss, ii = L.BasicMinSumDecoder(code, 0.8).decode(llr)
+    ref = O.decode(og, llr, T=T, dtype=np.float64, beta=np.full((T, og.E), 0.8))
+    assert np.array_equal(bb, ref.bits) and np.array_equal(ii, ref.iterations) and np.array_equal(ss, ref.success)
+    rcq = L.RCQMinSumDecoder(code, 4, 8, [(4.0, 1.2), (8.0, 1.0)], max_iterations=T)
+    b, s, i = rcq.decode(torch.from_numpy(llr.astype(np.float32)).cuda())
+    thr = np.array([q.thresholds for q in rcq.quantizers]).astype(np.float32)
+    ref = O.decode(og, llr.astype(np.float32), T=T, mode=MODE_RCQ, bc=4, thresholds=thr,
+                   quantizer_of_iter=quantizer_schedule(T, 2))
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+
+
+def test_large_batch_properties_full_size_code(built_lib):
+    """Size-independent properties on the full (16200,7200)-shaped code at a batch the oracle could not
+    finish: (1) confident LLRs of the all-zero codeword decode in one iteration with zero syndrome,
+    (2) success <=> zero syndrome of the returned bits, (3) iterations == T exactly when unsuccessful,
+    (4) a random sample of frames agrees with the oracle bit for bit."""
+    from oracle import capi as O
+    from oracle.restatement import SparseGraph
+    L = built_lib
+    code = L.codes.dvbs2_shaped(max_iterations=10)
+    g = code.graph
+    B = 4096
+    torch.manual_seed(0)
+    dec = L.Neural2DMinSumDecoder(code, 2, 10)
+    with torch.no_grad():
+        dec._beta_table.fill_(0.8)
+        dec._alpha_table.fill_(0.95)
+    llr = L.awgn_llr(g.n, B, 2.6, seed=11, llr_sign=1)   # ~2/3 of the frames converge within 10 iterations
+    bits, post, iters = dec(llr)
+    eng = dec._engine(0)
+    _, _, it2, succ = eng.decode_device(llr)
+    assert torch.equal(iters, it2)
+    syn = g.syndrome(bits.cpu().numpy())
+    ok = (syn.sum(axis=1) == 0)
+    assert np.array_equal(ok, succ.cpu().numpy().astype(bool))
+    assert ((iters.cpu().numpy() == 10) | ok).all() and (iters.cpu().numpy()[~ok] == 10).all()
+    assert 0.02 < ok.mean() < 0.999, "operating point should mix converged and failed frames"
+    assert torch.equal(bits.bool(), post < 0)
+    pick = np.random.default_rng(0).choice(B, 24, replace=False)
+    og = SparseGraph.from_coo(g.n, g.m, g.edge_check, g.check_var)
+    ref = O.decode(og, llr[pick].cpu().numpy(), T=10, beta=np.full((10, g.E), np.float32(0.8)),
+                   alpha=np.full((10, g.n), np.float32(0.95)), nthreads=8)
+    assert np.array_equal(bits[pick].cpu().numpy(), ref.bits)
+    assert np.array_equal(iters[pick].cpu().numpy(), ref.iterations)
+    assert np.array_equal(post[pick].cpu().numpy(), ref.posterior)
+    clean = torch.full((256, g.n), 9.0, device="cuda")
+    b, _, i = dec(clean)
+    assert int(b.sum()) == 0 and (i == 1).all()
+
+
+def test_concurrent_decoders_from_threads(built_lib):
+    """One decoder object per host thread, as the reference's thread pool drives them
+    (simulation_framework.py:192-198)."""
+    import threading
+    L = built_lib
+    code = L.codes.dvbs2_shaped(max_iterations=6, scale=20)
+    rng = np.random.default_rng(1)
+    llr = (rng.standard_normal((64, code.n)) * 2 + 2).astype(np.float32)
+    decs = [L.RCQMinSumDecoder(code, 3, 8, [(3.0 + k, 1.3)], max_iterations=6) for k in range(4)]
+    want = [d.decode(torch.from_numpy(llr))[0] for d in decs]
+    got = [None] * 4
+
+    def work(k):
+        for _ in range(5):
+            got[k] = decs[k].decode(torch.from_numpy(llr))[0]
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
