@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -309,15 +310,40 @@ struct Workspace {
     }
 };
 
-struct HostLane {            // one lane of the host pipeline: its own stream, staging and workspace
-    cudaStream_t stream = nullptr;
-    cudaEvent_t free_ev = nullptr;
+constexpr int kPipeDepth = 3;
+
+// Host-buffer pipeline: three streams (H2D copies, kernels, D2H copies) over kPipeDepth staging buffers
+// and ONE message workspace, so that the copy of chunk i+1, the decode of chunk i and the copy-out of
+// chunk i-1 overlap while kernels of different chunks never compete for the SMs.
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    struct Buf {
+        void* d_llr = nullptr;
+        uint8_t* d_bits = nullptr;
+        void* d_post = nullptr;
+        int32_t* d_it = nullptr;
+        uint8_t* d_su = nullptr;
+        cudaEvent_t in_ready = nullptr, run_done = nullptr, out_done = nullptr;
+    } buf[kPipeDepth];
     Workspace ws;
-    void* d_llr = nullptr;
-    uint8_t* d_bits = nullptr;
-    void* d_post = nullptr;
     int64_t cap = 0;
     bool post_cap = false;
+    void release() {
+        for (auto& b : buf) {
+            cudaFree(b.d_llr); cudaFree(b.d_bits); cudaFree(b.d_post); cudaFree(b.d_it); cudaFree(b.d_su);
+            if (b.in_ready) cudaEventDestroy(b.in_ready);
+            if (b.run_done) cudaEventDestroy(b.run_done);
+            if (b.out_done) cudaEventDestroy(b.out_done);
+            b = Buf();
+        }
+        ws.release();
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_out) cudaStreamDestroy(s_out);
+        s_in = s_run = s_out = nullptr;
+        cap = 0;
+        post_cap = false;
+    }
 };
 
 }  // namespace
@@ -341,7 +367,7 @@ struct ldpc_decoder {
     float* d_lut = nullptr;                // [Q][2^bc]
     int32_t* d_q_of_iter = nullptr;        // [T]
     Workspace ws;
-    HostLane lanes[2];
+    HostPipe pipe;
     int64_t host_chunk = 0;
     // instrumentation
     int prof_mode = 0;
@@ -560,6 +586,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->bc = cfg->bc;
     d->Q = cfg->bc ? cfg->n_quantizers : 0;
     d->nth = cfg->bc ? (1 << (cfg->bc - 1)) : 0;
+    if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
 
     DeviceGuard guard(g->device);
     if (!guard.ok) {
@@ -645,14 +672,7 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     DeviceGuard guard(d->g->device);
     cudaDeviceSynchronize();
     d->ws.release();
-    for (auto& ln : d->lanes) {
-        ln.ws.release();
-        cudaFree(ln.d_llr);
-        cudaFree(ln.d_bits);
-        cudaFree(ln.d_post);
-        if (ln.free_ev) cudaEventDestroy(ln.free_ev);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
-    }
+    d->pipe.release();
     for (auto& ev : d->ev_pool) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -683,7 +703,7 @@ extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, u
     return decode_on_device(d, d->ws, llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
 }
 
-// Host-buffer entry point: chunked, double-buffered H2D -> decode -> D2H on two private streams.
+// Host-buffer entry point: chunked three-stage pipeline (see HostPipe).
 extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
                                 int32_t* iterations, uint8_t* success) {
     if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
@@ -692,50 +712,64 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
     const ldpc_graph* g = d->g;
     const int64_t n = g->n;
-    // chunk: big enough to fill the GPU (>= 8192 frames when available), two chunks in flight
-    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : 8192;
+    HostPipe& pp = d->pipe;
+    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : 8192;   // enough frames to fill the GPU
     if (B <= chunk) chunk = B;
-    const int nl = (B > chunk) ? 2 : 1;
-    for (int l = 0; l < nl; ++l) {
-        HostLane& ln = d->lanes[l];
-        if (!ln.stream) CU(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-        if (ln.cap < chunk || (posterior && !ln.post_cap)) {
-            cudaFree(ln.d_llr); cudaFree(ln.d_bits); cudaFree(ln.d_post);
-            ln.d_llr = nullptr; ln.d_bits = nullptr; ln.d_post = nullptr;
-            CU(cudaMalloc(&ln.d_llr, (size_t)chunk * n * d->rsz));
-            CU(cudaMalloc((void**)&ln.d_bits, (size_t)chunk * n));
-            if (posterior) CU(cudaMalloc(&ln.d_post, (size_t)chunk * n * d->rsz));
-            ln.cap = chunk;
-            ln.post_cap = posterior != nullptr;
+    if (!pp.s_in) {
+        CU(cudaStreamCreateWithFlags(&pp.s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&pp.s_run, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&pp.s_out, cudaStreamNonBlocking));
+        for (auto& b : pp.buf) {
+            CU(cudaEventCreateWithFlags(&b.in_ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b.run_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b.out_done, cudaEventDisableTiming));
         }
-        int rc = ws_ensure(d, ln.ws, pad_frames(chunk));
-        if (rc) return rc;
     }
-    int rc = LDPC_OK;
-    int64_t done_frames = 0;
-    int l = 0;
-    while (done_frames < B && !rc) {
-        const int64_t b = std::min<int64_t>(chunk, B - done_frames);
-        HostLane& ln = d->lanes[l];
-        cudaStream_t stream = ln.stream;
-        const char* src = (const char*)llr + (size_t)done_frames * n * d->rsz;
-        CU(cudaMemcpyAsync(ln.d_llr, src, (size_t)b * n * d->rsz, cudaMemcpyHostToDevice, stream));
-        int32_t* d_it = ln.ws.iters;
-        uint8_t* d_su = ln.ws.success;
-        rc = decode_on_device(d, ln.ws, ln.d_llr, b, bits ? ln.d_bits : nullptr, posterior ? ln.d_post : nullptr,
-                              nullptr, nullptr, stream);
+    if (pp.cap < chunk || (posterior && !pp.post_cap)) {
+        for (auto& b : pp.buf) {
+            cudaFree(b.d_llr); cudaFree(b.d_bits); cudaFree(b.d_post); cudaFree(b.d_it); cudaFree(b.d_su);
+            b.d_llr = nullptr; b.d_bits = nullptr; b.d_post = nullptr; b.d_it = nullptr; b.d_su = nullptr;
+            CU(cudaMalloc(&b.d_llr, (size_t)chunk * n * d->rsz));
+            CU(cudaMalloc((void**)&b.d_bits, (size_t)chunk * n));
+            if (posterior) CU(cudaMalloc(&b.d_post, (size_t)chunk * n * d->rsz));
+            CU(cudaMalloc((void**)&b.d_it, (size_t)chunk * sizeof(int32_t)));
+            CU(cudaMalloc((void**)&b.d_su, (size_t)chunk));
+        }
+        pp.cap = chunk;
+        pp.post_cap = posterior != nullptr;
+    }
+    int rc = ws_ensure(d, pp.ws, pad_frames(chunk));
+    if (rc) return rc;
+    int64_t off = 0;
+    for (int64_t i = 0; off < B && !rc; ++i) {
+        // ramp the first chunks (1/8, 1/4, 1/2 of a chunk) so the kernels start while most of the input is
+        // still crossing PCIe; the un-overlapped head of the pipeline shrinks accordingly
+        int64_t want = chunk;
+        if (B > 2 * chunk && i < 3) want = std::max<int64_t>(kFrameAlign, (chunk >> (3 - i)) / kFrameAlign * kFrameAlign);
+        const int64_t b = std::min<int64_t>(want, B - off);
+        HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
+        if (i >= kPipeDepth) CU(cudaStreamWaitEvent(pp.s_in, bf.run_done, 0));     // staging input consumed
+        CU(cudaMemcpyAsync(bf.d_llr, (const char*)llr + (size_t)off * n * d->rsz, (size_t)b * n * d->rsz,
+                           cudaMemcpyHostToDevice, pp.s_in));
+        CU(cudaEventRecord(bf.in_ready, pp.s_in));
+        CU(cudaStreamWaitEvent(pp.s_run, bf.in_ready, 0));
+        if (i >= kPipeDepth) CU(cudaStreamWaitEvent(pp.s_run, bf.out_done, 0));    // staging outputs copied out
+        rc = decode_on_device(d, pp.ws, bf.d_llr, b, bits ? bf.d_bits : nullptr, posterior ? bf.d_post : nullptr,
+                              bf.d_it, bf.d_su, pp.s_run);
         if (rc) break;
-        if (bits) CU(cudaMemcpyAsync(bits + (size_t)done_frames * n, ln.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(bf.run_done, pp.s_run));
+        CU(cudaStreamWaitEvent(pp.s_out, bf.run_done, 0));
+        if (bits) CU(cudaMemcpyAsync(bits + (size_t)off * n, bf.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, pp.s_out));
         if (posterior)
-            CU(cudaMemcpyAsync((char*)posterior + (size_t)done_frames * n * d->rsz, ln.d_post, (size_t)b * n * d->rsz,
-                               cudaMemcpyDeviceToHost, stream));
-        if (iterations) CU(cudaMemcpyAsync(iterations + done_frames, d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        if (success) CU(cudaMemcpyAsync(success + done_frames, d_su, (size_t)b, cudaMemcpyDeviceToHost, stream));
-        done_frames += b;
-        l = (l + 1) % nl;
+            CU(cudaMemcpyAsync((char*)posterior + (size_t)off * n * d->rsz, bf.d_post, (size_t)b * n * d->rsz,
+                               cudaMemcpyDeviceToHost, pp.s_out));
+        if (iterations) CU(cudaMemcpyAsync(iterations + off, bf.d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, pp.s_out));
+        if (success) CU(cudaMemcpyAsync(success + off, bf.d_su, (size_t)b, cudaMemcpyDeviceToHost, pp.s_out));
+        CU(cudaEventRecord(bf.out_done, pp.s_out));
+        off += b;
     }
-    for (int k = 0; k < nl; ++k) {
-        cudaError_t e = cudaStreamSynchronize(d->lanes[k].stream);
+    for (cudaStream_t st : {pp.s_in, pp.s_run, pp.s_out}) {
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess && !rc) rc = fail(LDPC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
     }
     return rc;
