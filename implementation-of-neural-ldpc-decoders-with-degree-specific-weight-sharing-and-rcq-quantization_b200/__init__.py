@@ -10,8 +10,8 @@ _lib_mod.load()  # fail loudly if the CUDA library has not been built
 
 from .engine import Engine, LdpcError, PinnedBuffer, TannerGraph, awgn_llr, count_errors  # noqa: E402,F401
 from .ldpc_decoder import BasicMinSumDecoder, LDPCCode, create_test_ldpc_code, simulate_awgn_channel  # noqa: E402,F401
-from .neural_2d_decoder import Neural2DMinSumDecoder  # noqa: E402,F401
-from .neural_minsum_decoder import NeuralMinSumDecoder  # noqa: E402,F401
+from .neural_2d_decoder import Neural2DMinSumDecoder, Neural2DOffsetMinSumDecoder  # noqa: E402,F401
+from .neural_minsum_decoder import NeuralMinSumDecoder, NeuralOffsetMinSumDecoder  # noqa: E402,F401
 from .rcq_decoder import NonUniformQuantizer, RCQMinSumDecoder, WeightedRCQDecoder  # noqa: E402,F401
 from .simulation_framework import (LDPSimulator, SimulationConfig, SimulationResult,  # noqa: E402,F401
                                    create_test_decoders)

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libldpc_b200.so")
 
 LDPC_OK, LDPC_ERR_INVALID, LDPC_ERR_CUDA, LDPC_ERR_NOMEM, LDPC_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 LDPC_F32, LDPC_F64 = 0, 1
+RULE_NORMALIZED, RULE_OFFSET = 0, 1
+SCHEDULE_FLOODING, SCHEDULE_LAYERED = 0, 1
 (GRAPH_N, GRAPH_M, GRAPH_E, GRAPH_CHECK_CLASSES, GRAPH_VAR_CLASSES, GRAPH_MAX_DC, GRAPH_MAX_DV,
  GRAPH_DEVICE) = range(8)
 
@@ -36,7 +38,8 @@ class DecoderConfig(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("dtype", C.c_int32), ("max_iterations", C.c_int32),
         ("early_stop", C.c_int32), ("n_beta", C.c_int32), ("n_alpha", C.c_int32), ("bc", C.c_int32),
-        ("n_quantizers", C.c_int32), ("beta_index", C.c_void_p), ("beta", C.c_void_p),
+        ("n_quantizers", C.c_int32), ("check_rule", C.c_int32), ("schedule", C.c_int32),
+        ("beta_index", C.c_void_p), ("beta", C.c_void_p),
         ("alpha_index", C.c_void_p), ("alpha", C.c_void_p), ("thresholds", C.c_void_p),
         ("quantizer_of_iter", C.c_void_p),
     ]

@@ -95,7 +95,8 @@ class DecoderModule(nn.Module):
             eng = Engine(self.code.graph, dtype=np.float32, max_iterations=self.max_iterations,
                          beta=b, beta_index=self._beta_index if self._beta_table is not None else None,
                          alpha=a, alpha_index=self._alpha_index if a is not None else None,
-                         bc=bc, thresholds=thr, quantizer_of_iter=qoi, device=device)
+                         bc=bc, thresholds=thr, quantizer_of_iter=qoi,
+                         check_rule=getattr(self, "_check_rule", 0), device=device)
             self._engines[device] = eng
             self._pushed[device] = self._versions()
         elif self._pushed[device] != self._versions():

@@ -80,7 +80,12 @@ struct ldpc_graph {
     std::vector<int32_t> vpos_var;       // [n] position -> variable
     std::vector<int32_t> var_vpos;       // [n] variable -> position
     std::vector<WorkItem> cn_items, vn_items;
+    std::vector<int64_t> chk_ptr;        // original CSR (layered schedule walks checks in index order)
+    std::vector<int32_t> chk_var;
+    int nonempty_checks = 0;
     // device copies
+    int64_t* d_chk_ptr = nullptr;
+    int32_t* d_chk_var = nullptr;
     int32_t* d_slot_var = nullptr;
     int32_t* d_vslots = nullptr;
     int32_t* d_vpos_var = nullptr;
@@ -148,6 +153,9 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     g->E = E;
     g->max_dc = max_dc;
     g->max_dv = max_dv;
+    g->chk_ptr.assign(check_ptr, check_ptr + m + 1);
+    g->chk_var.assign(check_var, check_var + E);
+    for (int32_t i = 0; i < m; ++i) g->nonempty_checks += check_ptr[i + 1] > check_ptr[i];
 
     // ---- check side: stable sort of non-empty checks by degree -> slots ----
     std::vector<int32_t> corder;
@@ -246,6 +254,8 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     if (!rc) rc = upload(&g->d_vpos_var, g->vpos_var);
     if (!rc) rc = upload(&g->d_cn_items, g->cn_items);
     if (!rc) rc = upload(&g->d_vn_items, g->vn_items);
+    if (!rc) rc = upload(&g->d_chk_ptr, g->chk_ptr);
+    if (!rc) rc = upload(&g->d_chk_var, g->chk_var);
     if (rc) {
         ldpc_graph_destroy(g);
         return rc;
@@ -262,6 +272,8 @@ extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
     cudaFree(g->d_vpos_var);
     cudaFree(g->d_cn_items);
     cudaFree(g->d_vn_items);
+    cudaFree(g->d_chk_ptr);
+    cudaFree(g->d_chk_var);
     delete g;
     return LDPC_OK;
 }
@@ -361,6 +373,8 @@ struct ldpc_decoder {
     int32_t* d_bidx = nullptr;             // per slot
     int beta_per_edge = 0;                 // some check mixes beta columns
     int32_t* d_aidx = nullptr;             // per vpos
+    int32_t* d_aidx_slot = nullptr;        // per slot (offset rule: alpha is applied at the check node)
+    int check_rule = 0, schedule = 0;
     void* d_beta = nullptr;                // [T][n_beta]
     void* d_alpha = nullptr;               // [T][n_alpha]
     float* d_thr = nullptr;                // [Q][nth]
@@ -450,7 +464,36 @@ struct Timed {
 // The flooding schedule on frames already resident as llrT [n][Bp] in `ws`.
 // After it returns (stream order): ws.hardw holds the final hard decisions of every frame,
 // ws.iters / ws.success the per-frame results, and ws.v2c holds postT [n][Bp] if want_post.
+// Layered RCQ (rcq_decoder.py:281-350): the posteriors live in ws.llrT and are updated in place.
+int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
+    const ldpc_graph* g = d->g;
+    const int64_t Wn = Bp / 32;
+    LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
+    for (int t = 0; t < d->T; ++t) {
+        const int q = d->q_of_iter[t];
+        LAUNCH(K_CN, launch_layered_iter(static_cast<float*>(ws.llrT), g->d_chk_ptr, g->d_chk_var, g->m,
+                                         d->d_thr + (size_t)q * d->nth, d->nth, d->bc, d->mono[q], ws.done, Bp, stream));
+        LAUNCH(K_VN, launch_hard(d->dtype, ws.llrT, ws.hardw, Wn, g->n, Bp, stream));
+        if (d->early_stop || t == d->T - 1) {
+            uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
+            uint32_t* nxt = ws.unsat + (size_t)((t + 1) & 1) * Wn;
+            SynLaunch sy{};
+            sy.hardw = ws.hardw;
+            sy.Wn = Wn;
+            sy.slot_var = g->d_slot_var;
+            sy.items = g->d_cn_items;
+            sy.n_items = (int)g->cn_items.size();
+            sy.unsat = cur;
+            LAUNCH(K_OTHER, launch_syndrome(sy, stream));
+            LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
+        }
+    }
+    if (want_post) CU(cudaMemcpyAsync(ws.v2c, ws.llrT, (size_t)g->n * Bp * d->rsz, cudaMemcpyDeviceToDevice, stream));
+    return LDPC_OK;
+}
+
 int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
+    if (d->schedule == LDPC_SCHEDULE_LAYERED) return run_layered(d, ws, B, Bp, want_post, stream);
     const ldpc_graph* g = d->g;
     const int64_t Wn = Bp / 32;
     LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
@@ -471,7 +514,13 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
         cn.items = g->d_cn_items;
         cn.n_items = (int)g->cn_items.size();
         cn.Bp = Bp;
-        LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
+        if (d->check_rule == LDPC_RULE_OFFSET) {
+            cn.aidx_slot = d->d_aidx_slot;
+            cn.alpha_t = d->d_alpha ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
+            LAUNCH(K_CN, launch_cn_offset(d->dtype, cn, stream));
+        } else {
+            LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
+        }
 
         const bool last = (t == d->T - 1);
         VnLaunch vn{};
@@ -482,7 +531,8 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
         vn.vslots = g->d_vslots;
         vn.vpos_var = g->d_vpos_var;
         vn.aidx = d->d_aidx;
-        vn.alpha_t = d->d_alpha ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
+        vn.alpha_t = (d->d_alpha && d->check_rule != LDPC_RULE_OFFSET)
+                         ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
         vn.lut = d->d_lut;
         vn.bc = d->bc;
         vn.n_quant = d->Q;
@@ -560,6 +610,18 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
         if (((int64_t)cfg->n_quantizers << cfg->bc) > kMaxLutFloats)
             return fail(LDPC_ERR_UNSUPPORTED, "too many quantiser levels");
     }
+    if (cfg->check_rule != LDPC_RULE_NORMALIZED && cfg->check_rule != LDPC_RULE_OFFSET)
+        return fail(LDPC_ERR_INVALID, "bad check_rule");
+    if (cfg->check_rule == LDPC_RULE_OFFSET && cfg->bc != 0)
+        return fail(LDPC_ERR_UNSUPPORTED, "the offset rule has no quantised variant in the reference");
+    if (cfg->schedule != LDPC_SCHEDULE_FLOODING && cfg->schedule != LDPC_SCHEDULE_LAYERED)
+        return fail(LDPC_ERR_INVALID, "bad schedule");
+    if (cfg->schedule == LDPC_SCHEDULE_LAYERED) {
+        if (cfg->bc == 0 || cfg->n_beta || cfg->n_alpha || cfg->check_rule != LDPC_RULE_NORMALIZED)
+            return fail(LDPC_ERR_UNSUPPORTED, "the layered schedule exists for plain RCQ only (rcq_decoder.py:281-350)");
+        if (g->nonempty_checks == 1)
+            return fail(LDPC_ERR_UNSUPPORTED, "layered schedule on a graph with a single non-empty check");
+    }
     if (cfg->dtype == LDPC_F64 && g->max_dv > 129)
         return fail(LDPC_ERR_UNSUPPORTED, "float64 path models np.sum up to 128 terms (max variable degree 129)");
     const int T = cfg->max_iterations;
@@ -586,6 +648,8 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->bc = cfg->bc;
     d->Q = cfg->bc ? cfg->n_quantizers : 0;
     d->nth = cfg->bc ? (1 << (cfg->bc - 1)) : 0;
+    d->check_rule = cfg->check_rule;
+    d->schedule = cfg->schedule;
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
 
     DeviceGuard guard(g->device);
@@ -610,6 +674,11 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
         std::vector<int32_t> aidx((size_t)g->n);
         for (int32_t p = 0; p < g->n; ++p) aidx[(size_t)p] = cfg->alpha_index[g->vpos_var[(size_t)p]];
         rc = upload(&d->d_aidx, aidx);
+        if (!rc && cfg->check_rule == LDPC_RULE_OFFSET) {
+            std::vector<int32_t> as((size_t)E);
+            for (int64_t sl = 0; sl < E; ++sl) as[(size_t)sl] = cfg->alpha_index[g->slot_var[(size_t)sl]];
+            rc = upload(&d->d_aidx_slot, as);
+        }
     }
     if (!rc && cfg->n_beta > 0) {
         size_t bytes = (size_t)T * cfg->n_beta * d->rsz;
@@ -679,6 +748,7 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     }
     cudaFree(d->d_bidx);
     cudaFree(d->d_aidx);
+    cudaFree(d->d_aidx_slot);
     cudaFree(d->d_beta);
     cudaFree(d->d_alpha);
     cudaFree(d->d_thr);

@@ -26,7 +26,9 @@ struct CnLaunch {
     const int32_t* row_map;     // iteration 0: variable of each slot; else nullptr
     const int32_t* bidx;        // per-slot column of beta, or nullptr (column 0)
     int beta_per_edge;          // 0: every edge of a check uses the column of its first slot; 1: per edge
-    const void* beta_t;         // beta row of this iteration, or nullptr (beta == 1)
+    const void* beta_t;         // beta row of this iteration, or nullptr (beta == 1; offset rule: beta == 0)
+    const int32_t* aidx_slot;   // offset rule only: per-slot column of alpha (by the edge's variable), or nullptr
+    const void* alpha_t;        // offset rule only: alpha row of this iteration, or nullptr (alpha == 0)
     const float* thr;           // device thresholds of this iteration's quantiser [nth]
     int nth;                    // 2^(bc-1), 0 = float messages
     int bc;
@@ -73,6 +75,13 @@ struct SynLaunch {
 // All launchers enqueue on `stream` and return the CUDA launch status.
 cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream);
 cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream);
+// offset min-sum check rule: c2v = sp * (relu(raw - beta) - alpha)
+cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream);
+// one layered-RCQ iteration over all checks in index order, in place on the posteriors P [n][Bp]
+cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,
+                                int nth, int bc, int mono, const uint8_t* done, int64_t Bp, cudaStream_t stream);
+// hard decisions (P < 0) of every frame, bit-packed
+cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, int32_t n, int64_t Bp, cudaStream_t stream);
 cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream);
 // frames with done == 0 whose syndrome word bit is clear become done with iterations = t1;
 // also clears `unsat_next`.  V = frames per lane of the decoder's dtype.

@@ -373,22 +373,7 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
 #undef LDPC_CN_CASE
 }
 
-// ---------------------------------------------------------------------------------------------
-// Variable node + posterior + hard decision (ldpc_decoder.py:123-140; neural_2d_decoder.py:194-212)
-//   v2c_d = fl(llr + fl(alpha * S(c2v of the other checks, ascending check index)))
-//   post  = fl(llr + S(all c2v))        -- never alpha-weighted
-//   bit   = post < 0, ballot-packed: one 32-bit word holds the same variable of 32 frames.
-// ---------------------------------------------------------------------------------------------
-template <typename Real, bool QUANT>
-__device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t idx, const float* s_lut,
-                                          int lutbase, uint32_t lutmask) {
-    if constexpr (QUANT) {
-        return (Real)s_lut[lutbase + (static_cast<const uint8_t*>(c2v)[idx] & lutmask)];
-    } else {
-        return static_cast<const Real*>(c2v)[idx];
-    }
-}
-
+// One 32-bit word per (variable, V-th frame of 32 lanes): bit = lane.
 template <typename Real, int V>
 __device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t Wn, int64_t j, int64_t wbase,
                                            const bool (&bit)[V]) {
@@ -402,6 +387,207 @@ __device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t
         for (int v = 1; v < V; ++v)
             if (lane == v) w = words[v];
         hardw[j * Wn + wbase + lane] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Offset min-sum check node (neural_minsum_decoder.py:236-253, neural_2d_decoder.py:383-401):
+//   c2v = prod(other signs) * (relu(raw - beta) - alpha),   alpha indexed by the edge's VARIABLE degree
+// Here the reference's three-valued sign() is visible (relu(0 - beta) - alpha need not be 0), so a zero
+// among the OTHER inputs forces the output to 0: that is the case iff m2 == 0 (two zeros), or m1 == 0
+// and this edge is not the zero one.  A degree-1 check has an empty product (= 1).
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ Real offset_value(Real raw, Real beta, bool has_beta, Real alpha, bool has_alpha,
+                                             uint32_t signbits, bool zero_others) {
+    Real t = has_beta ? Arith<Real>::add(raw, -beta) : raw;
+    t = Arith<Real>::fmax_(t, Real(0));
+    if (has_alpha) t = Arith<Real>::add(t, -alpha);
+    t = Arith<Real>::flip(t, signbits);
+    return zero_others ? Real(0) : t;
+}
+
+template <typename Real>
+__device__ __forceinline__ void offset_weights(const CnLaunch& p, int64_t slot, Real beta_check, Real& beta, Real& alpha) {
+    beta = beta_check;
+    if (p.beta_t && p.beta_per_edge) beta = __ldg(static_cast<const Real*>(p.beta_t) + __ldg(p.bidx + slot));
+    alpha = Real(0);
+    if (p.alpha_t) alpha = __ldg(static_cast<const Real*>(p.alpha_t) + (p.aidx_slot ? __ldg(p.aidx_slot + slot) : 0));
+}
+
+template <typename Real, int DC>
+__device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask) {
+    constexpr int V = FramesPerLane<Real>::value;
+    const Real* __restrict__ src = static_cast<const Real*>(p.src);
+    Real* __restrict__ dst = static_cast<Real*>(p.dst);
+    Pack<Real, V> x[DC];
+    Real beta[DC], alpha[DC];
+    Real beta_check = Real(0);
+    if (p.beta_t && !p.beta_per_edge) beta_check = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+        offset_weights<Real>(p, slot0 + k, beta_check, beta[k], alpha[k]);
+    }
+    Pack<Real, V> out[DC];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        MinState<Real, false> st;
+        st.init();
+#pragma unroll
+        for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
+        if (DC == 1) st.m2 = st.m1;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            const bool is_min = Arith<Real>::abs(x[k].v[v]) == st.m1;
+            const bool zero_others = (DC > 1) && (st.m2 == Real(0) || (st.m1 == Real(0) && !is_min));
+            out[k].v[v] = offset_value<Real>(is_min ? st.m2 : st.m1, beta[k], p.beta_t != nullptr, alpha[k],
+                                             p.alpha_t != nullptr, st.par ^ Arith<Real>::hi(x[k].v[v]), zero_others);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) store_masked<Real, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+}
+
+template <typename Real>
+__device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask) {
+    constexpr int V = FramesPerLane<Real>::value;
+    const Real* __restrict__ src = static_cast<const Real*>(p.src);
+    Real* __restrict__ dst = static_cast<Real*>(p.dst);
+    MinState<Real, false> st[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) st[v].init();
+    for (int k = 0; k < dc; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        Pack<Real, V> x = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].push(x.v[v], k);
+    }
+    Real beta_check = Real(0);
+    if (p.beta_t && !p.beta_per_edge) beta_check = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+    for (int k = 0; k < dc; ++k) {
+        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
+        Pack<Real, V> x = *reinterpret_cast<const Pack<Real, V>*>(src + row * p.Bp + f0);
+        Real beta, alpha;
+        offset_weights<Real>(p, slot0 + k, beta_check, beta, alpha);
+        Pack<Real, V> out;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const bool is_min = Arith<Real>::abs(x.v[v]) == st[v].m1;
+            const bool zero_others = st[v].m2 == Real(0) || (st[v].m1 == Real(0) && !is_min);
+            out.v[v] = offset_value<Real>(is_min ? st[v].m2 : st[v].m1, beta, p.beta_t != nullptr, alpha,
+                                          p.alpha_t != nullptr, st[v].par ^ Arith<Real>::hi(x.v[v]), zero_others);
+        }
+        store_masked<Real, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb) {
+    constexpr int V = FramesPerLane<Real>::value;
+    const int fb = blockIdx.x % nfb;
+    const int item_id = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= p.Bp) return;
+    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    const WorkItem it = p.items[item_id];
+    int64_t slot = it.first_slot;
+#define LDPC_CNO_CASE(D)                                                \
+    case D:                                                             \
+        for (int c = 0; c < it.count; ++c, slot += D)                   \
+            cn_offset_small<Real, D>(p, slot, f0, dmask);               \
+        break;
+    switch (it.deg) {
+        LDPC_CNO_CASE(1)
+        LDPC_CNO_CASE(2)
+        LDPC_CNO_CASE(3)
+        LDPC_CNO_CASE(4)
+        LDPC_CNO_CASE(5)
+        LDPC_CNO_CASE(6)
+        LDPC_CNO_CASE(7)
+        LDPC_CNO_CASE(8)
+        default:
+            for (int c = 0; c < it.count; ++c, slot += it.deg) cn_offset_wide<Real>(p, slot, it.deg, f0, dmask);
+    }
+#undef LDPC_CNO_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layered RCQ schedule as the reference executes it (rcq_decoder.py:281-350):
+// posteriors start at the LLRs, checks are visited in INDEX order, each visit reads the current
+// posteriors of its variables, quantises sp*raw and ADDS the reconstruction to those posteriors in place
+// (the "subtract the previous C2V" step subtracts 0 on any graph with more than one non-empty check).
+// One thread = one frame walks all checks of one iteration; frames are independent.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restrict__ P, const int64_t* __restrict__ chk_ptr,
+                                                                 const int32_t* __restrict__ chk_var, int32_t m,
+                                                                 const float* __restrict__ thr, int nth, int bc, int mono,
+                                                                 const uint8_t* __restrict__ done, int64_t Bp) {
+    __shared__ float s_thr[kMaxQuantLevels];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
+    __syncthreads();
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Bp || done[f]) return;
+    Quantizer<0> qz;
+    qz.load(s_thr, nth, mono != 0);
+    for (int32_t i = 0; i < m; ++i) {
+        const int64_t e0 = __ldg(chk_ptr + i), e1 = __ldg(chk_ptr + i + 1);
+        const int dc = (int)(e1 - e0);
+        if (dc == 0) continue;
+        MinState<float, false> st;
+        st.init();
+        for (int k = 0; k < dc; ++k) st.push(P[(int64_t)__ldg(chk_var + e0 + k) * Bp + f], k);
+        if (dc == 1) st.m2 = st.m1;
+        const uint32_t ia = qz.index(st.m1), ib = qz.index(st.m2);
+        const float va = s_thr[ia], vb = s_thr[ib];
+        for (int k = 0; k < dc; ++k) {
+            float* ptr = P + (int64_t)__ldg(chk_var + e0 + k) * Bp + f;
+            const float x = *ptr;
+            const bool is_min = fabsf(x) == st.m1;
+            const float raw = is_min ? st.m2 : st.m1;
+            const float mag = is_min ? vb : va;
+            // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude
+            const bool neg = (((st.par ^ __float_as_uint(x)) >> 31) != 0u) && (raw != 0.f);
+            *ptr = __fadd_rn(x, neg ? -mag : mag);
+        }
+    }
+}
+
+// Hard decisions of every frame from a posterior array [n][Bp], ballot-packed like vn_kernel's.
+template <typename Real>
+__global__ void __launch_bounds__(kThreads) hard_kernel(const Real* __restrict__ P, uint32_t* __restrict__ hardw,
+                                                         int64_t Wn, int32_t n, int64_t Bp, int nfb) {
+    constexpr int V = FramesPerLane<Real>::value;
+    const int fb = blockIdx.x % nfb;
+    const int chunk = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= Bp) return;
+    const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
+    const int64_t wbase = (warp_f0 / (32 * V)) * V;
+    for (int32_t j = chunk * 16; j < min(n, (chunk + 1) * 16); ++j) {
+        Pack<Real, V> x = *reinterpret_cast<const Pack<Real, V>*>(P + (int64_t)j * Bp + f0);
+        bool bit[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) bit[v] = x.v[v] < Real(0);
+        write_hard<Real, V>(hardw, Wn, j, wbase, bit);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable node + posterior + hard decision (ldpc_decoder.py:123-140; neural_2d_decoder.py:194-212)
+//   v2c_d = fl(llr + fl(alpha * S(c2v of the other checks, ascending check index)))
+//   post  = fl(llr + S(all c2v))        -- never alpha-weighted
+//   bit   = post < 0, ballot-packed: one 32-bit word holds the same variable of 32 frames.
+// ---------------------------------------------------------------------------------------------
+template <typename Real, bool QUANT>
+__device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t idx, const float* s_lut,
+                                          int lutbase, uint32_t lutmask) {
+    if constexpr (QUANT) {
+        return (Real)s_lut[lutbase + (static_cast<const uint8_t*>(c2v)[idx] & lutmask)];
+    } else {
+        return static_cast<const Real*>(c2v)[idx];
     }
 }
 
@@ -888,6 +1074,36 @@ cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
     } else {
         cn_kernel<double, false, 0><<<g, threads, 0, stream>>>(p, nf);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
+    if (p.n_items == 0) return cudaSuccess;
+    const int V = dtype == 0 ? 4 : 2;
+    const int threads = threads_for(p.Bp, V);
+    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+    const int64_t grid = nfb * p.n_items;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (dtype == 0) cn_offset_kernel<float><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    else cn_offset_kernel<double><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,
+                                int nth, int bc, int mono, const uint8_t* done, int64_t Bp, cudaStream_t stream) {
+    const int threads = (int)(Bp < 128 ? Bp : 128);
+    layered_iter_kernel<<<(unsigned)((Bp + threads - 1) / threads), threads, 0, stream>>>(P, chk_ptr, chk_var, m, thr, nth,
+                                                                                            bc, mono, done, Bp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, int32_t n, int64_t Bp, cudaStream_t stream) {
+    const int V = dtype == 0 ? 4 : 2;
+    const int threads = threads_for(Bp, V);
+    const int64_t nfb = (Bp / V + threads - 1) / threads;
+    const int64_t grid = nfb * ((n + 15) / 16);
+    if (dtype == 0) hard_kernel<float><<<(unsigned)grid, threads, 0, stream>>>(static_cast<const float*>(P), hardw, Wn, n, Bp, (int)nfb);
+    else hard_kernel<double><<<(unsigned)grid, threads, 0, stream>>>(static_cast<const double*>(P), hardw, Wn, n, Bp, (int)nfb);
     return cudaGetLastError();
 }
 

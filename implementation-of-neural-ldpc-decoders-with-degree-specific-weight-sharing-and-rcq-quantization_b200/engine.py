@@ -133,7 +133,8 @@ class Engine:
                  beta: Optional[np.ndarray] = None, beta_index: Optional[np.ndarray] = None,
                  alpha: Optional[np.ndarray] = None, alpha_index: Optional[np.ndarray] = None,
                  bc: int = 0, thresholds: Optional[np.ndarray] = None,
-                 quantizer_of_iter: Optional[np.ndarray] = None, device: Optional[int] = None):
+                 quantizer_of_iter: Optional[np.ndarray] = None, check_rule: int = 0, schedule: int = 0,
+                 device: Optional[int] = None):
         self.graph = graph
         self.dtype = np.dtype(dtype)
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
@@ -146,6 +147,8 @@ class Engine:
         cfg.dtype = _lib.LDPC_F32 if self.dtype == np.float32 else _lib.LDPC_F64
         cfg.max_iterations = self.T
         cfg.early_stop = 1 if early_stop else 0
+        cfg.check_rule = int(check_rule)
+        cfg.schedule = int(schedule)
         keep = []
 
         def table(a, width_name):

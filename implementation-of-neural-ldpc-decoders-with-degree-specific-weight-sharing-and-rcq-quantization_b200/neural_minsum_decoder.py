@@ -34,6 +34,28 @@ class NeuralMinSumDecoder(DecoderModule):
         return self._forward_impl(llr)
 
 
+class NeuralOffsetMinSumDecoder(DecoderModule):
+    """Offset min-sum with one offset per (iteration, edge) (neural_minsum_decoder.py:152-286):
+    ``c2v = prod(other signs) * relu(raw - beta)``, offsets initialised ``0.1 * randn`` (:185)."""
+
+    _check_rule = 1  # LDPC_RULE_OFFSET
+
+    def __init__(self, code: LDPCCode, max_iterations: int = 50):
+        super().__init__()
+        self._init_base(code, max_iterations)
+        g = code.graph
+        T, E = max_iterations, g.E
+        self._beta_table = nn.Parameter(seeded_normal(T * E, 0.1, 0.0).reshape(T, E).clone())
+        self._alpha_table = None
+        self._beta_index = np.arange(E, dtype=np.int32)
+        self._alpha_index = None
+        self._beta_const = None
+        self.beta_weights = _EdgeKeyView(self._beta_table, T, g)
+
+    def forward(self, llr: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        return self._forward_impl(llr)
+
+
 class _EdgeKeyView(WeightView):
     """Key view for T*E per-edge weights without materialising T*E strings up front."""
 

@@ -9,7 +9,9 @@ What the reference's code actually does and what is r
 check-to-variable messages are quantised (to a bc-bit sign-magnitude code, reconstructed as the lower
 bin edge); variable-to-check messages and posteriors stay float32; ``bv`` is stored and unused.  On
 the device the C2V messages are held as the integer codes themselves (1 byte per edge per frame).
-The layered schedule of RCQMinSumDecoder (rcq_decoder.py:281-350) is not built yet.
+``RCQMinSumDecoder(layered=True)`` runs the layered schedule exactly as the reference executes it
+(rcq_decoder.py:281-350): posteriors updated in place check by check, the "subtract previous C2V" step
+being a no-op there.
 """
 from __future__ import annotations
 
@@ -86,17 +88,17 @@ class RCQMinSumDecoder:
         return self.quantizers[int(_schedule(self.max_iterations, len(self.quantizers))[iteration])]
 
     def _engine(self, device: int) -> Engine:
-        eng = self._engines.get(device)
+        key = (device, bool(self.layered))
+        eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self.code.graph, dtype=np.float32, max_iterations=self.max_iterations, bc=self.bc,
                          thresholds=_threshold_table(self.quantizers),
-                         quantizer_of_iter=_schedule(self.max_iterations, len(self.quantizers)), device=device)
-            self._engines[device] = eng
+                         quantizer_of_iter=_schedule(self.max_iterations, len(self.quantizers)),
+                         schedule=1 if self.layered else 0, device=device)
+            self._engines[key] = eng
         return eng
 
     def decode(self, llr: torch.Tensor) -> Tuple[torch.Tensor, bool, int]:
-        if self.layered:
-            raise NotImplementedError("layered RCQ schedule is not built yet (flooding only)")
         if not isinstance(llr, torch.Tensor):
             llr = torch.as_tensor(np.asarray(llr))
         single = llr.dim() == 1

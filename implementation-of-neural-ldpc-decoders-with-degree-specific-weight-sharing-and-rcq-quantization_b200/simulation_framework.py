@@ -26,8 +26,8 @@ import numpy as np
 import torch
 
 from .ldpc_decoder import BasicMinSumDecoder, LDPCCode
-from .neural_2d_decoder import Neural2DMinSumDecoder
-from .neural_minsum_decoder import NeuralMinSumDecoder
+from .neural_2d_decoder import Neural2DMinSumDecoder, Neural2DOffsetMinSumDecoder
+from .neural_minsum_decoder import NeuralMinSumDecoder, NeuralOffsetMinSumDecoder
 from .rcq_decoder import RCQMinSumDecoder, WeightedRCQDecoder
 
 logger = logging.getLogger(__name__)
@@ -222,16 +222,17 @@ class LDPSimulator:
 
 
 def create_test_decoders(code: LDPCCode) -> Dict[str, Union[Callable, torch.nn.Module]]:
-    """The comparison set of simulation_framework.py:384-420 with its canonical parameters (the two
-    offset-min-sum entries are not built yet, SURVEY.md section 8f #1)."""
+    """The ten-decoder comparison set of simulation_framework.py:384-420 with its canonical parameters."""
     qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
     decoders: Dict[str, Union[Callable, torch.nn.Module]] = {
         'Basic MinSum': BasicMinSumDecoder(code, factor=0.7),
         'N-NMS': NeuralMinSumDecoder(code, max_iterations=10),
+        'N-OMS': NeuralOffsetMinSumDecoder(code, max_iterations=10),
     }
     for weight_type in (1, 2, 3, 4):
         decoders[f'N-2D-NMS Type {weight_type}'] = Neural2DMinSumDecoder(
             code, weight_sharing_type=weight_type, max_iterations=10)
+    decoders['N-2D-OMS Type 2'] = Neural2DOffsetMinSumDecoder(code, weight_sharing_type=2, max_iterations=10)
     decoders['RCQ MinSum'] = RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=qp, max_iterations=10)
     decoders['W-RCQ Type 2'] = WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=qp,
                                                   weight_sharing_type=2, max_iterations=10)

@@ -35,6 +35,8 @@ enum {
 };
 
 enum { LDPC_F32 = 0, LDPC_F64 = 1 };
+enum { LDPC_RULE_NORMALIZED = 0, LDPC_RULE_OFFSET = 1 };
+enum { LDPC_SCHEDULE_FLOODING = 0, LDPC_SCHEDULE_LAYERED = 1 };
 
 typedef struct ldpc_graph ldpc_graph;     /* Tanner graph re-laid-out on one device           */
 typedef struct ldpc_decoder ldpc_decoder; /* graph + weights + quantisers + device workspace  */
@@ -82,6 +84,12 @@ int ldpc_graph_slot_of_edge(const ldpc_graph *g, int32_t *slot_of_edge /* [E] */
  *   Neural2DMinSumDecoder     (neural_2d_decoder.py:16-225)    types 1-4 through beta_index / alpha_index
  *   RCQMinSumDecoder flooding (rcq_decoder.py:123-279)         bc > 0, no beta / alpha
  *   WeightedRCQDecoder        (rcq_decoder.py:352-597)         bc > 0 plus beta / alpha
+ *   NeuralOffsetMinSumDecoder   (neural_minsum_decoder.py:152-286) check_rule OFFSET, beta[T][E]
+ *   Neural2DOffsetMinSumDecoder (neural_2d_decoder.py:227-434)     check_rule OFFSET, types 1-4
+ *   RCQMinSumDecoder layered    (rcq_decoder.py:281-350)           schedule LAYERED: posteriors updated in
+ *        place, checks in index order, exactly as the reference executes it (its "subtract the previous
+ *        C2V" step subtracts zero on every graph with more than one non-empty check; a graph with a
+ *        single non-empty check is rejected with LDPC_ERR_UNSUPPORTED).  No beta / alpha.
  *
  * Arithmetic (verified against the reference):
  *   check node   raw_k = min2 if k == first-argmin else min1;  c2v = fl(fl(beta*raw) * sp)
@@ -99,6 +107,9 @@ typedef struct ldpc_decoder_config {
     int32_t n_alpha;         /* columns of alpha; 0 -> no alpha multiply (alpha == 1)            */
     int32_t bc;              /* 0: float c2v; 2..8: c2v stored as bc-bit sign-magnitude codes    */
     int32_t n_quantizers;    /* Q                                                                */
+    int32_t check_rule;      /* LDPC_RULE_NORMALIZED: c2v = beta*raw*sp;  LDPC_RULE_OFFSET:          */
+                             /*   c2v = sp*(relu(raw - beta) - alpha[variable]) and unweighted VN sums */
+    int32_t schedule;        /* LDPC_SCHEDULE_FLOODING | LDPC_SCHEDULE_LAYERED (RCQ only, see below) */
     const int32_t *beta_index;        /* [E] column of beta per edge (check-major); NULL -> 0    */
     const void *beta;                 /* [T][n_beta] of dtype                                    */
     const int32_t *alpha_index;       /* [n] column of alpha per variable; NULL -> 0             */

@@ -8,7 +8,7 @@ from typing import Optional
 import numpy as np
 
 from . import build as _build
-from .restatement import MODE_NMS, MODE_RCQ, MODE_WRCQ, OracleResult, SparseGraph  # noqa: F401
+from .restatement import MODE_NMS, MODE_OFFSET, MODE_RCQ, MODE_WRCQ, OracleResult, SparseGraph  # noqa: F401
 
 _lib = None
 
@@ -69,4 +69,27 @@ def decode(graph: SparseGraph, llr: np.ndarray, *, T: int, mode: int = MODE_NMS,
             C.c_int64(B), _p(llr), _p(bits), _p(post), _p(iters), _p(succ), C.c_int(nthreads))
     if rc != 0:
         raise MemoryError("oracle_decode failed")
+    return OracleResult(bits=bits, posterior=post, iterations=iters, success=succ.astype(bool))
+
+
+def decode_layered_rcq(graph: SparseGraph, llr: np.ndarray, *, T: int, bc: int, thresholds: np.ndarray,
+                       quantizer_of_iter: np.ndarray, nthreads: int = 1) -> OracleResult:
+    """Same contract as restatement.decode_layered_rcq."""
+    llr = np.ascontiguousarray(np.asarray(llr, dtype=np.float32))
+    if llr.ndim == 1:
+        llr = llr[None, :]
+    B, n = llr.shape
+    cp = np.ascontiguousarray(graph.check_ptr, dtype=np.int64)
+    cv = np.ascontiguousarray(graph.check_var, dtype=np.int32)
+    th = np.ascontiguousarray(thresholds, dtype=np.float32)
+    qi = np.ascontiguousarray(quantizer_of_iter, dtype=np.int32)
+    bits = np.zeros((B, n), dtype=np.uint8)
+    post = np.zeros((B, n), dtype=np.float32)
+    iters = np.zeros(B, dtype=np.int32)
+    succ = np.zeros(B, dtype=np.uint8)
+    rc = lib().oracle_decode_layered_rcq(C.c_int(n), C.c_int(graph.m), _p(cp), _p(cv), C.c_int(T), C.c_int(bc), _p(th),
+                                         _p(qi), C.c_int64(B), _p(llr), _p(bits), _p(post), _p(iters), _p(succ),
+                                         C.c_int(nthreads))
+    if rc != 0:
+        raise MemoryError("oracle_decode_layered_rcq failed")
     return OracleResult(bits=bits, posterior=post, iterations=iters, success=succ.astype(bool))

@@ -203,6 +203,8 @@ def dequantize(q: np.ndarray, thresholds_f32: np.ndarray, bc: int) -> np.ndarray
 MODE_NMS = 0    # c2v = (beta * raw) * sp            Basic / N-NMS / N-2D   (neural_2d_decoder.py:188-191)
 MODE_RCQ = 1    # c2v = Qinv(Q(sp * raw))            RCQ                    (rcq_decoder.py:242-246)
 MODE_WRCQ = 2   # c2v = Qinv(Q((beta * sp) * raw))   W-RCQ                  (rcq_decoder.py:559-563)
+MODE_OFFSET = 3 # c2v = sp * (relu(raw - beta) - alpha_j)   N-OMS / N-2D-OMS (neural_minsum_decoder.py:252-253,
+                #                                            neural_2d_decoder.py:400-401); VN sums are unweighted
 
 
 @dataclass
@@ -284,6 +286,12 @@ def decode(graph: SparseGraph, llr: np.ndarray, *, T: int, mode: int = MODE_NMS,
                 if mode == MODE_NMS:
                     b = dt.type(1.0) if beta is None else dt.type(beta[t, e])
                     val = (b * raw).astype(dt) * sp
+                elif mode == MODE_OFFSET:
+                    b = dt.type(0.0) if beta is None else dt.type(beta[t, e])
+                    off = np.maximum((raw - b).astype(dt), dt.type(0.0))          # F.relu(raw_msg - beta)
+                    if alpha is not None:
+                        off = (off - dt.type(alpha[t, int(cv[e])])).astype(dt)    # ... - alpha (2-D variant)
+                    val = sp * off
                 else:
                     if mode == MODE_RCQ:
                         x = (sp * raw).astype(np.float32)
@@ -309,7 +317,7 @@ def decode(graph: SparseGraph, llr: np.ndarray, *, T: int, mode: int = MODE_NMS,
             msgs = [c2v[int(e)] for e in es]
             for d in range(dv):
                 s = ssum([msgs[q] for q in range(dv) if q != d])
-                if alpha is not None:
+                if alpha is not None and mode != MODE_OFFSET:
                     s = (dt.type(alpha[t, j]) * s)
                 new_v2c[int(es[d])] = llrT[j] + s
             post[j] = llrT[j] + ssum(msgs)
@@ -363,3 +371,75 @@ def expand_2d_weights(graph: SparseGraph, weight_sharing_type: int, T: int, beta
             for j in range(graph.n):
                 alpha[t, j] = np.float32(alpha_fn(t, int(dvs[j])))
     return beta, alpha
+
+
+def decode_layered_rcq(graph: SparseGraph, llr: np.ndarray, *, T: int, bc: int, thresholds: np.ndarray,
+                       quantizer_of_iter: np.ndarray) -> OracleResult:
+    """RCQMinSumDecoder._decode_layered as the reference actually behaves (rcq_decoder.py:281-350,
+    SURVEY appendix C6): posteriors start at the LLRs; checks are visited in index order; the
+    "subtract the previous C2V" step always subtracts 0 because ``c2v_messages`` is re-created as zeros
+    inside the check loop (:323) -- except on a graph with a single non-empty check, where the previous
+    visit's row survives (that degenerate case is restated too); the quantised new C2V are ADDED to the
+    posteriors in place; the syndrome is tested once per iteration."""
+    llr = np.ascontiguousarray(np.asarray(llr, dtype=np.float32))
+    if llr.ndim == 1:
+        llr = llr[None, :]
+    B, n = llr.shape
+    cp, cv = graph.check_ptr, graph.check_var
+    m = graph.m
+    post = np.ascontiguousarray(llr.T).copy()           # [n, B]
+    done = np.zeros(B, dtype=bool)
+    iters = np.full(B, T, dtype=np.int32)
+    success = np.zeros(B, dtype=bool)
+    out_bits = (llr < 0).astype(np.uint8)
+    ar = np.arange(B)
+    nonempty = [i for i in range(m) if cp[i + 1] > cp[i]]
+    prev_check, prev_vals = None, None
+    chk_of_edge = graph.edge_check()
+    for t in range(T):
+        act = ~done
+        if not act.any():
+            break
+        th = np.asarray(thresholds[int(quantizer_of_iter[t])], dtype=np.float32)
+        newp = post.copy()
+        for i in nonempty:
+            e0, e1 = int(cp[i]), int(cp[i + 1])
+            vs = cv[e0:e1]
+            dc = e1 - e0
+            if prev_check == i:                          # only possible with one non-empty check
+                for k in range(dc):
+                    newp[vs[k]] = newp[vs[k]] - prev_vals[k]
+            inc = newp[vs]
+            signs = np.sign(inc)
+            mags = np.abs(inc)
+            k0 = np.argmin(mags, axis=0)
+            m1 = mags[k0, ar]
+            if dc > 1:
+                tmp = mags.copy()
+                tmp[k0, ar] = np.inf
+                m2 = tmp.min(axis=0)
+            else:
+                m2 = m1
+            vals = []
+            for k in range(dc):
+                sp = np.ones(B, dtype=np.float32)
+                for q in range(dc):
+                    if q != k:
+                        sp = sp * signs[q]
+                raw = np.where(k0 == k, m2, m1)
+                x = (sp * raw).astype(np.float32)
+                vals.append(dequantize(quantize(x, th, bc), th, bc))
+            for k in range(dc):
+                newp[vs[k]] = (newp[vs[k]] + vals[k]).astype(np.float32)
+            prev_check, prev_vals = i, vals
+        post = np.where(act[None, :], newp, post)
+        bits = (post < 0).astype(np.uint8)
+        par = np.zeros((m, B), dtype=np.int64)
+        np.add.at(par, chk_of_edge, bits[cv].astype(np.int64))
+        ok = ((par % 2).sum(axis=0) == 0)
+        out_bits[act] = bits.T[act]
+        newly = act & ok
+        iters[newly] = t + 1
+        success[newly] = True
+        done |= newly
+    return OracleResult(bits=out_bits, posterior=post.T.copy(), iterations=iters, success=success)

@@ -159,3 +159,39 @@ def test_python_and_c_oracles_agree_on_irregular_random_code():
     a = R.decode(G, llr, T=T, beta=beta, alpha=alpha, early_stop=False)
     b = OC.decode(G, llr, T=T, beta=beta, alpha=alpha, early_stop=False)
     assert np.array_equal(a.bits, b.bits) and (b.iterations == T).all() and np.array_equal(a.success, b.success)
+
+
+# ---- SURVEY 8f "next" rows: offset min-sum and layered RCQ (tests/golden/*_next.npz) ----
+def next_cases():
+    import glob
+    import os
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*_next.npz"))):
+        stem = os.path.splitext(os.path.basename(f))[0]
+        z = np.load(f)
+        out += [(stem, c) for c in sorted(set(k.split("/")[0] for k in z.files))]
+    return out
+
+
+def oracle_run_next(impl, g: Golden):
+    G = R.SparseGraph.from_dense(g["H"])
+    T = int(g["T"])
+    if g.kind == "rcq_layered":
+        th = g["thresholds"].astype(np.float32)
+        return impl.decode_layered_rcq(G, g["llr"], T=T, bc=int(g["bc"]), thresholds=th,
+                                       quantizer_of_iter=R.quantizer_schedule(T, th.shape[0]))
+    alpha = g["alpha_var"] if g.kind == "n2doms" else None
+    return impl.decode(G, g["llr"], T=T, mode=R.MODE_OFFSET, beta=g["beta_edge"], alpha=alpha)
+
+
+@pytest.mark.parametrize("stem,case", next_cases())
+@pytest.mark.parametrize("impl", [R, OC], ids=["python", "c"])
+def test_next_rows_match_live_reference(stem, case, impl):
+    g = Golden(stem, case)
+    res = oracle_run_next(impl, g)
+    assert np.array_equal(res.bits, g["bits"])
+    assert np.array_equal(res.iterations, g["iterations"])
+    if "posterior" in g:
+        assert np.array_equal(res.posterior, g["posterior"])
+    if "success" in g:
+        assert np.array_equal(res.success, g["success"])
