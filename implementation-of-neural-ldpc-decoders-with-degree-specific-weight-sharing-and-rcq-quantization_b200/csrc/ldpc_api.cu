@@ -570,8 +570,8 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
 int emit_outputs(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, uint8_t* bits, void* post, int32_t* iters,
                  uint8_t* success, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
-    if (bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, bits, B, g->n, stream));
-    if (post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, post, B, Bp, g->n, stream));
+    if (bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, bits, B, g->n, nullptr, stream));
+    if (post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, post, B, Bp, g->n, nullptr, stream));
     if (iters) CU(cudaMemcpyAsync(iters, ws.iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     if (success) CU(cudaMemcpyAsync(success, ws.success, (size_t)B, cudaMemcpyDeviceToDevice, stream));
     return LDPC_OK;
@@ -875,7 +875,7 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     rc = run_iterations(d, ws, B, Bp, false, stream);
     if (rc) return rc;
     LAUNCH(K_OTHER, launch_count_packed(d->V, ws.hardw, Bp / 32, d->g->n, B, codeword, ws.iters, counters,
-                                        frame_bit_errors, frame_iterations, stream));
+                                        frame_bit_errors, frame_iterations, nullptr, nullptr, stream));
     return LDPC_OK;
 }
 

@@ -93,11 +93,12 @@ cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64
 cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, uint32_t* unsat2,
                                int64_t B, int64_t Bp, int32_t T, cudaStream_t stream);
 // hardw -> bits [B][n] uint8
+// `map` (may be nullptr): output row of local frame f is map[f] (frames of a re-decode level)
 cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B,
-                               int32_t n, cudaStream_t stream);
+                               int32_t n, const int32_t* map, cudaStream_t stream);
 // postT [n][Bp] -> post [B][n]
 cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp,
-                               int32_t n, cudaStream_t stream);
+                               int32_t n, const int32_t* map, cudaStream_t stream);
 cudaError_t launch_copy_frames(const int32_t* iters_src, const uint8_t* succ_src, int32_t* iters_dst,
                                uint8_t* succ_dst, int64_t B, cudaStream_t stream);
 // AWGN LLRs.  row_major != 0: out is float [B][n]; else out is Real [n][Bp] of `dtype`.
@@ -107,7 +108,16 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
 // counters += {frame_errors, bit_errors, total_iterations, total_frames}
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B,
                                 const uint8_t* codeword, const int32_t* iters, int64_t* counters,
-                                int32_t* frame_bit_errors, int32_t* frame_iters, cudaStream_t stream);
+                                int32_t* frame_bit_errors, int32_t* frame_iters, const int32_t* map,
+                                const uint8_t* skip, cudaStream_t stream);
+// re-decode level bookkeeping
+cudaError_t launch_count_pending(const uint8_t* done, int64_t Bp, int32_t* out, cudaStream_t stream);
+cudaError_t launch_mark_retry(const uint8_t* done, uint8_t* retry, int64_t Bp, cudaStream_t stream);
+cudaError_t launch_gather_cols(int dtype, const void* src, int64_t Bp_src, void* dst, int64_t Bp_dst, const int32_t* idx,
+                               int64_t count, int32_t n, cudaStream_t stream);
+cudaError_t launch_scatter_frames(const int32_t* iters_src, const uint8_t* succ_src, int32_t* iters_dst, uint8_t* succ_dst,
+                                  const int32_t* map, int64_t count, cudaStream_t stream);
+cudaError_t launch_compose_map(const int32_t* idx, const int32_t* parent_map, int32_t* out, int64_t count, cudaStream_t stream);
 cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const uint8_t* codeword,
                               const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
                               cudaStream_t stream);

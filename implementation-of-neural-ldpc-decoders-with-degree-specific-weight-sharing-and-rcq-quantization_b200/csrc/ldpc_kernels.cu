@@ -872,7 +872,7 @@ __global__ void pack_kernel(const Real* __restrict__ llr, Real* __restrict__ llr
 
 template <typename Real>
 __global__ void unpack_post_kernel(const Real* __restrict__ postT, Real* __restrict__ post, int64_t B, int64_t Bp,
-                                   int32_t n) {
+                                   int32_t n, const int32_t* __restrict__ map) {
     __shared__ Real tile[32][33];
     const int64_t f_base = (int64_t)blockIdx.x * 32;
     const int32_t j_base = blockIdx.y * 32;
@@ -885,13 +885,13 @@ __global__ void unpack_post_kernel(const Real* __restrict__ postT, Real* __restr
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int64_t f = f_base + r;
         int32_t j = j_base + threadIdx.x;
-        if (f < B && j < n) post[f * n + j] = tile[threadIdx.x][r];
+        if (f < B && j < n) post[(map ? (int64_t)map[f] : f) * n + j] = tile[threadIdx.x][r];
     }
 }
 
 // One warp: one hard word (32 frames) x 32 variables per step.
 __global__ void unpack_bits_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, uint8_t* __restrict__ bits,
-                                   int64_t B, int32_t n) {
+                                   int64_t B, int32_t n, const int32_t* __restrict__ map) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= Wn) return;
@@ -899,7 +899,7 @@ __global__ void unpack_bits_kernel(int V, const uint32_t* __restrict__ hardw, in
     const uint32_t word = (j < n) ? __ldg(hardw + (int64_t)j * Wn + w) : 0u;
     for (int b = 0; b < 32; ++b) {
         int64_t f = wordbit_to_frame(w, b, V);
-        if (f < B && j < n) bits[f * n + j] = (uint8_t)((word >> b) & 1u);
+        if (f < B && j < n) bits[(map ? (int64_t)map[f] : f) * n + j] = (uint8_t)((word >> b) & 1u);
     }
 }
 
@@ -995,7 +995,8 @@ __device__ __forceinline__ void accumulate_counters(int64_t* counters, int ferr,
 __global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, int32_t n, int64_t B,
                                     const uint8_t* __restrict__ codeword, const int32_t* __restrict__ iters,
                                     int64_t* counters, int32_t* __restrict__ frame_bit_errors,
-                                    int32_t* __restrict__ frame_iters) {
+                                    int32_t* __restrict__ frame_iters, const int32_t* __restrict__ map,
+                                    const uint8_t* __restrict__ skip) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= Wn) return;
@@ -1007,11 +1008,12 @@ __global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, i
         cnt += (int)bit;
     }
     const int64_t f = wordbit_to_frame(w, lane, V);
-    const int valid = f < B;
+    const int valid = f < B && !(skip && skip[f]);   // frames handed to a re-decode level are counted there
     const int it = valid ? iters[f] : 0;
     if (valid) {
-        if (frame_bit_errors) frame_bit_errors[f] = cnt;
-        if (frame_iters) frame_iters[f] = it;
+        const int64_t fo = map ? (int64_t)map[f] : f;
+        if (frame_bit_errors) frame_bit_errors[fo] = cnt;
+        if (frame_iters) frame_iters[fo] = it;
     }
     accumulate_counters(counters, valid && cnt > 0, valid ? cnt : 0, it, valid);
 }
@@ -1039,6 +1041,49 @@ __global__ void count_bits_kernel(const uint8_t* __restrict__ bits, int32_t n, i
         if (iters) atomicAdd(c + 2, (unsigned long long)iters[f]);
         atomicAdd(c + 3, 1ull);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Re-decode levels ("early stop at scale"): frames still running at a checkpoint are
+// handed to a smaller, dense batch that is decoded from scratch (the decode is a pure function of the
+// frame's LLRs, so the results are identical); these kernels do the bookkeeping.
+// ---------------------------------------------------------------------------------------------
+__global__ void count_pending_kernel(const uint8_t* __restrict__ done, int64_t Bp, int32_t* __restrict__ out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pend = (f < Bp) ? (done[f] == 0) : 0;
+    const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)pend);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (int32_t)c);
+}
+
+__global__ void mark_retry_kernel(const uint8_t* __restrict__ done, uint8_t* __restrict__ retry, int64_t Bp) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < Bp) retry[f] = done[f] == 0;
+}
+
+// dst[j][i] = src[j][idx[i]] for i < count, 0 for the pad frames
+template <typename Real>
+__global__ void gather_cols_kernel(const Real* __restrict__ src, int64_t Bp_src, Real* __restrict__ dst, int64_t Bp_dst,
+                                   const int32_t* __restrict__ idx, int64_t count, int32_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t j = blockIdx.y;
+    if (i >= Bp_dst || j >= n) return;
+    dst[(int64_t)j * Bp_dst + i] = (i < count) ? src[(int64_t)j * Bp_src + idx[i]] : Real(0);
+}
+
+__global__ void scatter_frames_kernel(const int32_t* __restrict__ iters_src, const uint8_t* __restrict__ succ_src,
+                                      int32_t* __restrict__ iters_dst, uint8_t* __restrict__ succ_dst,
+                                      const int32_t* __restrict__ map, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t f = map ? (int64_t)map[i] : i;
+    if (iters_dst) iters_dst[f] = iters_src[i];
+    if (succ_dst) succ_dst[f] = succ_src[i];
+}
+
+__global__ void compose_map_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ parent_map,
+                                   int32_t* __restrict__ out, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = parent_map ? parent_map[idx[i]] : idx[i];
 }
 
 inline int threads_for(int64_t Bp, int V) {
@@ -1168,19 +1213,19 @@ cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64
 }
 
 cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B, int32_t n,
-                               cudaStream_t stream) {
+                               const int32_t* map, cudaStream_t stream) {
     const int warps = 8;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((Wn + warps - 1) / warps));
-    unpack_bits_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, bits, B, n);
+    unpack_bits_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, bits, B, n, map);
     return cudaGetLastError();
 }
 
 cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp, int32_t n,
-                               cudaStream_t stream) {
+                               const int32_t* map, cudaStream_t stream) {
     dim3 block(32, 8);
     dim3 grid((unsigned)((B + 31) / 32), (unsigned)((n + 31) / 32));
-    if (dtype == 0) unpack_post_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n);
-    else unpack_post_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n);
+    if (dtype == 0) unpack_post_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n, map);
+    else unpack_post_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n, map);
     return cudaGetLastError();
 }
 
@@ -1202,10 +1247,10 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
 
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B, const uint8_t* codeword,
                                 const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
-                                int32_t* frame_iters, cudaStream_t stream) {
+                                int32_t* frame_iters, const int32_t* map, const uint8_t* skip, cudaStream_t stream) {
     const int warps = 4;
     count_packed_kernel<<<(unsigned)((Wn + warps - 1) / warps), warps * 32, 0, stream>>>(
-        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters);
+        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters, map, skip);
     return cudaGetLastError();
 }
 
@@ -1214,6 +1259,37 @@ cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const u
     const int warps = 8;
     count_bits_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, stream>>>(bits, n, B, codeword, iters,
                                                                                        counters, frame_bit_errors);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_pending(const uint8_t* done, int64_t Bp, int32_t* out, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+    count_pending_kernel<<<(unsigned)((Bp + 255) / 256), 256, 0, stream>>>(done, Bp, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mark_retry(const uint8_t* done, uint8_t* retry, int64_t Bp, cudaStream_t stream) {
+    mark_retry_kernel<<<(unsigned)((Bp + 255) / 256), 256, 0, stream>>>(done, retry, Bp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_cols(int dtype, const void* src, int64_t Bp_src, void* dst, int64_t Bp_dst, const int32_t* idx,
+                               int64_t count, int32_t n, cudaStream_t stream) {
+    dim3 grid((unsigned)((Bp_dst + 255) / 256), (unsigned)n);
+    if (dtype == 0) gather_cols_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), Bp_src, static_cast<float*>(dst), Bp_dst, idx, count, n);
+    else gather_cols_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(src), Bp_src, static_cast<double*>(dst), Bp_dst, idx, count, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_frames(const int32_t* iters_src, const uint8_t* succ_src, int32_t* iters_dst, uint8_t* succ_dst,
+                                  const int32_t* map, int64_t count, cudaStream_t stream) {
+    scatter_frames_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(iters_src, succ_src, iters_dst, succ_dst, map, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compose_map(const int32_t* idx, const int32_t* parent_map, int32_t* out, int64_t count, cudaStream_t stream) {
+    compose_map_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(idx, parent_map, out, count);
     return cudaGetLastError();
 }
 
