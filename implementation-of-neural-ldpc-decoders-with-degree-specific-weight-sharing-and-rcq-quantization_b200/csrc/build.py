@@ -41,6 +41,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_variant(name: str, defines: list) -> str:
+    """Tuning builds (kernel-geometry A/B on the GPU box): <repo>/tuning/libldpc_b200_<name>.so, selected
+    at run time with LDPC_B200_LIB=<path>.  Not used by the product path."""
+    outdir = os.path.join(os.path.dirname(PKG), "tuning")
+    os.makedirs(outdir, exist_ok=True)
+    out = os.path.join(outdir, f"libldpc_b200_{name}.so")
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SOURCES
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     import sys
-    print(build(force=True, verbose="-v" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":      # build.py variant NAME DEF1=V1 DEF2=V2 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force=True, verbose="-v" in sys.argv))

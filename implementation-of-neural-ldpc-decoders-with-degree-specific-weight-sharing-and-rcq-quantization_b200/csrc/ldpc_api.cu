@@ -83,6 +83,7 @@ struct ldpc_graph {
     std::vector<int64_t> chk_ptr;        // original CSR (layered schedule walks checks in index order)
     std::vector<int32_t> chk_var;
     int nonempty_checks = 0;
+    int cn_wide_begin = 0, cn_wide_end = 0;   // cn_items [begin, end): check degree 9..64
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
@@ -199,6 +200,12 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             pos = end;
         }
     }
+    g->cn_wide_begin = g->cn_wide_end = (int)g->cn_items.size();
+    for (size_t i = 0; i < g->cn_items.size(); ++i) {
+        if (g->cn_items[i].deg > 8 && g->cn_wide_begin == (int)g->cn_items.size()) g->cn_wide_begin = (int)i;
+        if (g->cn_items[i].deg > 64) { g->cn_wide_end = (int)i; break; }
+    }
+    if (g->cn_wide_end < g->cn_wide_begin) g->cn_wide_begin = g->cn_wide_end;   // no degree in 9..64
     // ---- variable side: stable sort by degree; slot lists in ascending check index ----
     std::vector<int32_t> vorder(n);
     for (int32_t j = 0; j < n; ++j) vorder[j] = j;
@@ -375,6 +382,7 @@ struct ldpc_decoder {
     int32_t* d_aidx = nullptr;             // per vpos
     int32_t* d_aidx_slot = nullptr;        // per slot (offset rule: alpha is applied at the check node)
     int check_rule = 0, schedule = 0;
+    int wide_ring = 1;                     // checks of degree 9..64 through the bulk-async row ring
     void* d_beta = nullptr;                // [T][n_beta]
     void* d_alpha = nullptr;               // [T][n_alpha]
     float* d_thr = nullptr;                // [Q][nth]
@@ -513,6 +521,9 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
         cn.done = ws.done;
         cn.items = g->d_cn_items;
         cn.n_items = (int)g->cn_items.size();
+        cn.items_wide_begin = g->cn_wide_begin;
+        cn.items_wide_end = g->cn_wide_end;
+        cn.wide_ring = d->wide_ring;
         cn.Bp = Bp;
         if (d->check_rule == LDPC_RULE_OFFSET) {
             cn.aidx_slot = d->d_aidx_slot;
@@ -651,6 +662,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->check_rule = cfg->check_rule;
     d->schedule = cfg->schedule;
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
+    if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
 
     DeviceGuard guard(g->device);
     if (!guard.ok) {

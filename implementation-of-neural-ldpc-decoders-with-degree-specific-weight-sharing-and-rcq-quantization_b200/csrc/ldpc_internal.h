@@ -36,6 +36,9 @@ struct CnLaunch {
     const uint8_t* done;        // [Bp]
     const WorkItem* items;
     int n_items;
+    int items_wide_begin;       // items [begin, end) hold checks of degree 9..64 (sorted by degree)
+    int items_wide_end;
+    int wide_ring;              // 1: those items run in the bulk-async row-ring kernel
     int64_t Bp;
 };
 

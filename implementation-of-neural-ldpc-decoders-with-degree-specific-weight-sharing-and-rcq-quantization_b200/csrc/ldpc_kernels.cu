@@ -330,7 +330,7 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
 }
 
 template <typename Real, bool QUANT, int NTH>
-__global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const int nfb) {
+__global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     __shared__ float s_thr[kMaxQuantLevels];
     Quantizer<NTH> qz;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
         qz.load(s_thr, p.nth, p.mono != 0);
     }
     const int fb = blockIdx.x % nfb;
-    const int item_id = blockIdx.x / nfb;
+    const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;  // whole warps: Bp is a multiple of 32*V
     const uint32_t dmask = load_done_mask<V>(p.done, f0);
@@ -371,6 +371,253 @@ __global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const in
             }
     }
 #undef LDPC_CN_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide checks (degree 9..64): bulk-async row ring.
+//
+// A register-staged streaming loop keeps only a handful of 16-byte loads per thread in flight and none at
+// all while a check's outputs are written, so wide checks ran latency-bound (long_scoreboard, ~0.6 of the
+// HBM roofline).  Here the rows of a work item -- `count * deg` CONSECUTIVE message rows, one contiguous
+// segment of `blockDim.x * 16` bytes each for this CTA's frames -- are streamed into a shared-memory ring
+// by the copy engine (cp.async.bulk + mbarrier transaction counts, SASS UBLKCP), kWideSlabs - 1 slabs of
+// kWideRows rows ahead of the arithmetic, across check boundaries and across the output phase.  A thread
+// reads its own 16-byte column of each row (conflict-free LDS.128), so registers hold only the running
+// min1 / min2 / first-argmin / parity and one sign bit per edge.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWideThreads = 128;
+#ifndef LDPC_WIDE_ROWS
+#define LDPC_WIDE_ROWS 4
+#endif
+#ifndef LDPC_WIDE_SLABS
+#define LDPC_WIDE_SLABS 4
+#endif
+#ifndef LDPC_WIDE_MINCTAS
+#define LDPC_WIDE_MINCTAS 6
+#endif
+constexpr int kWideRows = LDPC_WIDE_ROWS;     // rows per slab
+constexpr int kWideSlabs = LDPC_WIDE_SLABS;   // slabs in the ring
+constexpr int kWideMinCtas = LDPC_WIDE_MINCTAS;
+constexpr int kWideRowBytes = kWideThreads * 16;
+constexpr size_t kWideSmem = (size_t)kWideSlabs * kWideRows * kWideRowBytes;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_addr(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16); completes `bytes` on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+
+template <typename MaskT> struct SignMask;
+template <> struct SignMask<uint32_t> {
+    static __device__ __forceinline__ uint32_t push(uint32_t m, uint32_t signword) { return __funnelshift_l(signword, m, 1); }
+    static __device__ __forceinline__ uint32_t align(uint32_t m, int dc) { return m << (32 - dc); }
+    static __device__ __forceinline__ uint32_t top(uint32_t m) { return m & 0x80000000u; }
+};
+template <> struct SignMask<uint64_t> {
+    static __device__ __forceinline__ uint64_t push(uint64_t m, uint32_t signword) { return (m << 1) | (uint64_t)(signword >> 31); }
+    static __device__ __forceinline__ uint64_t align(uint64_t m, int dc) { return m << (64 - dc); }
+    static __device__ __forceinline__ uint32_t top(uint64_t m) { return (uint32_t)(m >> 32) & 0x80000000u; }
+};
+
+// The ring as seen by one thread.  A check occupies ceil(deg / kWideRows) consecutive slabs (its last slab
+// may hold fewer rows), so slab boundaries never fall inside the unrolled row loop.  All threads of the CTA
+// walk the slabs in lockstep: acquire(), read rows, release().
+template <typename Real>
+struct RowRing {
+    static constexpr int V = FramesPerLane<Real>::value;
+    unsigned char* smem;
+    uint64_t* bars;
+    const Real* src;
+    const int32_t* row_map;
+    int64_t Bp, cta_f0;
+    int64_t first_row;
+    int deg, slabs_per_check, slabs_total;
+    uint32_t row_bytes;
+    uint64_t policy;
+    int g;  // slabs consumed so far
+
+    __device__ __forceinline__ int rows_in(int s) const { return min(kWideRows, deg - s * kWideRows); }
+    // warp 0: arm the barrier, then one lane per row issues its copy
+    __device__ __forceinline__ void issue(int slab) {
+        if (threadIdx.x < 32) {
+            const int buf = slab % kWideSlabs;
+            const int c = slab / slabs_per_check, s = slab - c * slabs_per_check;
+            const int nrows = rows_in(s);
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(bars + buf, (uint32_t)nrows * row_bytes);
+            __syncwarp();
+            if ((int)threadIdx.x < nrows) {
+                const int64_t slot = first_row + (int64_t)c * deg + s * kWideRows + threadIdx.x;
+                const int64_t row = row_map ? (int64_t)__ldg(row_map + slot) : slot;
+                bulk_g2s(smem + (size_t)(buf * kWideRows + threadIdx.x) * kWideRowBytes, src + row * Bp + cta_f0, row_bytes,
+                         bars + buf, policy);
+            }
+        }
+    }
+    __device__ __forceinline__ void start() {
+        g = 0;
+        for (int s = 0; s < kWideSlabs && s < slabs_total; ++s) issue(s);
+    }
+    // wait until the current slab has landed; returns this thread's column of its first row
+    __device__ __forceinline__ const unsigned char* acquire(bool active) {
+        const int buf = g % kWideSlabs;
+        if (active) mbar_wait(bars + buf, (uint32_t)(g / kWideSlabs) & 1u);
+        return smem + (size_t)buf * kWideRows * kWideRowBytes + threadIdx.x * 16;
+    }
+    // every warp is through with the current slab: refill its buffer with the slab kWideSlabs ahead
+    __device__ __forceinline__ void release() {
+        __syncthreads();
+        if (g + kWideSlabs < slabs_total) issue(g + kWideSlabs);
+        ++g;
+    }
+};
+
+template <typename Real, bool QUANT, int NTH, typename MaskT>
+__device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& ring, int64_t slot0, int dc, int64_t f0,
+                                              uint32_t dmask, bool active, const Quantizer<NTH>& qz) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using OutT = typename CnOut<Real, QUANT>::type;
+    const bool has_beta = p.beta_t != nullptr;
+    MinState<Real, true> st[V];
+    MaskT neg[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        st[v].init();
+        neg[v] = 0;
+    }
+    for (int s = 0, k0 = 0; s < ring.slabs_per_check; ++s, k0 += kWideRows) {
+        const unsigned char* col = ring.acquire(active);
+        if (active) {
+            if (k0 + kWideRows <= dc) {
+#pragma unroll
+                for (int q = 0; q < kWideRows; ++q) {
+                    const Pack<Real, V> x = *reinterpret_cast<const Pack<Real, V>*>(col + q * kWideRowBytes);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        st[v].push(x.v[v], k0 + q);
+                        neg[v] = SignMask<MaskT>::push(neg[v], Arith<Real>::hi(x.v[v]));
+                    }
+                }
+            } else {
+                for (int q = 0; q < dc - k0; ++q) {
+                    const Pack<Real, V> x = *reinterpret_cast<const Pack<Real, V>*>(col + q * kWideRowBytes);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        st[v].push(x.v[v], k0 + q);
+                        neg[v] = SignMask<MaskT>::push(neg[v], Arith<Real>::hi(x.v[v]));
+                    }
+                }
+            }
+        }
+        ring.release();
+    }
+    if (!active) return;
+    CheckOut<Real, QUANT> co[V];
+    if (!p.beta_per_edge) {
+        Real beta = Real(1);
+        if (has_beta) beta = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+#pragma unroll
+        for (int v = 0; v < V; ++v) co[v].prepare(st[v].m1, st[v].m2, st[v].par, beta, has_beta, qz, p.bc);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) neg[v] = SignMask<MaskT>::align(neg[v], dc);  // top bit = sign of edge 0
+    OutT* __restrict__ out_row = static_cast<OutT*>(p.dst) + slot0 * p.Bp + f0;
+#pragma unroll 4
+    for (int k = 0; k < dc; ++k, out_row += p.Bp) {
+        Real beta = Real(1);
+        if (p.beta_per_edge) beta = __ldg(static_cast<const Real*>(p.beta_t) + __ldg(p.bidx + slot0 + k));
+        Pack<OutT, V> out;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint32_t sb = SignMask<MaskT>::top(neg[v]);
+            neg[v] <<= 1;
+            if (!p.beta_per_edge) {
+                out.v[v] = co[v].emit(k == st[v].k0, sb);
+            } else {
+                Real raw = (k == st[v].k0) ? st[v].m2 : st[v].m1;
+                out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
+            }
+        }
+        store_masked<OutT, V>(out_row, out, dmask);
+    }
+}
+
+template <typename Real, bool QUANT, int NTH>
+__global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
+    constexpr int V = FramesPerLane<Real>::value;
+    extern __shared__ __align__(128) unsigned char wide_smem[];
+    __shared__ __align__(8) uint64_t bars[kWideSlabs];
+    __shared__ float s_thr[kMaxQuantLevels];
+    Quantizer<NTH> qz;
+    if (QUANT) {
+        for (int i = threadIdx.x; i < p.nth; i += blockDim.x) s_thr[i] = p.thr[i];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kWideSlabs; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const int fb = blockIdx.x % nfb;
+    const int item_id = item0 + blockIdx.x / nfb;
+    const int64_t cta_f0 = (int64_t)fb * kWideThreads * V;
+    const int64_t f0 = cta_f0 + (int64_t)threadIdx.x * V;
+    uint32_t dmask = (1u << V) - 1u;
+    if (f0 < p.Bp) dmask = load_done_mask<V>(p.done, f0);
+    const bool active = !__all_sync(0xffffffffu, dmask == ((1u << V) - 1u));   // warp-uniform
+    if (!__syncthreads_or(active ? 1 : 0)) return;   // also publishes the barriers and s_thr
+    if (QUANT) qz.load(s_thr, p.nth, p.mono != 0);
+    const WorkItem it = p.items[item_id];
+    RowRing<Real> ring;
+    ring.smem = wide_smem;
+    ring.bars = bars;
+    ring.src = static_cast<const Real*>(p.src);
+    ring.row_map = p.row_map;
+    ring.Bp = p.Bp;
+    ring.cta_f0 = cta_f0;
+    ring.first_row = it.first_slot;
+    ring.deg = it.deg;
+    ring.slabs_per_check = (it.deg + kWideRows - 1) / kWideRows;
+    ring.slabs_total = ring.slabs_per_check * it.count;
+    const int64_t cta_frames = min((int64_t)kWideThreads * V, p.Bp - cta_f0);
+    ring.row_bytes = (uint32_t)(cta_frames * (int64_t)sizeof(Real));
+    ring.policy = l2_evict_first_policy();
+    ring.start();
+    int64_t slot = it.first_slot;
+    if (it.deg <= 32) {
+        for (int c = 0; c < it.count; ++c, slot += it.deg)
+            cn_wide_check<Real, QUANT, NTH, uint32_t>(p, ring, slot, it.deg, f0, dmask, active, qz);
+    } else {
+        for (int c = 0; c < it.count; ++c, slot += it.deg)
+            cn_wide_check<Real, QUANT, NTH, uint64_t>(p, ring, slot, it.deg, f0, dmask, active, qz);
+    }
 }
 
 // One 32-bit word per (variable, V-th frame of 32 lanes): bit = lane.
@@ -1098,28 +1345,55 @@ inline int threads_for(int64_t Bp, int V) {
 // ---------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+template <typename Real, bool QUANT, int NTH>
+cudaError_t launch_cn_range(const CnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
+    if (item1 <= item0) return cudaSuccess;
+    constexpr int V = FramesPerLane<Real>::value;
+    if (wide) {
+        // per device and cheap, so simply repeated on every launch
+        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, QUANT, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kWideSmem);
+        if (e != cudaSuccess) return e;
+        const int64_t nfb = (p.Bp + (int64_t)kWideThreads * V - 1) / ((int64_t)kWideThreads * V);
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        cn_wide_kernel<Real, QUANT, NTH><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
+    } else {
+        const int threads = threads_for(p.Bp, V);
+        const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        cn_kernel<Real, QUANT, NTH><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
+    }
+    return cudaGetLastError();
+}
+
+template <typename Real, bool QUANT, int NTH>
+cudaError_t launch_cn_all(const CnLaunch& p, cudaStream_t stream) {
+    // items are sorted by degree: [0, wide0) degree <= 8, [wide0, wide1) degree 9..64 (row ring), rest > 64
+    const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
+    cudaError_t e = launch_cn_range<Real, QUANT, NTH>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide1, p.n_items, false, stream);
+    return e;
+}
+
+}  // namespace
+
 cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
     if (p.n_items == 0) return cudaSuccess;
-    const int V = dtype == 0 ? 4 : 2;
-    const int threads = threads_for(p.Bp, V);
-    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
-    const int64_t grid = nfb * p.n_items;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const unsigned g = (unsigned)grid;
-    const int nf = (int)nfb;
     if (dtype == 0) {
         if (p.nth > 0) {
             // register-resident thresholds need a non-decreasing table (count == last index reached)
-            if (p.mono && p.nth <= 4) cn_kernel<float, true, 4><<<g, threads, 0, stream>>>(p, nf);
-            else if (p.mono && p.nth <= 8) cn_kernel<float, true, 8><<<g, threads, 0, stream>>>(p, nf);
-            else cn_kernel<float, true, 0><<<g, threads, 0, stream>>>(p, nf);
-        } else {
-            cn_kernel<float, false, 0><<<g, threads, 0, stream>>>(p, nf);
+            if (p.mono && p.nth <= 4) return launch_cn_all<float, true, 4>(p, stream);
+            if (p.mono && p.nth <= 8) return launch_cn_all<float, true, 8>(p, stream);
+            return launch_cn_all<float, true, 0>(p, stream);
         }
-    } else {
-        cn_kernel<double, false, 0><<<g, threads, 0, stream>>>(p, nf);
+        return launch_cn_all<float, false, 0>(p, stream);
     }
-    return cudaGetLastError();
+    return launch_cn_all<double, false, 0>(p, stream);
 }
 
 cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
