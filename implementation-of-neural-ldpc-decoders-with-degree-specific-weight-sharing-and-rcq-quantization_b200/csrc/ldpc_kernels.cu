@@ -171,6 +171,53 @@ struct CheckOut {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Byte-parallel (SWAR) assembly of RCQ codes: one 32-bit word holds the codes of a lane's four frames, so
+// selecting between the check's two magnitudes, applying the sign and packing the store cost a few
+// LOP3/PRMT per EDGE instead of per edge and frame.  prmt's sign-replicate mode (selector nibble | 8) turns
+// the top bit of a byte into 0x00 / 0xFF.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// byte v of the result = low byte of w[v]
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return prmt(prmt(w0, w1, 0x0040u), prmt(w2, w3, 0x0040u), 0x5410u);
+}
+// byte v of the result = byte `b` (0..3) of w[v]
+__device__ __forceinline__ uint32_t pack_bytes_at(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t b) {
+    const uint32_t sel = b | ((b + 4u) << 4);
+    return prmt(prmt(w0, w1, sel), prmt(w2, w3, sel), 0x5410u);
+}
+// byte v of the result = 0xFF if bit 31 of w[v] is set, else 0x00
+__device__ __forceinline__ uint32_t pack_sign_masks(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return prmt(prmt(w0, w1, 0x00FBu), prmt(w2, w3, 0x00FBu), 0x5410u);
+}
+// every byte -> 0xFF if its top bit is set, else 0x00
+__device__ __forceinline__ uint32_t spread_byte_signs(uint32_t w) { return prmt(w, 0u, 0xBA98u); }
+
+// The four frames' CheckOut of one check, byte-packed (RCQ, one beta per check).
+struct CheckOut4 {
+    uint32_t CA, CB;   // magnitude index of the non-minimum / minimum edges
+    uint32_t MA, MB;   // sign-bit mask (1 << (bc-1), or 0 where the value is +-0)
+    uint32_t PAR;      // 0xFF where the product of ALL input signs (and beta's) is negative
+    __device__ __forceinline__ void pack(const CheckOut<float, true> (&co)[4]) {
+        CA = pack_low_bytes(co[0].ia, co[1].ia, co[2].ia, co[3].ia);
+        CB = pack_low_bytes(co[0].ib, co[1].ib, co[2].ib, co[3].ib);
+        MA = pack_low_bytes(co[0].ma, co[1].ma, co[2].ma, co[3].ma);
+        MB = pack_low_bytes(co[0].mb, co[1].mb, co[2].mb, co[3].mb);
+        PAR = pack_sign_masks(co[0].par, co[1].par, co[2].par, co[3].par);
+    }
+    // min4: 0xFF where this edge carries the frame's minimum; neg4: 0xFF where the output is negative
+    __device__ __forceinline__ uint32_t emit(uint32_t min4, uint32_t neg4) const {
+        const uint32_t idx = (CB & min4) | (CA & ~min4);
+        const uint32_t msk = (MB & min4) | (MA & ~min4);
+        return idx | (neg4 & msk);
+    }
+};
+
 template <typename Real, bool QUANT, int NTH, int DC>
 __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask,
                                                const Quantizer<NTH>& qz) {
@@ -186,6 +233,42 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
         x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
     }
     Pack<OutT, V> out[DC];
+    if constexpr (QUANT && V == 4) {
+        if (!p.beta_per_edge) {
+            // byte-parallel output phase (see CheckOut4): per edge a few LOP3/PRMT for all four frames
+            float beta = 1.f;
+            if (has_beta) beta = __ldg(static_cast<const float*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+            CheckOut<float, true> co[4];
+            uint32_t nm1[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                MinState<float, false> st;
+                st.init();
+#pragma unroll
+                for (int k = 0; k < DC; ++k) st.push(x[k].v[v], k);
+                if (DC == 1) st.m2 = st.m1;
+                co[v].prepare(st.m1, st.m2, st.par, beta, has_beta, qz, p.bc);
+                nm1[v] = ~__float_as_uint(st.m1);
+            }
+            CheckOut4 c4;
+            c4.pack(co);
+#pragma unroll
+            for (int k = 0; k < DC; ++k) {
+                uint32_t xb[4], eq[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    xb[v] = __float_as_uint(x[k].v[v]);
+                    eq[v] = (xb[v] & 0x7fffffffu) + nm1[v];   // |x| - m1 - 1: negative iff |x| == m1 (|x| >= m1)
+                }
+                const uint32_t min4 = pack_sign_masks(eq[0], eq[1], eq[2], eq[3]);
+                const uint32_t neg4 = pack_sign_masks(xb[0], xb[1], xb[2], xb[3]) ^ c4.PAR;
+                *reinterpret_cast<uint32_t*>(&out[k]) = c4.emit(min4, neg4);
+            }
+#pragma unroll
+            for (int k = 0; k < DC; ++k) store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+            return;
+        }
+    }
     if (!p.beta_per_edge) {
         Real beta = Real(1);
         if (has_beta) beta = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
@@ -440,11 +523,13 @@ template <> struct SignMask<uint32_t> {
     static __device__ __forceinline__ uint32_t push(uint32_t m, uint32_t signword) { return __funnelshift_l(signword, m, 1); }
     static __device__ __forceinline__ uint32_t align(uint32_t m, int dc) { return m << (32 - dc); }
     static __device__ __forceinline__ uint32_t top(uint32_t m) { return m & 0x80000000u; }
+    static __device__ __forceinline__ uint32_t word(uint32_t m, int) { return m; }   // 32 edges per word, edge 0 on top
 };
 template <> struct SignMask<uint64_t> {
     static __device__ __forceinline__ uint64_t push(uint64_t m, uint32_t signword) { return (m << 1) | (uint64_t)(signword >> 31); }
     static __device__ __forceinline__ uint64_t align(uint64_t m, int dc) { return m << (64 - dc); }
     static __device__ __forceinline__ uint32_t top(uint64_t m) { return (uint32_t)(m >> 32) & 0x80000000u; }
+    static __device__ __forceinline__ uint32_t word(uint64_t m, int i) { return i == 0 ? (uint32_t)(m >> 32) : (uint32_t)m; }
 };
 
 // The ring as seen by one thread.  A check occupies ceil(deg / kWideRows) consecutive slabs (its last slab
@@ -549,6 +634,35 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
 #pragma unroll
     for (int v = 0; v < V; ++v) neg[v] = SignMask<MaskT>::align(neg[v], dc);  // top bit = sign of edge 0
     OutT* __restrict__ out_row = static_cast<OutT*>(p.dst) + slot0 * p.Bp + f0;
+    if constexpr (QUANT && V == 4) {
+        if (!p.beta_per_edge) {
+            // byte-parallel output phase: edges in groups of eight, whose input signs sit in one byte per frame
+            CheckOut4 c4;
+            c4.pack(co);
+            const uint32_t K0 = pack_low_bytes((uint32_t)st[0].k0, (uint32_t)st[1].k0, (uint32_t)st[2].k0, (uint32_t)st[3].k0);
+            for (int j = 0; j * 8 < dc; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) w[v] = SignMask<MaskT>::word(neg[v], j >> 2);
+                // byte v = input signs of edges 8j..8j+7 of frame v (edge 8j in bit 7), times the total parity
+                const uint32_t S = pack_bytes_at(w[0], w[1], w[2], w[3], 3u - (uint32_t)(j & 3)) ^ c4.PAR;
+                const int kend = min(8, dc - j * 8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < kend) {
+                        const uint32_t kk = (uint32_t)(j * 8 + i) * 0x01010101u;
+                        const uint32_t min4 = spread_byte_signs(0x80808080u - (K0 ^ kk));   // k, k0 < 128
+                        const uint32_t neg4 = spread_byte_signs(S << i);
+                        Pack<OutT, V> out;
+                        *reinterpret_cast<uint32_t*>(&out) = c4.emit(min4, neg4);
+                        store_masked<OutT, V>(out_row, out, dmask);
+                        out_row += p.Bp;
+                    }
+                }
+            }
+            return;
+        }
+    }
 #pragma unroll 4
     for (int k = 0; k < dc; ++k, out_row += p.Bp) {
         Real beta = Real(1);
