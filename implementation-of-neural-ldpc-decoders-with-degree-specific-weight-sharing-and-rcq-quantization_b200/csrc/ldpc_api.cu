@@ -406,6 +406,7 @@ int64_t pad_frames(int64_t B) { return (B + kFrameAlign - 1) / kFrameAlign * kFr
 
 int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     if (ws.cap >= Bp) return LDPC_OK;
+    if (Bp > ((int64_t)1 << 28)) return fail(LDPC_ERR_UNSUPPORTED, "more than 2^28 frames per call (32-bit row strides)");
     ws.release();
     const ldpc_graph* g = d->g;
     const size_t rows_v2c = (size_t)std::max<int64_t>(std::max<int64_t>(g->E, g->n), 1);

@@ -11,6 +11,8 @@
 //   syn_kernel  parity checks on the bit-packed hard decisions (32 frames per word)
 //   commit      per-frame early stop bookkeeping
 //   pack/unpack row-major user buffers <-> interleaved layout, Philox AWGN, error counting
+#include <type_traits>
+
 #include "ldpc_device.cuh"
 #include "ldpc_internal.h"
 
@@ -19,6 +21,27 @@ namespace ldpc {
 namespace {
 
 constexpr int kThreads = 256;
+
+// variables per group in vn_item_small (loads of a whole group are issued before the first use)
+#ifndef LDPC_VN_UQ_LO
+#define LDPC_VN_UQ_LO 4
+#endif
+#ifndef LDPC_VN_UQ_MID
+#define LDPC_VN_UQ_MID 2
+#endif
+#ifndef LDPC_VN_UQ_HI
+#define LDPC_VN_UQ_HI 1
+#endif
+#ifndef LDPC_VN_UF_LO
+#define LDPC_VN_UF_LO 2
+#endif
+// resident CTAs per SM the float32 variable-node kernels are compiled for (4 -> at most 64 registers)
+#ifndef LDPC_VN_F32_MINCTAS
+#define LDPC_VN_F32_MINCTAS 4
+#endif
+#ifndef LDPC_VN_UF_MID
+#define LDPC_VN_UF_MID 1
+#endif
 
 template <int V>
 __device__ __forceinline__ uint32_t load_done_mask(const uint8_t* __restrict__ done, int64_t f0) {
@@ -33,6 +56,14 @@ __device__ __forceinline__ uint32_t load_done_mask(const uint8_t* __restrict__ d
         for (int v = 0; v < 2; ++v) m |= ((w >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
     }
     return m;
+}
+
+// Row addressing: `base` already points at this lane's first frame of row 0; one IMAD.WIDE.U32 per row
+// (row index and row stride in bytes both fit 32 bits: the host caps Bp at 2^28 frames).
+template <typename T>
+__device__ __forceinline__ T* row_at(T* base, uint32_t row, uint32_t stride_bytes) {
+    using C = typename std::conditional<std::is_const<T>::value, const char, char>::type;
+    return reinterpret_cast<T*>(reinterpret_cast<C*>(base) + (uint64_t)row * stride_bytes);
 }
 
 // Store V frames of one row; frames whose done bit is set keep their old (frozen) value.
@@ -227,10 +258,13 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
     OutT* __restrict__ dst = static_cast<OutT*>(p.dst);
     Pack<Real, V> x[DC];
     const bool has_beta = p.beta_t != nullptr;
+    const uint32_t in_stride = (uint32_t)p.Bp * (uint32_t)sizeof(Real), out_stride = (uint32_t)p.Bp * (uint32_t)sizeof(OutT);
+    src += f0;
+    dst += f0;
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
-        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
-        x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
+        const uint32_t row = p.row_map ? (uint32_t)__ldg(p.row_map + slot0 + k) : (uint32_t)(slot0 + k);
+        x[k] = ld_stream<Pack<Real, V>>(row_at(src, row, in_stride));
     }
     Pack<OutT, V> out[DC];
     if constexpr (QUANT && V == 4) {
@@ -265,7 +299,7 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
                 *reinterpret_cast<uint32_t*>(&out[k]) = c4.emit(min4, neg4);
             }
 #pragma unroll
-            for (int k = 0; k < DC; ++k) store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+            for (int k = 0; k < DC; ++k) store_masked<OutT, V>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k], dmask);
             return;
         }
     }
@@ -304,7 +338,7 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
         }
     }
 #pragma unroll
-    for (int k = 0; k < DC; ++k) store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+    for (int k = 0; k < DC; ++k) store_masked<OutT, V>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k], dmask);
 }
 
 // Checks of degree 9..32: stream the inputs once, keeping min1/min2/first-argmin/parity and one sign
@@ -412,8 +446,11 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
     }
 }
 
+// resident CTAs per SM the check-node kernel is compiled for: the RCQ variant is issue-bound and gains from
+// 4 (64 registers); float32 / float64 stream at the HBM roofline with 3 / 2
+#define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : 2))
 template <typename Real, bool QUANT, int NTH>
-__global__ void __launch_bounds__(kThreads) cn_kernel(const CnLaunch p, const int nfb, const int item0) {
+__global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     __shared__ float s_thr[kMaxQuantLevels];
     Quantizer<NTH> qz;
@@ -965,21 +1002,25 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
     const InT* __restrict__ c2v = static_cast<const InT*>(p.c2v);
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
     const uint32_t lutmask = (1u << p.bc) - 1u;  // pad frames hold unwritten codes: keep the LUT index in range
-    int64_t j[U];
-    int64_t slot[U][D1];
+    uint32_t j[U];
+    uint32_t slot[U][D1];
     Pack<InT, V> cin[U][D1];
     Pack<Real, V> L[U];
+    const uint32_t in_stride = (uint32_t)p.Bp * (uint32_t)sizeof(InT), real_stride = (uint32_t)p.Bp * (uint32_t)sizeof(Real);
+    c2v += f0;
+    v2c += f0;
+    const Real* __restrict__ llr0 = static_cast<const Real*>(p.llrT) + f0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        j[u] = __ldg(p.vpos_var + vpos + u);
+        j[u] = (uint32_t)__ldg(p.vpos_var + vpos + u);
 #pragma unroll
-        for (int d = 0; d < DV; ++d) slot[u][d] = __ldg(p.vslots + lbase + u * DV + d);
+        for (int d = 0; d < DV; ++d) slot[u][d] = (uint32_t)__ldg(p.vslots + lbase + u * DV + d);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int d = 0; d < DV; ++d) cin[u][d] = ld_stream<Pack<InT, V>>(c2v + slot[u][d] * p.Bp + f0);
-        L[u] = ld_stream<Pack<Real, V>>(static_cast<const Real*>(p.llrT) + j[u] * p.Bp + f0);
+        for (int d = 0; d < DV; ++d) cin[u][d] = ld_stream<Pack<InT, V>>(row_at(c2v, slot[u][d], in_stride));
+        L[u] = ld_stream<Pack<Real, V>>(row_at(llr0, j[u], real_stride));
     }
     const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
 #pragma unroll
@@ -1015,9 +1056,9 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
         }
         if constexpr (!FINAL) {
 #pragma unroll
-            for (int d = 0; d < DV; ++d) store_masked<Real, V>(v2c + slot[u][d] * p.Bp + f0, out[d], dmask);
+            for (int d = 0; d < DV; ++d) store_masked<Real, V>(row_at(v2c, slot[u][d], real_stride), out[d], dmask);
         } else {
-            if (p.postT) st_stream<Pack<Real, V>>(static_cast<Real*>(p.postT) + j[u] * p.Bp + f0, post);
+            if (p.postT) st_stream<Pack<Real, V>>(row_at(static_cast<Real*>(p.postT) + f0, j[u], real_stride), post);
         }
         write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit);
     }
@@ -1029,7 +1070,8 @@ __device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem&
                                               int64_t wbase, const float* s_lut,
                                               const int (&lutbase)[FramesPerLane<Real>::value]) {
     // byte-wide RCQ code rows need more rows in flight than 16-byte float rows
-    constexpr int U = QUANT ? ((DV <= 2) ? 4 : ((DV <= 4) ? 2 : 1)) : ((DV <= 2) ? 2 : 1);
+    constexpr int U = QUANT ? ((DV <= 2) ? LDPC_VN_UQ_LO : ((DV <= 4) ? LDPC_VN_UQ_MID : LDPC_VN_UQ_HI))
+                            : ((DV <= 2) ? LDPC_VN_UF_LO : ((DV <= 4) ? LDPC_VN_UF_MID : 1));
     int64_t lbase = it.first_slot;
     int32_t vpos = it.first_node;
     int c = 0;
@@ -1092,7 +1134,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
 }
 
 template <typename Real, bool QUANT, bool FINAL>
-__global__ void __launch_bounds__(kThreads) vn_kernel(const VnLaunch p, const int nfb) {
+__global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ float s_lut[];
     if (QUANT) {
