@@ -330,6 +330,7 @@ struct Workspace {
 };
 
 constexpr int kPipeDepth = 3;
+constexpr size_t kMaxLevels = 32;   // compaction levels (each at most 60 % of its parent)
 
 // Host-buffer pipeline: three streams (H2D copies, kernels, D2H copies) over kPipeDepth staging buffers
 // and ONE message workspace, so that the copy of chunk i+1, the decode of chunk i and the copy-out of
@@ -391,6 +392,21 @@ struct ldpc_decoder {
     Workspace ws;
     HostPipe pipe;
     int64_t host_chunk = 0;
+    // frame compaction (early stop at scale): child workspaces, one per level, plus bookkeeping buffers
+    struct Level {
+        Workspace ws;
+        int32_t* idx = nullptr;   // [cap] running frames of the parent, ascending
+        int32_t* map = nullptr;   // [cap] frame of this level -> frame of the caller's batch
+        int64_t cap = 0;
+    };
+    std::vector<Level> levels;
+    int32_t* d_scan = nullptr;    // [scan_cap] per-block counts / offsets
+    int64_t scan_cap = 0;
+    int32_t* d_total = nullptr;   // device int32
+    int32_t* h_total = nullptr;   // pinned host int32
+    int compact = 1;              // LDPC_COMPACT=0 switches compaction and the all-done exit off
+    int64_t compact_min_frames = 512;
+    int64_t stat_compactions = 0, stat_early_exits = 0;
     // instrumentation
     int prof_mode = 0;
     ldpc_profile prof{};
@@ -501,67 +517,86 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
     return LDPC_OK;
 }
 
-int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
-    if (d->schedule == LDPC_SCHEDULE_LAYERED) return run_layered(d, ws, B, Bp, want_post, stream);
+// Where the results of a decode go: row-major user buffers (decode) or error counters (Monte-Carlo round).
+struct OutSpec {
+    uint8_t* bits = nullptr;
+    void* post = nullptr;
+    int32_t* iters = nullptr;
+    uint8_t* success = nullptr;
+    bool count = false;              // Monte-Carlo: accumulate into counters instead
+    const uint8_t* codeword = nullptr;
+    int64_t* counters = nullptr;
+    int32_t* frame_bit_errors = nullptr;
+    int32_t* frame_iters = nullptr;
+};
+
+void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, CnLaunch& cn) {
+    const ldpc_graph* g = d->g;
+    const int q = d->bc ? d->q_of_iter[t] : 0;
+    cn.src = (t == 0) ? ws.llrT : ws.v2c;
+    cn.dst = ws.c2v;
+    cn.row_map = (t == 0) ? g->d_slot_var : nullptr;
+    cn.bidx = d->d_bidx;
+    cn.beta_per_edge = d->beta_per_edge;
+    cn.beta_t = d->d_beta ? (const char*)d->d_beta + (size_t)t * d->n_beta * d->rsz : nullptr;
+    cn.thr = d->bc ? d->d_thr + (size_t)q * d->nth : nullptr;
+    cn.nth = d->nth;
+    cn.bc = d->bc;
+    cn.mono = d->bc ? d->mono[q] : 1;
+    cn.done = ws.done;
+    cn.items = g->d_cn_items;
+    cn.n_items = (int)g->cn_items.size();
+    cn.items_wide_begin = g->cn_wide_begin;
+    cn.items_wide_end = g->cn_wide_end;
+    cn.wide_ring = d->wide_ring;
+    cn.Bp = Bp;
+    if (d->check_rule == LDPC_RULE_OFFSET) {
+        cn.aidx_slot = d->d_aidx_slot;
+        cn.alpha_t = d->d_alpha ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
+    }
+}
+
+void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass, bool want_post, VnLaunch& vn) {
+    const ldpc_graph* g = d->g;
+    vn.c2v = ws.c2v;
+    vn.v2c = ws.v2c;
+    vn.llrT = ws.llrT;
+    vn.postT = (final_pass && want_post) ? ws.v2c : nullptr;  // v2c is dead once the final pass runs
+    vn.vslots = g->d_vslots;
+    vn.vpos_var = g->d_vpos_var;
+    vn.aidx = d->d_aidx;
+    vn.alpha_t = (d->d_alpha && d->check_rule != LDPC_RULE_OFFSET)
+                     ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
+    vn.lut = d->d_lut;
+    vn.bc = d->bc;
+    vn.n_quant = d->Q;
+    vn.q_now = d->bc ? d->q_of_iter[t] : 0;
+    vn.q_of_iter = d->d_q_of_iter;
+    vn.iters = ws.iters;
+    vn.hardw = ws.hardw;
+    vn.Wn = Bp / 32;
+    vn.done = ws.done;
+    vn.items = g->d_vn_items;
+    vn.n_items = (int)g->vn_items.size();
+    vn.Bp = Bp;
+    vn.final_pass = final_pass ? 1 : 0;
+}
+
+// Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node pass:
+// it recomputes posterior + decision of EVERY frame from its frozen c2v (frames that stopped at iteration t
+// kept c2v(t)); the dead v2c update of iteration T-1 is not written.
+int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool want_post, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
     const int64_t Wn = Bp / 32;
-    LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
-    for (int t = 0; t < d->T; ++t) {
-        const int q = d->bc ? d->q_of_iter[t] : 0;
+    for (int t = t0; t < t1; ++t) {
         CnLaunch cn{};
-        cn.src = (t == 0) ? ws.llrT : ws.v2c;
-        cn.dst = ws.c2v;
-        cn.row_map = (t == 0) ? g->d_slot_var : nullptr;
-        cn.bidx = d->d_bidx;
-        cn.beta_per_edge = d->beta_per_edge;
-        cn.beta_t = d->d_beta ? (const char*)d->d_beta + (size_t)t * d->n_beta * d->rsz : nullptr;
-        cn.thr = d->bc ? d->d_thr + (size_t)q * d->nth : nullptr;
-        cn.nth = d->nth;
-        cn.bc = d->bc;
-        cn.mono = d->bc ? d->mono[q] : 1;
-        cn.done = ws.done;
-        cn.items = g->d_cn_items;
-        cn.n_items = (int)g->cn_items.size();
-        cn.items_wide_begin = g->cn_wide_begin;
-        cn.items_wide_end = g->cn_wide_end;
-        cn.wide_ring = d->wide_ring;
-        cn.Bp = Bp;
-        if (d->check_rule == LDPC_RULE_OFFSET) {
-            cn.aidx_slot = d->d_aidx_slot;
-            cn.alpha_t = d->d_alpha ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
-            LAUNCH(K_CN, launch_cn_offset(d->dtype, cn, stream));
-        } else {
-            LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
-        }
-
+        fill_cn(d, ws, Bp, t, cn);
+        if (d->check_rule == LDPC_RULE_OFFSET) LAUNCH(K_CN, launch_cn_offset(d->dtype, cn, stream));
+        else LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
         const bool last = (t == d->T - 1);
         VnLaunch vn{};
-        vn.c2v = ws.c2v;
-        vn.v2c = ws.v2c;
-        vn.llrT = ws.llrT;
-        vn.postT = (last && want_post) ? ws.v2c : nullptr;  // v2c is dead after the last check pass
-        vn.vslots = g->d_vslots;
-        vn.vpos_var = g->d_vpos_var;
-        vn.aidx = d->d_aidx;
-        vn.alpha_t = (d->d_alpha && d->check_rule != LDPC_RULE_OFFSET)
-                         ? (const char*)d->d_alpha + (size_t)t * d->n_alpha * d->rsz : nullptr;
-        vn.lut = d->d_lut;
-        vn.bc = d->bc;
-        vn.n_quant = d->Q;
-        vn.q_now = q;
-        vn.q_of_iter = d->d_q_of_iter;
-        vn.iters = ws.iters;
-        vn.hardw = ws.hardw;
-        vn.Wn = Wn;
-        vn.done = ws.done;
-        vn.items = g->d_vn_items;
-        vn.n_items = (int)g->vn_items.size();
-        vn.Bp = Bp;
-        vn.final_pass = last ? 1 : 0;
-        // The last pass recomputes posterior + decision of EVERY frame from its frozen c2v (frames that
-        // stopped at iteration t kept c2v(t)); the dead v2c update of iteration T-1 is not written.
+        fill_vn(d, ws, Bp, t, last, want_post, vn);
         LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
-
         if (d->early_stop || last) {
             uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
             uint32_t* nxt = ws.unsat + (size_t)((t + 1) & 1) * Wn;
@@ -579,14 +614,142 @@ int run_iterations(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool w
     return LDPC_OK;
 }
 
-int emit_outputs(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, uint8_t* bits, void* post, int32_t* iters,
-                 uint8_t* success, cudaStream_t stream) {
-    const ldpc_graph* g = d->g;
-    if (bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, bits, B, g->n, nullptr, stream));
-    if (post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, post, B, Bp, g->n, nullptr, stream));
-    if (iters) CU(cudaMemcpyAsync(iters, ws.iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-    if (success) CU(cudaMemcpyAsync(success, ws.success, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+// The final pass on its own (frames of a level whose remaining frames have all stopped, or whose running
+// frames are about to move to a compacted level): decisions / posteriors of every frame from its frozen c2v.
+int run_final_pass(ldpc_decoder* d, Workspace& ws, int64_t Bp, bool want_post, cudaStream_t stream) {
+    VnLaunch vn{};
+    fill_vn(d, ws, Bp, d->T - 1, true, want_post, vn);
+    LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
     return LDPC_OK;
+}
+
+// Results of one level -> the caller's buffers.  `map` (nullptr = identity) gives the caller's frame of each
+// frame of the level; `only_done` != nullptr leaves the running frames to the next level.
+int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int32_t* map, const uint8_t* only_done,
+               const OutSpec& o, cudaStream_t stream) {
+    const ldpc_graph* g = d->g;
+    if (o.count) {
+        LAUNCH(K_OTHER, launch_count_packed(d->V, ws.hardw, Bp / 32, g->n, B, o.codeword, ws.iters, o.counters,
+                                            o.frame_bit_errors, o.frame_iters, map, only_done, stream));
+        return LDPC_OK;
+    }
+    // running frames of a parent level also write their (unfinished) rows here; the next level overwrites them
+    if (o.bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, o.bits, B, g->n, map, stream));
+    if (o.post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, o.post, B, Bp, g->n, map, stream));
+    if (map) {
+        if (o.iters || o.success)
+            LAUNCH(K_OTHER, launch_scatter_frames(ws.iters, ws.success, o.iters, o.success, map, B, stream));
+    } else {
+        if (o.iters) CU(cudaMemcpyAsync(o.iters, ws.iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+        if (o.success) CU(cudaMemcpyAsync(o.success, ws.success, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+    }
+    return LDPC_OK;
+}
+
+// Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
+int next_checkpoint(int t, int T) {
+    int c;
+    if (t < 8) c = t + 2;
+    else if (t < 24) c = t + 4;
+    else c = t + 8;
+    return c < T ? c : T;
+}
+
+int scan_ensure(ldpc_decoder* d, int64_t Bp) {
+    const int64_t nb = (Bp + 1023) / 1024;
+    if (d->scan_cap < nb) {
+        cudaFree(d->d_scan);
+        d->d_scan = nullptr;
+        d->scan_cap = 0;
+        CU(cudaMalloc((void**)&d->d_scan, (size_t)nb * sizeof(int32_t)));
+        d->scan_cap = nb;
+    }
+    if (!d->d_total) CU(cudaMalloc((void**)&d->d_total, sizeof(int32_t)));
+    if (!d->h_total) CU(cudaHostAlloc((void**)&d->h_total, sizeof(int32_t), cudaHostAllocDefault));
+    return LDPC_OK;
+}
+
+// The whole decode of the frames resident as llrT [n][Bp] in `root`, results delivered per OutSpec.
+//
+// Flooding with early stop runs in spans between checkpoints.  At a checkpoint the number of running frames
+// comes back to the host: zero ends the decode (no empty launches up to T); if at most 60 % of the level's
+// lanes still run, those frames' LLR and V2C columns are gathered into a dense child level that carries on
+// from the same iteration, and the parent level delivers the results of its finished frames.  Every frame
+// sees exactly the arithmetic of the uncompacted schedule (columns are independent), so results are identical.
+int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
+    const bool want_post = o.post != nullptr;
+    if (d->schedule == LDPC_SCHEDULE_LAYERED) {
+        int rc = run_layered(d, root, B, Bp, want_post, stream);
+        if (rc) return rc;
+        return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
+    }
+    const ldpc_graph* g = d->g;
+    LAUNCH(K_OTHER, launch_reset_state(root.done, root.iters, root.success, root.unsat, B, Bp, d->T, stream));
+    const bool checkpoints = d->early_stop && d->compact && d->T > 2;
+    Workspace* ws = &root;
+    const int32_t* map = nullptr;
+    int64_t curB = B, curBp = Bp;
+    size_t level = 0;
+    int t = 0;
+    if (checkpoints) {
+        int rc = scan_ensure(d, Bp);
+        if (rc) return rc;
+    }
+    while (true) {
+        const int t1 = checkpoints ? next_checkpoint(t, d->T) : d->T;
+        int rc = run_span(d, *ws, curBp, t, t1, want_post, stream);
+        if (rc) return rc;
+        t = t1;
+        if (t >= d->T) return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
+        LAUNCH(K_OTHER, launch_pending_scan(ws->done, curBp, d->d_scan, d->d_total, stream));
+        CU(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        const int64_t pending = *d->h_total;
+        if (pending == 0) {
+            d->stat_early_exits++;
+            rc = run_final_pass(d, *ws, curBp, want_post, stream);
+            if (rc) return rc;
+            return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
+        }
+        if (curBp < d->compact_min_frames || pending * 10 > curBp * 6 || level >= kMaxLevels) continue;
+        // ---- move the running frames to a dense child level ----
+        if (d->levels.size() <= level) d->levels.emplace_back();   // capacity reserved at creation: no reallocation
+        ldpc_decoder::Level& lv = d->levels[level];
+        const int64_t childBp = pad_frames(pending);
+        if (lv.cap < childBp) {
+            const int64_t cap = std::max(childBp, pad_frames((curBp * 6 + 9) / 10));   // any later count of this level fits
+            cudaFree(lv.idx);
+            cudaFree(lv.map);
+            lv.idx = lv.map = nullptr;
+            lv.cap = 0;
+            CU(cudaMalloc((void**)&lv.idx, (size_t)cap * sizeof(int32_t)));
+            CU(cudaMalloc((void**)&lv.map, (size_t)cap * sizeof(int32_t)));
+            lv.cap = cap;
+        }
+        rc = ws_ensure(d, lv.ws, std::max(childBp, std::min(lv.cap, pad_frames((curBp * 6 + 9) / 10))));
+        if (rc == LDPC_ERR_NOMEM) {   // no room for a child level: carry on uncompacted
+            cudaGetLastError();
+            lv.ws.release();
+            continue;
+        }
+        if (rc) return rc;
+        LAUNCH(K_OTHER, launch_pending_indices(ws->done, curBp, d->d_scan, lv.idx, stream));
+        LAUNCH(K_OTHER, launch_compose_map(lv.idx, map, lv.map, pending, stream));
+        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->llrT, curBp, lv.ws.llrT, childBp, lv.idx, pending, g->n, stream));
+        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->v2c, curBp, lv.ws.v2c, childBp, lv.idx, pending, g->E, stream));
+        LAUNCH(K_OTHER, launch_reset_state(lv.ws.done, lv.ws.iters, lv.ws.success, lv.ws.unsat, pending, childBp, d->T, stream));
+        // the parent's finished frames: final pass (after the gather: it reuses v2c for the posteriors) and delivery
+        rc = run_final_pass(d, *ws, curBp, want_post, stream);
+        if (rc) return rc;
+        rc = emit_level(d, *ws, curB, curBp, map, ws->done, o, stream);
+        if (rc) return rc;
+        d->stat_compactions++;
+        ws = &lv.ws;
+        map = lv.map;
+        curB = pending;
+        curBp = childBp;
+        ++level;
+    }
 }
 
 int decode_on_device(ldpc_decoder* d, Workspace& ws, const void* llr, int64_t B, uint8_t* bits, void* post,
@@ -596,9 +759,12 @@ int decode_on_device(ldpc_decoder* d, Workspace& ws, const void* llr, int64_t B,
     if (rc) return rc;
     d->prof.frames_padded = Bp;
     LAUNCH(K_OTHER, launch_pack(d->dtype, llr, ws.llrT, B, Bp, d->g->n, ws.done, ws.iters, ws.success, d->T, stream));
-    rc = run_iterations(d, ws, B, Bp, post != nullptr, stream);
-    if (rc) return rc;
-    return emit_outputs(d, ws, B, Bp, bits, post, iters, success, stream);
+    OutSpec o;
+    o.bits = bits;
+    o.post = post;
+    o.iters = iters;
+    o.success = success;
+    return decode_resident(d, ws, B, Bp, o, stream);
 }
 
 }  // namespace
@@ -662,8 +828,11 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->nth = cfg->bc ? (1 << (cfg->bc - 1)) : 0;
     d->check_rule = cfg->check_rule;
     d->schedule = cfg->schedule;
+    d->levels.reserve(kMaxLevels);   // decode_resident keeps pointers into this vector
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
+    if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
+    if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
     DeviceGuard guard(g->device);
     if (!guard.ok) {
@@ -755,6 +924,14 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     cudaDeviceSynchronize();
     d->ws.release();
     d->pipe.release();
+    for (auto& lv : d->levels) {
+        lv.ws.release();
+        cudaFree(lv.idx);
+        cudaFree(lv.map);
+    }
+    cudaFree(d->d_scan);
+    cudaFree(d->d_total);
+    if (d->h_total) cudaFreeHost(d->h_total);
     for (auto& ev : d->ev_pool) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -823,20 +1000,37 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
     }
     int rc = ws_ensure(d, pp.ws, pad_frames(chunk));
     if (rc) return rc;
-    int64_t off = 0;
-    for (int64_t i = 0; off < B && !rc; ++i) {
-        // ramp the first chunks (1/8, 1/4, 1/2 of a chunk) so the kernels start while most of the input is
-        // still crossing PCIe; the un-overlapped head of the pipeline shrinks accordingly
+    // chunk boundaries: the first chunks are ramped (1/8, 1/4, 1/2 of a chunk) so the kernels start while most of
+    // the input is still crossing PCIe; the un-overlapped head of the pipeline shrinks accordingly
+    std::vector<std::pair<int64_t, int64_t>> chunks;   // (offset, frames)
+    for (int64_t off = 0, i = 0; off < B; ++i) {
         int64_t want = chunk;
         if (B > 2 * chunk && i < 3) want = std::max<int64_t>(kFrameAlign, (chunk >> (3 - i)) / kFrameAlign * kFrameAlign);
         const int64_t b = std::min<int64_t>(want, B - off);
+        chunks.emplace_back(off, b);
+        off += b;
+    }
+    // The input copy of chunk i+1 is enqueued BEFORE the decode of chunk i: the decode may block the host at
+    // its checkpoints (frame compaction), and the copy engine should be busy meanwhile.
+    auto enqueue_input = [&](size_t i) -> int {
         HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
-        if (i >= kPipeDepth) CU(cudaStreamWaitEvent(pp.s_in, bf.run_done, 0));     // staging input consumed
-        CU(cudaMemcpyAsync(bf.d_llr, (const char*)llr + (size_t)off * n * d->rsz, (size_t)b * n * d->rsz,
-                           cudaMemcpyHostToDevice, pp.s_in));
+        if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_in, bf.run_done, 0));     // staging input consumed
+        CU(cudaMemcpyAsync(bf.d_llr, (const char*)llr + (size_t)chunks[i].first * n * d->rsz,
+                           (size_t)chunks[i].second * n * d->rsz, cudaMemcpyHostToDevice, pp.s_in));
         CU(cudaEventRecord(bf.in_ready, pp.s_in));
+        return LDPC_OK;
+    };
+    rc = enqueue_input(0);
+    for (size_t i = 0; i < chunks.size() && !rc; ++i) {
+        const int64_t off = chunks[i].first, b = chunks[i].second;
+        HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
+        if (i + 1 < chunks.size()) {
+            // buffer (i+1) % depth was last read by the decode of chunk i+1-depth, already enqueued
+            rc = enqueue_input(i + 1);
+            if (rc) break;
+        }
         CU(cudaStreamWaitEvent(pp.s_run, bf.in_ready, 0));
-        if (i >= kPipeDepth) CU(cudaStreamWaitEvent(pp.s_run, bf.out_done, 0));    // staging outputs copied out
+        if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_run, bf.out_done, 0));    // staging outputs copied out
         rc = decode_on_device(d, pp.ws, bf.d_llr, b, bits ? bf.d_bits : nullptr, posterior ? bf.d_post : nullptr,
                               bf.d_it, bf.d_su, pp.s_run);
         if (rc) break;
@@ -849,7 +1043,6 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         if (iterations) CU(cudaMemcpyAsync(iterations + off, bf.d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, pp.s_out));
         if (success) CU(cudaMemcpyAsync(success + off, bf.d_su, (size_t)b, cudaMemcpyDeviceToHost, pp.s_out));
         CU(cudaEventRecord(bf.out_done, pp.s_out));
-        off += b;
     }
     for (cudaStream_t st : {pp.s_in, pp.s_run, pp.s_out}) {
         cudaError_t e = cudaStreamSynchronize(st);
@@ -885,11 +1078,13 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     d->prof.frames_padded = Bp;
     Workspace& ws = d->ws;
     LAUNCH(K_OTHER, launch_awgn(d->dtype, 0, ws.llrT, d->g->n, B, Bp, frame0, seed, snr_db, llr_sign, codeword, stream));
-    rc = run_iterations(d, ws, B, Bp, false, stream);
-    if (rc) return rc;
-    LAUNCH(K_OTHER, launch_count_packed(d->V, ws.hardw, Bp / 32, d->g->n, B, codeword, ws.iters, counters,
-                                        frame_bit_errors, frame_iterations, nullptr, nullptr, stream));
-    return LDPC_OK;
+    OutSpec o;
+    o.count = true;
+    o.codeword = codeword;
+    o.counters = counters;
+    o.frame_bit_errors = frame_bit_errors;
+    o.frame_iters = frame_iterations;
+    return decode_resident(d, ws, B, Bp, o, stream);
 }
 
 extern "C" int ldpc_count_errors(int device, int32_t n, int64_t B, const uint8_t* bits, const uint8_t* codeword,
@@ -927,8 +1122,11 @@ extern "C" int ldpc_decoder_profile_read(ldpc_decoder* d, ldpc_profile* out, int
         d->pending.clear();
         d->ev_next = 0;
     }
+    d->prof.compactions = d->stat_compactions;
+    d->prof.early_exits = d->stat_early_exits;
     *out = d->prof;
     if (reset) {
+        d->stat_compactions = d->stat_early_exits = 0;
         int64_t fp = d->prof.frames_padded;
         d->prof = ldpc_profile{};
         d->prof.frames_padded = fp;

@@ -109,17 +109,23 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
                         uint64_t frame0, uint64_t seed, float snr_db, int32_t llr_sign,
                         const uint8_t* codeword, cudaStream_t stream);
 // counters += {frame_errors, bit_errors, total_iterations, total_frames}
+// `map` (may be nullptr): per-frame outputs of local frame f go to row map[f]; `only_done` (may be nullptr):
+// frames with only_done[f] == 0 are left out (they were handed on to a compacted level and are counted there)
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B,
                                 const uint8_t* codeword, const int32_t* iters, int64_t* counters,
                                 int32_t* frame_bit_errors, int32_t* frame_iters, const int32_t* map,
-                                const uint8_t* skip, cudaStream_t stream);
-// re-decode level bookkeeping
-cudaError_t launch_count_pending(const uint8_t* done, int64_t Bp, int32_t* out, cudaStream_t stream);
-cudaError_t launch_mark_retry(const uint8_t* done, uint8_t* retry, int64_t Bp, cudaStream_t stream);
+                                const uint8_t* only_done, cudaStream_t stream);
+// frame compaction bookkeeping: counts[ceil(Bp/1024)] becomes the exclusive scan of running frames per
+// 1024-frame block and total[0] their number; then idx[0..total) = the running frames in ascending order
+cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, cudaStream_t stream);
+cudaError_t launch_pending_indices(const uint8_t* done, int64_t Bp, const int32_t* offsets, int32_t* idx, cudaStream_t stream);
+// dst [rows][Bp_dst] column i = src [rows][Bp_src] column idx[i] (i < count), zero for the pad columns
 cudaError_t launch_gather_cols(int dtype, const void* src, int64_t Bp_src, void* dst, int64_t Bp_dst, const int32_t* idx,
-                               int64_t count, int32_t n, cudaStream_t stream);
+                               int64_t count, int64_t rows, cudaStream_t stream);
+// iters_dst[map[i]] = iters_src[i] (same for success); map == nullptr: identity
 cudaError_t launch_scatter_frames(const int32_t* iters_src, const uint8_t* succ_src, int32_t* iters_dst, uint8_t* succ_dst,
                                   const int32_t* map, int64_t count, cudaStream_t stream);
+// out[i] = parent_map ? parent_map[idx[i]] : idx[i]
 cudaError_t launch_compose_map(const int32_t* idx, const int32_t* parent_map, int32_t* out, int64_t count, cudaStream_t stream);
 cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const uint8_t* codeword,
                               const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,

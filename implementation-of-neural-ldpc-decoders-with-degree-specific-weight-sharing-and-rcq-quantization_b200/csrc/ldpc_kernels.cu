@@ -574,7 +574,6 @@ template <> struct SignMask<uint64_t> {
 // walk the slabs in lockstep: acquire(), read rows, release().
 template <typename Real>
 struct RowRing {
-    static constexpr int V = FramesPerLane<Real>::value;
     unsigned char* smem;
     uint64_t* bars;
     const Real* src;
@@ -1399,7 +1398,7 @@ __global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, i
                                     const uint8_t* __restrict__ codeword, const int32_t* __restrict__ iters,
                                     int64_t* counters, int32_t* __restrict__ frame_bit_errors,
                                     int32_t* __restrict__ frame_iters, const int32_t* __restrict__ map,
-                                    const uint8_t* __restrict__ skip) {
+                                    const uint8_t* __restrict__ only_done) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= Wn) return;
@@ -1411,7 +1410,7 @@ __global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, i
         cnt += (int)bit;
     }
     const int64_t f = wordbit_to_frame(w, lane, V);
-    const int valid = f < B && !(skip && skip[f]);   // frames handed to a re-decode level are counted there
+    const int valid = f < B && !(only_done && !only_done[f]);   // frames handed on to a compacted level are counted there
     const int it = valid ? iters[f] : 0;
     if (valid) {
         const int64_t fo = map ? (int64_t)map[f] : f;
@@ -1447,30 +1446,103 @@ __global__ void count_bits_kernel(const uint8_t* __restrict__ bits, int32_t n, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Re-decode levels ("early stop at scale"): frames still running at a checkpoint are
-// handed to a smaller, dense batch that is decoded from scratch (the decode is a pure function of the
-// frame's LLRs, so the results are identical); these kernels do the bookkeeping.
+// Frame compaction ("early stop at scale").  Lanes own fixed frames, so a batch in which
+// most frames have stopped still streams every message row of every warp that holds one running frame.  At
+// checkpoints the frames still running are gathered (LLRs and V2C state, column by column) into a smaller
+// dense batch that carries on from the same iteration; these kernels do the bookkeeping.
 // ---------------------------------------------------------------------------------------------
-__global__ void count_pending_kernel(const uint8_t* __restrict__ done, int64_t Bp, int32_t* __restrict__ out) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kScanBlock = 1024;
+
+// counts[b] = frames of block b (kScanBlock frames) that are still running
+__global__ void __launch_bounds__(kScanBlock) pending_count_kernel(const uint8_t* __restrict__ done, int64_t Bp,
+                                                                    int32_t* __restrict__ counts) {
+    __shared__ int32_t s_warp[kScanBlock / 32];
+    const int64_t f = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
     const int pend = (f < Bp) ? (done[f] == 0) : 0;
     const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)pend);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (int32_t)c);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = (int32_t)c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned t = __reduce_add_sync(0xffffffffu, (unsigned)s_warp[threadIdx.x]);
+        if (threadIdx.x == 0) counts[blockIdx.x] = (int32_t)t;
+    }
 }
 
-__global__ void mark_retry_kernel(const uint8_t* __restrict__ done, uint8_t* __restrict__ retry, int64_t Bp) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < Bp) retry[f] = done[f] == 0;
+// in-place exclusive scan of counts[nb] by one block; total[0] = sum
+__global__ void __launch_bounds__(kScanBlock) pending_scan_kernel(int32_t* __restrict__ counts, int nb,
+                                                                   int32_t* __restrict__ total) {
+    __shared__ int32_t s_warp[kScanBlock / 32];
+    __shared__ int32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += kScanBlock) {
+        const int i = base + threadIdx.x;
+        const int32_t x = (i < nb) ? counts[i] : 0;
+        int32_t incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const int32_t carry = s_carry;
+        const int32_t before = carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
+        if (i < nb) counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) s_carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = s_carry;
 }
 
-// dst[j][i] = src[j][idx[i]] for i < count, 0 for the pad frames
+// idx[offsets[b] + r] = r-th running frame of block b (ascending frame order overall)
+__global__ void __launch_bounds__(kScanBlock) pending_index_kernel(const uint8_t* __restrict__ done, int64_t Bp,
+                                                                    const int32_t* __restrict__ offsets,
+                                                                    int32_t* __restrict__ idx) {
+    __shared__ int32_t s_warp[kScanBlock / 32];
+    const int64_t f = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    const int pend = (f < Bp) ? (done[f] == 0) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, pend);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (pend) {
+        const int32_t pos = offsets[blockIdx.x] + (warp ? s_warp[warp - 1] : 0) + __popc(bal & ((1u << lane) - 1u));
+        idx[pos] = (int32_t)f;
+    }
+}
+
+// dst[j][i] = src[j][idx[i]] for i < count, 0 for the pad frames; rows j stride over gridDim.y
 template <typename Real>
 __global__ void gather_cols_kernel(const Real* __restrict__ src, int64_t Bp_src, Real* __restrict__ dst, int64_t Bp_dst,
-                                   const int32_t* __restrict__ idx, int64_t count, int32_t n) {
+                                   const int32_t* __restrict__ idx, int64_t count, int64_t rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int32_t j = blockIdx.y;
-    if (i >= Bp_dst || j >= n) return;
-    dst[(int64_t)j * Bp_dst + i] = (i < count) ? src[(int64_t)j * Bp_src + idx[i]] : Real(0);
+    if (i >= Bp_dst) return;
+    const int64_t col = (i < count) ? (int64_t)__ldg(idx + i) : -1;
+    for (int64_t j = blockIdx.y; j < rows; j += gridDim.y)
+        dst[j * Bp_dst + i] = (col >= 0) ? __ldg(src + j * Bp_src + col) : Real(0);
 }
 
 __global__ void scatter_frames_kernel(const int32_t* __restrict__ iters_src, const uint8_t* __restrict__ succ_src,
@@ -1677,10 +1749,10 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
 
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B, const uint8_t* codeword,
                                 const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
-                                int32_t* frame_iters, const int32_t* map, const uint8_t* skip, cudaStream_t stream) {
+                                int32_t* frame_iters, const int32_t* map, const uint8_t* only_done, cudaStream_t stream) {
     const int warps = 4;
     count_packed_kernel<<<(unsigned)((Wn + warps - 1) / warps), warps * 32, 0, stream>>>(
-        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters, map, skip);
+        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters, map, only_done);
     return cudaGetLastError();
 }
 
@@ -1692,23 +1764,25 @@ cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const u
     return cudaGetLastError();
 }
 
-cudaError_t launch_count_pending(const uint8_t* done, int64_t Bp, int32_t* out, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int32_t), stream);
-    if (e != cudaSuccess) return e;
-    count_pending_kernel<<<(unsigned)((Bp + 255) / 256), 256, 0, stream>>>(done, Bp, out);
+cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, cudaStream_t stream) {
+    const int nb = (int)((Bp + kScanBlock - 1) / kScanBlock);
+    pending_count_kernel<<<nb, kScanBlock, 0, stream>>>(done, Bp, counts);
+    pending_scan_kernel<<<1, kScanBlock, 0, stream>>>(counts, nb, total);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mark_retry(const uint8_t* done, uint8_t* retry, int64_t Bp, cudaStream_t stream) {
-    mark_retry_kernel<<<(unsigned)((Bp + 255) / 256), 256, 0, stream>>>(done, retry, Bp);
+cudaError_t launch_pending_indices(const uint8_t* done, int64_t Bp, const int32_t* offsets, int32_t* idx, cudaStream_t stream) {
+    const int nb = (int)((Bp + kScanBlock - 1) / kScanBlock);
+    pending_index_kernel<<<nb, kScanBlock, 0, stream>>>(done, Bp, offsets, idx);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather_cols(int dtype, const void* src, int64_t Bp_src, void* dst, int64_t Bp_dst, const int32_t* idx,
-                               int64_t count, int32_t n, cudaStream_t stream) {
-    dim3 grid((unsigned)((Bp_dst + 255) / 256), (unsigned)n);
-    if (dtype == 0) gather_cols_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), Bp_src, static_cast<float*>(dst), Bp_dst, idx, count, n);
-    else gather_cols_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(src), Bp_src, static_cast<double*>(dst), Bp_dst, idx, count, n);
+                               int64_t count, int64_t rows, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((Bp_dst + 255) / 256), (unsigned)(rows < 4096 ? rows : 4096));
+    if (dtype == 0) gather_cols_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), Bp_src, static_cast<float*>(dst), Bp_dst, idx, count, rows);
+    else gather_cols_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(src), Bp_src, static_cast<double*>(dst), Bp_dst, idx, count, rows);
     return cudaGetLastError();
 }
 

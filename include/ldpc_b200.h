@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LDPC_B200_VERSION 100
+#define LDPC_B200_VERSION 101
 
 enum {
     LDPC_OK = 0,
@@ -132,7 +132,9 @@ int ldpc_decoder_reserve(ldpc_decoder *d, int64_t frames);
  *   posterior[B][n] of dtype, may be NULL  (forward() returns it, decode() does not)
  *   iterations[B] int32, success[B] uint8 (either may be NULL)
  * _device: all pointers are device pointers on the graph's device; work is enqueued on `stream`
- *          (a cudaStream_t, NULL = default stream) and NOT synchronised.
+ *          (a cudaStream_t, NULL = default stream).  With early_stop the call synchronises the stream at
+          a few checkpoints (to read the number of running frames: an all-stopped batch ends at once,
+          a mostly-stopped one is compacted); the tail of the work is left enqueued, NOT synchronised.
  * _host:   all pointers are host pointers (pinned for full speed); the call copies in, decodes and
  *          copies out through an internal chunked double-buffered pipeline and returns when the
  *          outputs are valid.
@@ -186,6 +188,8 @@ typedef struct ldpc_profile {
     double vn_ms;
     double other_ms;          /* pack / unpack / syndrome / commit / awgn / count                  */
     int64_t frames_padded;    /* Bp of the last call                                               */
+    int64_t compactions;      /* times the running frames were gathered into a smaller dense batch */
+    int64_t early_exits;      /* decodes that ended before T because every frame had stopped       */
 } ldpc_profile;
 /* mode 0: count launches only (no overhead); mode 1: also bracket every kernel with CUDA events. */
 int ldpc_decoder_profile_mode(ldpc_decoder *d, int32_t mode);
