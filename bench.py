@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--decoder", default="n2d2", choices=["n2d2", "rcq", "wrcq1", "basic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mc", action="store_true", help="skip the early-stop Monte-Carlo leg (T=50, frames converge)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -250,6 +251,52 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def mc_leg(L, code, kind, B, local_rank, rank, world, barrier, dev, T=50, snrs=(2.0, 3.0), rounds=3):
+    import torch
+    import torch.distributed as dist
+    t = np.arange(T, dtype=np.float64)
+    beta = np.minimum(0.75 + t / 64, 1.0).astype(np.float32)
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    out = []
+    for compact in (0, 1):
+        os.environ["LDPC_COMPACT"] = str(compact)      # read when the decoder handle is created
+        if kind == "n2d2":
+            dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
+            with torch.no_grad():
+                dec._beta_table.copy_(torch.from_numpy(beta)[:, None].expand_as(dec._beta_table))
+                dec._alpha_table.fill_(1.0)
+        elif kind == "rcq":
+            dec = L.RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=qp, max_iterations=T)
+        else:
+            dec = L.WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=qp, weight_sharing_type=1, max_iterations=T)
+            with torch.no_grad():
+                dec._beta_table.copy_(torch.from_numpy(beta)[:, None].expand_as(dec._beta_table))
+        eng = dec._engine(local_rank)
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        for snr in snrs:
+            eng.mc_round(snr, B, seed=7, frame0=rank * B, llr_sign=1, counters=counters)     # warm-up / allocation
+            barrier()
+            counters.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for r in range(rounds):
+                eng.mc_round(snr, B, seed=11, frame0=(r * world + rank) * B, llr_sign=1, counters=counters)
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(counters)
+            fe, be, it, nf = (int(v) for v in counters.tolist())
+            fps = nf / (float(ms.item()) / 1e3)
+            out.append({"snr_db": snr, "max_iterations": T, "compaction": bool(compact), "frames": nf,
+                        "frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "avg_iterations": it / max(nf, 1),
+                        "fer": fe / max(nf, 1), "ber": be / max(nf * code.n, 1)})
+        del dec, eng
+    os.environ.pop("LDPC_COMPACT", None)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -382,6 +429,13 @@ def run_ours(args):
         for p in (pin_llr, pin_bits, pin_it, pin_su):
             p.free()
 
+    # ---- early-stop leg: BASELINE configs[4] shape -- T = 50, LLRs of the all-zero codeword in the
+    # converging sign convention, AWGN generated on the device (ldpc_mc_round), frames stop at different
+    # iterations; with and without frame compaction.  Reported next to the headline, not part of `value`.
+    early = None
+    if not args.no_mc and kind != "basic":
+        early = mc_leg(L, code, kind, B, local_rank, rank, world, barrier, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _, _ = cpu_leg(L, code, kind, args.cpu_seconds, os.cpu_count() or 1)
@@ -396,7 +450,8 @@ def run_ours(args):
                        "n": g.n, "k": code.k, "E": g.E, "iterations": T_ITERS, "early_stop": True,
                        "l2": "inputs larger than L2 (message arrays %.1f GB per GPU)" % (2 * 4 * g.E * Bp / 1e9),
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(prof["launches"]),
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "early_stop_mc": early,
+            "gpu_launches": int(prof["launches"]),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

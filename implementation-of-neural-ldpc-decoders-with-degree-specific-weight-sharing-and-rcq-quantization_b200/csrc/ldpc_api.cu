@@ -322,7 +322,9 @@ struct Workspace {
     uint8_t* done = nullptr;
     int32_t* iters = nullptr;
     uint8_t* success = nullptr;
+    int32_t* fcnt = nullptr;    // [Bp] per-frame bit-error scratch of the Monte-Carlo count
     void release() {
+        cudaFree(fcnt);
         cudaFree(llrT); cudaFree(v2c); cudaFree(c2v); cudaFree(hardw); cudaFree(unsat);
         cudaFree(done); cudaFree(iters); cudaFree(success);
         *this = Workspace();
@@ -437,6 +439,7 @@ int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     CU(cudaMalloc((void**)&ws.done, (size_t)Bp));
     CU(cudaMalloc((void**)&ws.iters, (size_t)Bp * sizeof(int32_t)));
     CU(cudaMalloc((void**)&ws.success, (size_t)Bp));
+    CU(cudaMalloc((void**)&ws.fcnt, (size_t)Bp * sizeof(int32_t)));
     ws.cap = Bp;
     return LDPC_OK;
 }
@@ -530,7 +533,7 @@ struct OutSpec {
     int32_t* frame_iters = nullptr;
 };
 
-void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, CnLaunch& cn) {
+void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool want_post, CnLaunch& cn) {
     const ldpc_graph* g = d->g;
     const int q = d->bc ? d->q_of_iter[t] : 0;
     cn.src = (t == 0) ? ws.llrT : ws.v2c;
@@ -549,6 +552,7 @@ void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, CnLaunch& cn) {
     cn.items_wide_begin = g->cn_wide_begin;
     cn.items_wide_end = g->cn_wide_end;
     cn.wide_ring = d->wide_ring;
+    cn.freeze = want_post ? 1 : 0;
     cn.Bp = Bp;
     if (d->check_rule == LDPC_RULE_OFFSET) {
         cn.aidx_slot = d->d_aidx_slot;
@@ -580,17 +584,19 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.n_items = (int)g->vn_items.size();
     vn.Bp = Bp;
     vn.final_pass = final_pass ? 1 : 0;
+    vn.freeze = want_post ? 1 : 0;
 }
 
-// Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node pass:
-// it recomputes posterior + decision of EVERY frame from its frozen c2v (frames that stopped at iteration t
-// kept c2v(t)); the dead v2c update of iteration T-1 is not written.
+// Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node pass: the
+// dead v2c update of iteration T-1 is not written, and when posteriors are wanted it recomputes them for EVERY
+// frame from its frozen c2v (frames that stopped at iteration t kept c2v(t)); packed decisions of stopped
+// frames stay in place from the iteration they stopped at.
 int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool want_post, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
     const int64_t Wn = Bp / 32;
     for (int t = t0; t < t1; ++t) {
         CnLaunch cn{};
-        fill_cn(d, ws, Bp, t, cn);
+        fill_cn(d, ws, Bp, t, want_post, cn);
         if (d->check_rule == LDPC_RULE_OFFSET) LAUNCH(K_CN, launch_cn_offset(d->dtype, cn, stream));
         else LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
         const bool last = (t == d->T - 1);
@@ -614,8 +620,8 @@ int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool wa
     return LDPC_OK;
 }
 
-// The final pass on its own (frames of a level whose remaining frames have all stopped, or whose running
-// frames are about to move to a compacted level): decisions / posteriors of every frame from its frozen c2v.
+// The final pass on its own, for forward()'s posterior output (a level whose frames have all stopped, or whose
+// running frames are about to move to a compacted level): posteriors of every frame from its frozen c2v.
 int run_final_pass(ldpc_decoder* d, Workspace& ws, int64_t Bp, bool want_post, cudaStream_t stream) {
     VnLaunch vn{};
     fill_vn(d, ws, Bp, d->T - 1, true, want_post, vn);
@@ -630,7 +636,7 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
     const ldpc_graph* g = d->g;
     if (o.count) {
         LAUNCH(K_OTHER, launch_count_packed(d->V, ws.hardw, Bp / 32, g->n, B, o.codeword, ws.iters, o.counters,
-                                            o.frame_bit_errors, o.frame_iters, map, only_done, stream));
+                                            o.frame_bit_errors, o.frame_iters, map, only_done, ws.fcnt, stream));
         return LDPC_OK;
     }
     // running frames of a parent level also write their (unfinished) rows here; the next level overwrites them
@@ -647,9 +653,12 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
 }
 
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
-int next_checkpoint(int t, int T) {
+// Large batches can afford a look every other iteration (an iteration is milliseconds long); small ones
+// space the checkpoints out so that the syncs stay a small part of the decode.
+int next_checkpoint(int t, int T, int64_t Bp) {
     int c;
-    if (t < 8) c = t + 2;
+    if (Bp >= 4096) c = t + (t < 20 ? 2 : 4);
+    else if (t < 8) c = t + 2;
     else if (t < 24) c = t + 4;
     else c = t + 8;
     return c < T ? c : T;
@@ -696,7 +705,7 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         if (rc) return rc;
     }
     while (true) {
-        const int t1 = checkpoints ? next_checkpoint(t, d->T) : d->T;
+        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp) : d->T;
         int rc = run_span(d, *ws, curBp, t, t1, want_post, stream);
         if (rc) return rc;
         t = t1;
@@ -707,8 +716,10 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         const int64_t pending = *d->h_total;
         if (pending == 0) {
             d->stat_early_exits++;
-            rc = run_final_pass(d, *ws, curBp, want_post, stream);
-            if (rc) return rc;
+            if (want_post) {   // decisions of stopped frames are already in place; posteriors are not
+                rc = run_final_pass(d, *ws, curBp, want_post, stream);
+                if (rc) return rc;
+            }
             return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
         }
         if (curBp < d->compact_min_frames || pending * 10 > curBp * 6 || level >= kMaxLevels) continue;
@@ -739,8 +750,10 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->v2c, curBp, lv.ws.v2c, childBp, lv.idx, pending, g->E, stream));
         LAUNCH(K_OTHER, launch_reset_state(lv.ws.done, lv.ws.iters, lv.ws.success, lv.ws.unsat, pending, childBp, d->T, stream));
         // the parent's finished frames: final pass (after the gather: it reuses v2c for the posteriors) and delivery
-        rc = run_final_pass(d, *ws, curBp, want_post, stream);
-        if (rc) return rc;
+        if (want_post) {
+            rc = run_final_pass(d, *ws, curBp, want_post, stream);
+            if (rc) return rc;
+        }
         rc = emit_level(d, *ws, curB, curBp, map, ws->done, o, stream);
         if (rc) return rc;
         d->stat_compactions++;

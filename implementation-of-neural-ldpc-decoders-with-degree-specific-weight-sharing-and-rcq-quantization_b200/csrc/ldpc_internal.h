@@ -39,6 +39,7 @@ struct CnLaunch {
     int items_wide_begin;       // items [begin, end) hold checks of degree 9..64 (sorted by degree)
     int items_wide_end;
     int wide_ring;              // 1: those items run in the bulk-async row-ring kernel
+    int freeze;                 // 1: stopped frames keep their c2v (their posterior is still to be delivered)
     int64_t Bp;
 };
 
@@ -64,6 +65,7 @@ struct VnLaunch {
     int n_items;
     int64_t Bp;
     int final_pass;
+    int freeze;                 // 1: stopped frames keep their v2c / c2v
 };
 
 struct SynLaunch {
@@ -114,7 +116,7 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B,
                                 const uint8_t* codeword, const int32_t* iters, int64_t* counters,
                                 int32_t* frame_bit_errors, int32_t* frame_iters, const int32_t* map,
-                                const uint8_t* only_done, cudaStream_t stream);
+                                const uint8_t* only_done, int32_t* frame_cnt /* scratch [Wn*32] */, cudaStream_t stream);
 // frame compaction bookkeeping: counts[ceil(Bp/1024)] becomes the exclusive scan of running frames per
 // 1024-frame block and total[0] their number; then idx[0..total) = the running frames in ascending order
 cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, cudaStream_t stream);

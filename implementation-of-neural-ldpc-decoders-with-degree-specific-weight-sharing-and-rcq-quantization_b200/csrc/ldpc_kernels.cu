@@ -66,16 +66,17 @@ __device__ __forceinline__ T* row_at(T* base, uint32_t row, uint32_t stride_byte
     return reinterpret_cast<T*>(reinterpret_cast<C*>(base) + (uint64_t)row * stride_bytes);
 }
 
-// Store V frames of one row; frames whose done bit is set keep their old (frozen) value.
+// Store V frames of one row; frames whose bit is set in `keep` hold on to their old (frozen) value: the row
+// segment is read, merged and written back whole, so the access stays one vector transaction per lane.
 template <typename T, int V>
-__device__ __forceinline__ void store_masked(T* __restrict__ rowptr, const Pack<T, V>& val, uint32_t dmask) {
-    if (dmask == 0) {
-        st_stream<Pack<T, V>>(rowptr, val);
-    } else {
+__device__ __forceinline__ void store_masked(T* __restrict__ rowptr, Pack<T, V> val, uint32_t keep) {
+    if (keep != 0) {
+        const Pack<T, V> old = *reinterpret_cast<const Pack<T, V>*>(rowptr);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-            if (!((dmask >> v) & 1u)) rowptr[v] = val.v[v];
+            if ((keep >> v) & 1u) val.v[v] = old.v[v];
     }
+    st_stream<Pack<T, V>>(rowptr, val);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,7 +450,8 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
 // resident CTAs per SM the check-node kernel is compiled for: the RCQ variant is issue-bound and gains from
 // 4 (64 registers); float32 / float64 stream at the HBM roofline with 3 / 2
 #define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : 2))
-template <typename Real, bool QUANT, int NTH>
+// FREEZE: stopped frames keep their c2v (forward()'s posterior output); otherwise the stores carry no mask code.
+template <typename Real, bool QUANT, int NTH, bool FREEZE>
 __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     __shared__ float s_thr[kMaxQuantLevels];
@@ -463,8 +465,9 @@ __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const 
     const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;  // whole warps: Bp is a multiple of 32*V
-    const uint32_t dmask = load_done_mask<V>(p.done, f0);
-    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    const uint32_t done_mask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u))) return;
+    const uint32_t dmask = FREEZE ? done_mask : 0u;   // otherwise nobody reads the messages of stopped frames
     const WorkItem it = p.items[item_id];
     int64_t slot = it.first_slot;
 #define LDPC_CN_CASE(D)                                                                   \
@@ -719,7 +722,7 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
     }
 }
 
-template <typename Real, bool QUANT, int NTH>
+template <typename Real, bool QUANT, int NTH, bool FREEZE>
 __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ __align__(128) unsigned char wide_smem[];
@@ -739,10 +742,11 @@ __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(con
     const int item_id = item0 + blockIdx.x / nfb;
     const int64_t cta_f0 = (int64_t)fb * kWideThreads * V;
     const int64_t f0 = cta_f0 + (int64_t)threadIdx.x * V;
-    uint32_t dmask = (1u << V) - 1u;
-    if (f0 < p.Bp) dmask = load_done_mask<V>(p.done, f0);
-    const bool active = !__all_sync(0xffffffffu, dmask == ((1u << V) - 1u));   // warp-uniform
+    uint32_t done_mask = (1u << V) - 1u;
+    if (f0 < p.Bp) done_mask = load_done_mask<V>(p.done, f0);
+    const bool active = !__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u));   // warp-uniform
     if (!__syncthreads_or(active ? 1 : 0)) return;   // also publishes the barriers and s_thr
+    const uint32_t dmask = FREEZE ? done_mask : 0u;
     if (QUANT) qz.load(s_thr, p.nth, p.mono != 0);
     const WorkItem it = p.items[item_id];
     RowRing<Real> ring;
@@ -770,10 +774,12 @@ __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(con
     }
 }
 
-// One 32-bit word per (variable, V-th frame of 32 lanes): bit = lane.
+// One 32-bit word per (variable, V-th frame of 32 lanes): bit = lane.  `keepw` (lanes < V: the word of this
+// lane's frame slot) marks frames that have stopped: their decisions of the iteration they stopped at stay in
+// place (read-modify-write), so no later pass has to recompute them.
 template <typename Real, int V>
 __device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t Wn, int64_t j, int64_t wbase,
-                                           const bool (&bit)[V]) {
+                                           const bool (&bit)[V], uint32_t keepw) {
     uint32_t words[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) words[v] = __ballot_sync(0xffffffffu, bit[v]);
@@ -783,8 +789,23 @@ __device__ __forceinline__ void write_hard(uint32_t* __restrict__ hardw, int64_t
 #pragma unroll
         for (int v = 1; v < V; ++v)
             if (lane == v) w = words[v];
-        hardw[j * Wn + wbase + lane] = w;
+        uint32_t* ptr = hardw + j * Wn + wbase + lane;
+        if (keepw) w = (w & ~keepw) | (*ptr & keepw);
+        *ptr = w;
     }
+}
+
+// keep-word of this lane (see write_hard) from the per-lane done masks of the warp
+template <int V>
+__device__ __forceinline__ uint32_t keep_word(uint32_t dmask) {
+    uint32_t kw = 0;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (dmask >> v) & 1u);
+        if (lane == v) kw = b;
+    }
+    return kw;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -880,15 +901,16 @@ __device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t
     }
 }
 
-template <typename Real>
+template <typename Real, bool FREEZE>
 __global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb) {
     constexpr int V = FramesPerLane<Real>::value;
     const int fb = blockIdx.x % nfb;
     const int item_id = blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
-    const uint32_t dmask = load_done_mask<V>(p.done, f0);
-    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    const uint32_t done_mask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u))) return;
+    const uint32_t dmask = FREEZE ? done_mask : 0u;
     const WorkItem it = p.items[item_id];
     int64_t slot = it.first_slot;
 #define LDPC_CNO_CASE(D)                                                \
@@ -968,7 +990,7 @@ __global__ void __launch_bounds__(kThreads) hard_kernel(const Real* __restrict__
         bool bit[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) bit[v] = x.v[v] < Real(0);
-        write_hard<Real, V>(hardw, Wn, j, wbase, bit);
+        write_hard<Real, V>(hardw, Wn, j, wbase, bit, 0u);
     }
 }
 
@@ -993,8 +1015,8 @@ __device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t 
 // has only 3 loads to overlap; RCQ code rows are just 128 bytes per warp).
 template <typename Real, bool QUANT, bool FINAL, int DV, int U>
 __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, int64_t lbase, int64_t f0,
-                                              uint32_t dmask, int64_t wbase, const float* s_lut,
-                                              const int (&lutbase)[FramesPerLane<Real>::value]) {
+                                              uint32_t dmask, uint32_t smask, uint32_t keepw, int64_t wbase,
+                                              const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
     constexpr int D1 = DV > 0 ? DV : 1;
     using InT = typename CnOut<Real, QUANT>::type;
@@ -1051,22 +1073,22 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
             Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
             Real pv = (DV > 0) ? Arith<Real>::add(L[u].v[v], tot) : L[u].v[v];
             post.v[v] = pv;
-            bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
+            bit[v] = (pv < Real(0)) && !((dmask >> v) & 1u);
         }
         if constexpr (!FINAL) {
 #pragma unroll
-            for (int d = 0; d < DV; ++d) store_masked<Real, V>(row_at(v2c, slot[u][d], real_stride), out[d], dmask);
+            for (int d = 0; d < DV; ++d) store_masked<Real, V>(row_at(v2c, slot[u][d], real_stride), out[d], smask);
         } else {
             if (p.postT) st_stream<Pack<Real, V>>(row_at(static_cast<Real*>(p.postT) + f0, j[u], real_stride), post);
         }
-        write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit);
+        write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit, keepw);
     }
 }
 
 // All variables of one work item, in groups of U (remainder one by one).
 template <typename Real, bool QUANT, bool FINAL, int DV>
 __device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem& it, int64_t f0, uint32_t dmask,
-                                              int64_t wbase, const float* s_lut,
+                                              uint32_t smask, uint32_t keepw, int64_t wbase, const float* s_lut,
                                               const int (&lutbase)[FramesPerLane<Real>::value]) {
     // byte-wide RCQ code rows need more rows in flight than 16-byte float rows
     constexpr int U = QUANT ? ((DV <= 2) ? LDPC_VN_UQ_LO : ((DV <= 4) ? LDPC_VN_UQ_MID : LDPC_VN_UQ_HI))
@@ -1076,15 +1098,15 @@ __device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem&
     int c = 0;
     if constexpr (U > 1) {
         for (; c + U <= it.count; c += U, lbase += U * DV, vpos += U)
-            vn_node_small<Real, QUANT, FINAL, DV, U>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);
+            vn_node_small<Real, QUANT, FINAL, DV, U>(p, vpos, lbase, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
     }
     for (; c < it.count; ++c, lbase += DV, ++vpos)
-        vn_node_small<Real, QUANT, FINAL, DV, 1>(p, vpos, lbase, f0, dmask, wbase, s_lut, lutbase);
+        vn_node_small<Real, QUANT, FINAL, DV, 1>(p, vpos, lbase, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
 }
 
 template <typename Real, bool QUANT, bool FINAL>
 __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, int dv, int64_t f0, uint32_t dmask,
-                                int64_t wbase, const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
+                                uint32_t smask, uint32_t keepw, int64_t wbase, const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
     const int64_t j = __ldg(p.vpos_var + vpos);
@@ -1107,7 +1129,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
         Real tot = LibSum<Real>::dyn(elem, dv);
         Real pv = dv > 0 ? Arith<Real>::add(L.v[v], tot) : L.v[v];
         post.v[v] = pv;
-        bit[v] = (pv < Real(0)) && (FINAL || !((dmask >> v) & 1u));
+        bit[v] = (pv < Real(0)) && !((dmask >> v) & 1u);
     }
     if constexpr (!FINAL) {
         // all sums are formed from c2v before any v2c of this variable is written (separate arrays)
@@ -1124,15 +1146,16 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
                 out.v[v] = Arith<Real>::add(L.v[v], s);
             }
             int64_t sd = __ldg(p.vslots + lbase + d);
-            store_masked<Real, V>(v2c + sd * p.Bp + f0, out, dmask);
+            store_masked<Real, V>(v2c + sd * p.Bp + f0, out, smask);
         }
     } else {
         if (p.postT) *reinterpret_cast<Pack<Real, V>*>(static_cast<Real*>(p.postT) + j * p.Bp + f0) = post;
     }
-    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit);
+    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
 }
 
-template <typename Real, bool QUANT, bool FINAL>
+// FREEZE: stopped frames keep their v2c (forward()'s posterior output); otherwise their stores are plain.
+template <typename Real, bool QUANT, bool FINAL, bool FREEZE>
 __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ float s_lut[];
@@ -1145,11 +1168,16 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
     const int item_id = blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
+    // Stopped frames keep their messages and their packed decisions in place; only forward()'s posterior
+    // output makes the final pass recompute them (posterior of the iteration a frame stopped at, from its
+    // frozen c2v).
     uint32_t dmask = 0;
-    if (!FINAL) {
+    if (!FINAL || p.postT == nullptr) {
         dmask = load_done_mask<V>(p.done, f0);
         if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
     }
+    const uint32_t keepw = keep_word<V>(dmask);
+    const uint32_t smask = FREEZE ? dmask : 0u;
     int lutbase[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -1170,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
     int32_t vpos = it.first_node;
 #define LDPC_VN_CASE(D)                                                                               \
     case D:                                                                                           \
-        vn_item_small<Real, QUANT, FINAL, D>(p, it, f0, dmask, wbase, s_lut, lutbase);                \
+        vn_item_small<Real, QUANT, FINAL, D>(p, it, f0, dmask, smask, keepw, wbase, s_lut, lutbase);  \
         break;
     switch (it.deg) {
         LDPC_VN_CASE(0)
@@ -1184,7 +1212,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
         LDPC_VN_CASE(8)
         default:
             for (int c = 0; c < it.count; ++c, lbase += it.deg, ++vpos)
-                vn_node_generic<Real, QUANT, FINAL>(p, vpos, lbase, it.deg, f0, dmask, wbase, s_lut, lutbase);
+                vn_node_generic<Real, QUANT, FINAL>(p, vpos, lbase, it.deg, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
     }
 #undef LDPC_VN_CASE
 }
@@ -1394,30 +1422,58 @@ __device__ __forceinline__ void accumulate_counters(int64_t* counters, int ferr,
     }
 }
 
-__global__ void count_packed_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, int32_t n, int64_t B,
-                                    const uint8_t* __restrict__ codeword, const int32_t* __restrict__ iters,
-                                    int64_t* counters, int32_t* __restrict__ frame_bit_errors,
-                                    int32_t* __restrict__ frame_iters, const int32_t* __restrict__ map,
-                                    const uint8_t* __restrict__ only_done) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Bit errors per frame from the packed decisions.  Pass 1: a thread owns one 32-frame word and a chunk of
+// variables (coalesced word loads), counts per bit in registers and adds the non-zero counts to
+// frame_cnt[frame]; pass 2: one thread per frame folds them into the counters / per-frame outputs.
+constexpr int kCountVarChunk = 128;
+
+__global__ void __launch_bounds__(128) count_partial_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, int32_t n,
+                                                             const uint8_t* __restrict__ codeword,
+                                                             int32_t* __restrict__ frame_cnt) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= Wn) return;
-    int cnt = 0;
-    for (int32_t j = 0; j < n; ++j) {
-        uint32_t word = __ldg(hardw + (int64_t)j * Wn + w);
-        uint32_t bit = (word >> lane) & 1u;
-        if (codeword) bit ^= (uint32_t)__ldg(codeword + j);
-        cnt += (int)bit;
+    const int32_t j0 = blockIdx.y * kCountVarChunk, j1 = min(n, j0 + kCountVarChunk);
+    // vertical (bit-sliced) counters: plane[k] holds bit k of the 32 per-frame counts (kCountVarChunk < 256)
+    uint32_t plane[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) plane[k] = 0;
+    for (int32_t j = j0; j < j1; ++j) {
+        uint32_t carry = __ldg(hardw + (int64_t)j * Wn + w);
+        if (codeword && __ldg(codeword + j)) carry = ~carry;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t t = plane[k] & carry;
+            plane[k] ^= carry;
+            carry = t;
+        }
     }
-    const int64_t f = wordbit_to_frame(w, lane, V);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) any |= plane[k];
+    while (any) {
+        const int b = __ffs(any) - 1;
+        any &= any - 1;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnt |= (int)((plane[k] >> b) & 1u) << k;
+        atomicAdd(frame_cnt + wordbit_to_frame(w, b, V), cnt);
+    }
+}
+
+__global__ void count_final_kernel(const int32_t* __restrict__ frame_cnt, int64_t B, const int32_t* __restrict__ iters,
+                                   int64_t* counters, int32_t* __restrict__ frame_bit_errors,
+                                   int32_t* __restrict__ frame_iters, const int32_t* __restrict__ map,
+                                   const uint8_t* __restrict__ only_done) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int valid = f < B && !(only_done && !only_done[f]);   // frames handed on to a compacted level are counted there
+    const int cnt = valid ? frame_cnt[f] : 0;
     const int it = valid ? iters[f] : 0;
     if (valid) {
         const int64_t fo = map ? (int64_t)map[f] : f;
         if (frame_bit_errors) frame_bit_errors[fo] = cnt;
         if (frame_iters) frame_iters[fo] = it;
     }
-    accumulate_counters(counters, valid && cnt > 0, valid ? cnt : 0, it, valid);
+    accumulate_counters(counters, valid && cnt > 0, cnt, it, valid);
 }
 
 __global__ void count_bits_kernel(const uint8_t* __restrict__ bits, int32_t n, int64_t B,
@@ -1575,37 +1631,42 @@ inline int threads_for(int64_t Bp, int V) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-template <typename Real, bool QUANT, int NTH>
+template <typename Real, bool QUANT, int NTH, bool FREEZE>
 cudaError_t launch_cn_range(const CnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
     if (item1 <= item0) return cudaSuccess;
     constexpr int V = FramesPerLane<Real>::value;
     if (wide) {
         // per device and cheap, so simply repeated on every launch
-        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, QUANT, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, QUANT, NTH, FREEZE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kWideSmem);
         if (e != cudaSuccess) return e;
         const int64_t nfb = (p.Bp + (int64_t)kWideThreads * V - 1) / ((int64_t)kWideThreads * V);
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_wide_kernel<Real, QUANT, NTH><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
+        cn_wide_kernel<Real, QUANT, NTH, FREEZE><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
     } else {
         const int threads = threads_for(p.Bp, V);
         const int64_t nfb = (p.Bp / V + threads - 1) / threads;
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_kernel<Real, QUANT, NTH><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
+        cn_kernel<Real, QUANT, NTH, FREEZE><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
     }
     return cudaGetLastError();
 }
 
-template <typename Real, bool QUANT, int NTH>
-cudaError_t launch_cn_all(const CnLaunch& p, cudaStream_t stream) {
+template <typename Real, bool QUANT, int NTH, bool FREEZE>
+cudaError_t launch_cn_frz(const CnLaunch& p, cudaStream_t stream) {
     // items are sorted by degree: [0, wide0) degree <= 8, [wide0, wide1) degree 9..64 (row ring), rest > 64
     const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
-    cudaError_t e = launch_cn_range<Real, QUANT, NTH>(p, 0, wide0, false, stream);
-    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide0, wide1, true, stream);
-    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide1, p.n_items, false, stream);
+    cudaError_t e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, wide1, p.n_items, false, stream);
     return e;
+}
+
+template <typename Real, bool QUANT, int NTH>
+cudaError_t launch_cn_all(const CnLaunch& p, cudaStream_t stream) {
+    return p.freeze ? launch_cn_frz<Real, QUANT, NTH, true>(p, stream) : launch_cn_frz<Real, QUANT, NTH, false>(p, stream);
 }
 
 }  // namespace
@@ -1631,8 +1692,13 @@ cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) 
     const int64_t nfb = (p.Bp / V + threads - 1) / threads;
     const int64_t grid = nfb * p.n_items;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (dtype == 0) cn_offset_kernel<float><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
-    else cn_offset_kernel<double><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    if (dtype == 0) {
+        if (p.freeze) cn_offset_kernel<float, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        else cn_offset_kernel<float, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    } else {
+        if (p.freeze) cn_offset_kernel<double, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        else cn_offset_kernel<double, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+    }
     return cudaGetLastError();
 }
 
@@ -1664,18 +1730,19 @@ cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream) {
     const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
     const unsigned g = (unsigned)grid;
     const int nf = (int)nfb;
+#define LDPC_VN_LAUNCH(REAL, Q)                                                                              \
+    do {                                                                                                     \
+        if (p.final_pass) vn_kernel<REAL, Q, true, false><<<g, threads, smem, stream>>>(p, nf);              \
+        else if (p.freeze) vn_kernel<REAL, Q, false, true><<<g, threads, smem, stream>>>(p, nf);             \
+        else vn_kernel<REAL, Q, false, false><<<g, threads, smem, stream>>>(p, nf);                          \
+    } while (0)
     if (dtype == 0) {
-        if (p.bc) {
-            if (p.final_pass) vn_kernel<float, true, true><<<g, threads, smem, stream>>>(p, nf);
-            else vn_kernel<float, true, false><<<g, threads, smem, stream>>>(p, nf);
-        } else {
-            if (p.final_pass) vn_kernel<float, false, true><<<g, threads, smem, stream>>>(p, nf);
-            else vn_kernel<float, false, false><<<g, threads, smem, stream>>>(p, nf);
-        }
+        if (p.bc) LDPC_VN_LAUNCH(float, true);
+        else LDPC_VN_LAUNCH(float, false);
     } else {
-        if (p.final_pass) vn_kernel<double, false, true><<<g, threads, smem, stream>>>(p, nf);
-        else vn_kernel<double, false, false><<<g, threads, smem, stream>>>(p, nf);
+        LDPC_VN_LAUNCH(double, false);
     }
+#undef LDPC_VN_LAUNCH
     return cudaGetLastError();
 }
 
@@ -1749,10 +1816,14 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
 
 cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_t n, int64_t B, const uint8_t* codeword,
                                 const int32_t* iters, int64_t* counters, int32_t* frame_bit_errors,
-                                int32_t* frame_iters, const int32_t* map, const uint8_t* only_done, cudaStream_t stream) {
-    const int warps = 4;
-    count_packed_kernel<<<(unsigned)((Wn + warps - 1) / warps), warps * 32, 0, stream>>>(
-        V, hardw, Wn, n, B, codeword, iters, counters, frame_bit_errors, frame_iters, map, only_done);
+                                int32_t* frame_iters, const int32_t* map, const uint8_t* only_done, int32_t* frame_cnt,
+                                cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(frame_cnt, 0, (size_t)Wn * 32 * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((Wn + 127) / 128), (unsigned)((n + kCountVarChunk - 1) / kCountVarChunk));
+    count_partial_kernel<<<grid, 128, 0, stream>>>(V, hardw, Wn, n, codeword, frame_cnt);
+    count_final_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(frame_cnt, B, iters, counters, frame_bit_errors,
+                                                                          frame_iters, map, only_done);
     return cudaGetLastError();
 }
 
