@@ -35,13 +35,17 @@ UNIT = "info Gb/s"
 T_ITERS = 10
 SNR_DB = 2.0
 # dram__bytes_read.sum + dram__bytes_write.sum per FRAME of one launch, from the committed `ncu --set full`
-# captures (profiles/r01_ncu_full_*_8192frames.csv: bytes of one launch / 8192 frames); scaled by the
+# captures (profiles/r01b_ncu_full_*_8192frames_raw.csv: bytes of one launch / 8192 frames); scaled by the
 # frames of the benchmarked launch.  Only the captured (decoder, code, kernel) pairs have an entry.
 NCU_TRAFFIC_BYTES_PER_FRAME = {
-    ("n2d2", "dvbs2", "vn_kernel"): (2.123935e9 + 1.572802e9) / 8192,
-    ("n2d2", "dvbs2", "cn_kernel"): (1.592792e9 + 1.542397e9) / 8192,
-    ("rcq", "dvbs2", "vn_kernel"): (0.929394e9 + 1.550779e9) / 8192,
-    ("rcq", "dvbs2", "cn_kernel"): (1.592605e9 + 0.370780e9) / 8192,
+    ("n2d2", "dvbs2", "vn_kernel"): (2.123882e9 + 1.558320e9) / 8192,
+    ("n2d2", "dvbs2", "cn_kernel"): (1.592799e9 + 1.542210e9) / 8192,
+    ("rcq", "dvbs2", "vn_kernel"): (0.929480e9 + 1.551163e9) / 8192,
+    ("rcq", "dvbs2", "cn_kernel"): (1.592856e9 + 0.371589e9) / 8192,
+    ("n2d2", "qc", "vn_kernel"): (1.552332e9 + 1.204139e9) / 8192,
+    ("n2d2", "qc", "cn_kernel"): (1.242029e9 + 1.192600e9) / 8192,       # cn_wide_kernel (row ring)
+    ("wrcq1", "qc", "vn_kernel"): (0.621112e9 + 1.193412e9) / 8192,
+    ("wrcq1", "qc", "cn_kernel"): (1.241724e9 + 0.280145e9) / 8192,      # cn_wide_kernel (row ring)
 }
 
 
@@ -383,7 +387,7 @@ def run_ours(args):
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
         "traffic": (NCU_TRAFFIC_BYTES_PER_FRAME[(kind, args.code, dominant)] * Bp
                     if (kind, args.code, dominant) in NCU_TRAFFIC_BYTES_PER_FRAME else None),
-        "traffic_source": "ncu --set full at 8192 frames per launch, scaled per frame (profiles/README.md)",
+        "traffic_source": "ncu --set full at 8192 frames per launch, scaled per frame (profiles/README.md, r01b captures)",
         "kernel": dominant, "peak_source": peak_src,
         "bytes_per_launch": vn_bytes if dominant == "vn_kernel" else cn_bytes,
         "avg_launch_ms": vn_ms if dominant == "vn_kernel" else cn_ms,
