@@ -153,3 +153,42 @@ def test_concurrent_decoders_from_threads(built_lib):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+def test_integration_md_binding_stub_runs(built_lib):
+    """The ctypes stub shown in INTEGRATION.md (binding the C ABI underneath a reference-style module) is
+    executed verbatim against the built library and must agree with the shipped class."""
+    import os
+    import re
+    import types
+    from conftest import ROOT
+    L = built_lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code_block = re.search(r"```python\n(# ldpc_b200_binding\.py.*?)```", md, re.S).group(1)
+    code_block = code_block.replace('C.CDLL("libldpc_b200.so")', f'C.CDLL({L._lib_mod.LIB_PATH!r})')
+    ns = {}
+    exec(compile(code_block, "INTEGRATION.md", "exec"), ns)
+
+    code = L.create_test_ldpc_code()
+    T = 6
+    torch.manual_seed(4)
+    ours = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
+    with torch.no_grad():
+        ours._beta_table.uniform_(0.5, 1.0)
+        ours._alpha_table.uniform_(0.8, 1.0)
+    beta_full = ours._beta_table.detach().numpy()[:, ours._beta_index]     # [T, E] in check-major edge order
+    alpha_full = ours._alpha_table.detach().numpy()[:, ours._alpha_index]  # [T, n]
+    rows, cols = np.nonzero(np.asarray(code.H) == 1)
+    edge_of = {(int(i), int(j)): e for e, (i, j) in enumerate(zip(rows, cols))}
+    # a stand-in with the reference module's surface the stub touches (neural_2d_decoder.py:84-131)
+    fake = types.SimpleNamespace(
+        code=types.SimpleNamespace(H=np.asarray(code.H)), max_iterations=T,
+        _get_beta_weight=lambda t, i, j: torch.tensor(beta_full[t, edge_of[(i, j)]]),
+        _get_alpha_weight=lambda t, i, j: torch.tensor(alpha_full[t, j]))
+    ns["attach"](fake, device=0)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        llr = torch.from_numpy((rng.standard_normal(7) * 2 + 1).astype(np.float32))
+        b0, p0, i0 = ours(llr)
+        b1, p1, i1 = ns["forward"](fake, llr)
+        assert torch.equal(b0, b1) and torch.equal(p0, p1) and i0 == i1
