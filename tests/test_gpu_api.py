@@ -192,3 +192,57 @@ def test_integration_md_binding_stub_runs(built_lib):
         b0, p0, i0 = ours(llr)
         b1, p1, i1 = ns["forward"](fake, llr)
         assert torch.equal(b0, b1) and torch.equal(p0, p1) and i0 == i1
+
+
+@pytest.mark.parametrize("kind,cname,snr", [("rcq", "dvbs2", 3.0), ("wrcq1", "qc", 5.8), ("n2d2", "qc", 5.8),
+                                             ("wrcq1", "dvbs2", 3.0)])
+def test_full_size_named_configs_properties_and_oracle_sample(built_lib, kind, cname, snr):
+    """BASELINE configs 3 and 4 at their full code sizes (RCQ bc=3 on the (16200,7200) shape, W-RCQ type 1 on the
+    (9472,8192)-shaped QC code, both through the row-ring / SWAR kernels): success <=> zero syndrome,
+    iterations == T for every failed frame, and a random sample of frames bit-exact against the oracle."""
+    from oracle import capi as O
+    from oracle.restatement import MODE_NMS, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule
+    L = built_lib
+    T = 12
+    code = L.codes.dvbs2_shaped(max_iterations=T) if cname == "dvbs2" else L.codes.qc_shaped(max_iterations=T)
+    g = code.graph
+    B = 3000
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    torch.manual_seed(5)
+    if kind == "rcq":
+        dec = L.RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=qp, max_iterations=T)
+    elif kind == "wrcq1":
+        dec = L.WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=qp, weight_sharing_type=1, max_iterations=T)
+        with torch.no_grad():
+            dec._beta_table.uniform_(0.8, 1.0)
+    else:
+        dec = L.Neural2DMinSumDecoder(code, 2, T)
+        with torch.no_grad():
+            dec._beta_table.uniform_(0.7, 0.9)
+            dec._alpha_table.fill_(1.0)
+    llr = torch.cat([L.awgn_llr(g.n, B // 2, snr, seed=21, llr_sign=1), L.awgn_llr(g.n, B - B // 2, snr + 1.0, seed=22, llr_sign=1)])
+    eng = dec._engine(0)
+    bits, post, iters, succ = eng.decode_device(llr, want_posterior=(kind != "rcq"))
+    bits_h, iters_h, succ_h = bits.cpu().numpy(), iters.cpu().numpy(), succ.cpu().numpy().astype(bool)
+    ok = g.syndrome(bits_h).sum(axis=1) == 0
+    assert np.array_equal(ok, succ_h)
+    assert (iters_h[~ok] == T).all() and (iters_h >= 1).all() and (iters_h <= T).all()
+    assert len(set(iters_h.tolist())) > 2, "operating point should spread the stopping iterations"
+    pick = np.random.default_rng(1).choice(B, 16, replace=False)
+    og = SparseGraph.from_coo(g.n, g.m, g.edge_check, g.check_var)
+    x = llr[pick].cpu().numpy()
+    if kind == "n2d2":
+        ref = O.decode(og, x, T=T, mode=MODE_NMS, beta=dec._beta_table.detach().numpy()[:, dec._beta_index],
+                       alpha=dec._alpha_table.detach().numpy()[:, dec._alpha_index], nthreads=8)
+    else:
+        thr = np.array([q.thresholds for q in dec.quantizers], dtype=np.float64).astype(np.float32)
+        kw = dict(T=T, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 3), nthreads=8)
+        if kind == "rcq":
+            ref = O.decode(og, x, mode=MODE_RCQ, **kw)
+        else:
+            ref = O.decode(og, x, mode=MODE_WRCQ, beta=dec._beta_table.detach().numpy()[:, dec._beta_index],
+                           alpha=np.ones((T, g.n), np.float32), **kw)
+    assert np.array_equal(bits_h[pick], ref.bits) and np.array_equal(iters_h[pick], ref.iterations)
+    assert np.array_equal(succ_h[pick], ref.success.astype(bool))
+    if post is not None:
+        assert np.array_equal(post[pick].cpu().numpy(), ref.posterior)
