@@ -1282,21 +1282,44 @@ __global__ void reset_kernel(uint8_t* __restrict__ done, int32_t* __restrict__ i
 // ---------------------------------------------------------------------------------------------
 // Layout conversion: user [B][n] row-major <-> interleaved [n][Bp]
 // ---------------------------------------------------------------------------------------------
-template <typename Real>
-__global__ void pack_kernel(const Real* __restrict__ llr, Real* __restrict__ llrT, int64_t B, int64_t Bp, int32_t n) {
-    __shared__ Real tile[32][33];
-    const int64_t f_base = (int64_t)blockIdx.x * 32;
-    const int32_t j_base = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int64_t f = f_base + r;
-        int32_t j = j_base + threadIdx.x;
-        tile[r][threadIdx.x] = (f < B && j < n) ? llr[f * n + j] : Real(0);
+// 64 frames x 64 variables per CTA; both the row-major reads and the interleaved writes move two elements per
+// lane (256- / 512-byte segments per warp instead of 128 / 256).  PAIR needs an even n (aligned row starts).
+template <typename Real, bool PAIR>
+__global__ void __launch_bounds__(256) pack_kernel(const Real* __restrict__ llr, Real* __restrict__ llrT, int64_t B,
+                                                    int64_t Bp, int32_t n) {
+    __shared__ Real tile[64][65];   // [variable][frame]
+    const int64_t f_base = (int64_t)blockIdx.x * 64;
+    const int32_t j_base = blockIdx.y * 64;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    for (int r = wy; r < 64; r += 8) {
+        const int64_t f = f_base + r;
+        const int32_t j = j_base + 2 * lane;
+        Real a = Real(0), b = Real(0);
+        if (f < B) {
+            if (PAIR) {
+                if (j < n) {   // n even: j + 1 < n as well
+                    const Pack<Real, 2> v = *reinterpret_cast<const Pack<Real, 2>*>(llr + f * n + j);
+                    a = v.v[0];
+                    b = v.v[1];
+                }
+            } else {
+                if (j < n) a = llr[f * n + j];
+                if (j + 1 < n) b = llr[f * n + j + 1];
+            }
+        }
+        tile[2 * lane][r] = a;
+        tile[2 * lane + 1][r] = b;
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int32_t j = j_base + r;
-        int64_t f = f_base + threadIdx.x;
-        if (j < n && f < Bp) llrT[(int64_t)j * Bp + f] = tile[threadIdx.x][r];
+    for (int c = wy; c < 64; c += 8) {
+        const int32_t j = j_base + c;
+        const int64_t f = f_base + 2 * lane;   // Bp is a multiple of 128: f + 1 < Bp whenever f < Bp
+        if (j < n && f < Bp) {
+            Pack<Real, 2> v;
+            v.v[0] = tile[c][2 * lane];
+            v.v[1] = tile[c][2 * lane + 1];
+            *reinterpret_cast<Pack<Real, 2>*>(llrT + (int64_t)j * Bp + f) = v;
+        }
     }
 }
 
@@ -1319,17 +1342,31 @@ __global__ void unpack_post_kernel(const Real* __restrict__ postT, Real* __restr
     }
 }
 
-// One warp: one hard word (32 frames) x 32 variables per step.
+// One warp: one hard word (32 frames) x 128 variables; a lane holds the words of 4 consecutive variables and
+// writes 4 bytes per frame (128-byte rows per warp store).  n % 4 != 0 falls back to byte stores at the tail.
 __global__ void unpack_bits_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, uint8_t* __restrict__ bits,
                                    int64_t B, int32_t n, const int32_t* __restrict__ map) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= Wn) return;
-    const int32_t j = blockIdx.x * 32 + lane;
-    const uint32_t word = (j < n) ? __ldg(hardw + (int64_t)j * Wn + w) : 0u;
+    const int32_t j = blockIdx.x * 128 + lane * 4;
+    uint32_t word[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) word[i] = (j + i < n) ? __ldg(hardw + (int64_t)(j + i) * Wn + w) : 0u;
+    const bool vec = (n % 4 == 0) && (j + 3 < n) && ((reinterpret_cast<uintptr_t>(bits) & 3u) == 0);
     for (int b = 0; b < 32; ++b) {
-        int64_t f = wordbit_to_frame(w, b, V);
-        if (f < B && j < n) bits[(map ? (int64_t)map[f] : f) * n + j] = (uint8_t)((word >> b) & 1u);
+        const int64_t f = wordbit_to_frame(w, b, V);
+        if (f >= B) continue;
+        uint8_t* row = bits + (map ? (int64_t)map[f] : f) * n + j;
+        if (vec) {
+            const uint32_t v = ((word[0] >> b) & 1u) | (((word[1] >> b) & 1u) << 8) | (((word[2] >> b) & 1u) << 16) |
+                               (((word[3] >> b) & 1u) << 24);
+            *reinterpret_cast<uint32_t*>(row) = v;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (j + i < n) row[i] = (uint8_t)((word[i] >> b) & 1u);
+        }
     }
 }
 
@@ -1774,17 +1811,22 @@ cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, 
 cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64_t Bp, int32_t n, uint8_t* done,
                         int32_t* iters, uint8_t* success, int32_t T, cudaStream_t stream) {
     (void)done; (void)iters; (void)success; (void)T;
-    dim3 block(32, 8);
-    dim3 grid((unsigned)((Bp + 31) / 32), (unsigned)((n + 31) / 32));
-    if (dtype == 0) pack_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(llr), static_cast<float*>(llrT), B, Bp, n);
-    else pack_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(llr), static_cast<double*>(llrT), B, Bp, n);
+    dim3 grid((unsigned)((Bp + 63) / 64), (unsigned)((n + 63) / 64));
+    const bool pair = (n % 2 == 0) && (reinterpret_cast<uintptr_t>(llr) % (dtype == 0 ? 8 : 16) == 0);
+    if (dtype == 0) {
+        if (pair) pack_kernel<float, true><<<grid, 256, 0, stream>>>(static_cast<const float*>(llr), static_cast<float*>(llrT), B, Bp, n);
+        else pack_kernel<float, false><<<grid, 256, 0, stream>>>(static_cast<const float*>(llr), static_cast<float*>(llrT), B, Bp, n);
+    } else {
+        if (pair) pack_kernel<double, true><<<grid, 256, 0, stream>>>(static_cast<const double*>(llr), static_cast<double*>(llrT), B, Bp, n);
+        else pack_kernel<double, false><<<grid, 256, 0, stream>>>(static_cast<const double*>(llr), static_cast<double*>(llrT), B, Bp, n);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B, int32_t n,
                                const int32_t* map, cudaStream_t stream) {
     const int warps = 8;
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((Wn + warps - 1) / warps));
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)((Wn + warps - 1) / warps));
     unpack_bits_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, bits, B, n, map);
     return cudaGetLastError();
 }
