@@ -654,13 +654,16 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
 
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
 // Large batches can afford a look every other iteration (an iteration is milliseconds long); small ones
-// space the checkpoints out so that the syncs stay a small part of the decode.
-int next_checkpoint(int t, int T, int64_t Bp) {
-    int c;
-    if (Bp >= 4096) c = t + (t < 20 ? 2 : 4);
-    else if (t < 8) c = t + 2;
-    else if (t < 24) c = t + 4;
-    else c = t + 8;
+// space the checkpoints out so that the syncs stay a small part of the decode.  `quiet` counts the
+// checkpoints in a row at which no frame had stopped yet: until the first frame stops the interval is doubled.
+int next_checkpoint(int t, int T, int64_t Bp, int quiet) {
+    int step;
+    if (Bp >= 4096) step = t < 20 ? 2 : 4;
+    else if (t < 8) step = 2;
+    else if (t < 24) step = 4;
+    else step = 8;
+    if (quiet > 0) step *= 2;   // one doubling only: the first frames to stop must not be noticed much later
+    const int c = t + step;
     return c < T ? c : T;
 }
 
@@ -704,8 +707,9 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         int rc = scan_ensure(d, Bp);
         if (rc) return rc;
     }
+    int quiet = 0;
     while (true) {
-        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp) : d->T;
+        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp, quiet) : d->T;
         int rc = run_span(d, *ws, curBp, t, t1, want_post, stream);
         if (rc) return rc;
         t = t1;
@@ -714,6 +718,7 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         CU(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         const int64_t pending = *d->h_total;
+        quiet = (pending >= curB) ? quiet + 1 : 0;
         if (pending == 0) {
             d->stat_early_exits++;
             if (want_post) {   // decisions of stopped frames are already in place; posteriors are not
