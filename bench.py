@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU per step")
-    ap.add_argument("--code", default="dvbs2", choices=["dvbs2", "qc"])
+    ap.add_argument("--code", default="dvbs2", choices=["dvbs2", "qc", "dv12"])
     ap.add_argument("--decoder", default="n2d2", choices=["n2d2", "rcq", "wrcq1", "basic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -66,11 +66,14 @@ def parse_args():
 
 
 def make_code(L, name):
+    if name == "dv12":   # not a BASELINE shape: exercises the variable-node path for degrees above 8
+        return L.codes.ira_code({12: 1620, 3: 4860}, {5: 4861, 6: 4859}, max_iterations=T_ITERS)
     return L.codes.dvbs2_shaped(max_iterations=T_ITERS) if name == "dvbs2" else L.codes.qc_shaped(max_iterations=T_ITERS)
 
 
 def workload_name(args):
-    shape = "(16200,7200)-shaped E=48599" if args.code == "dvbs2" else "(9472,8192)-shaped QC E=37888"
+    shape = {"dvbs2": "(16200,7200)-shaped E=48599", "qc": "(9472,8192)-shaped QC E=37888",
+             "dv12": "(16200,6480) IRA dv 12/3/2 E=53459"}[args.code]
     dec = {"n2d2": "Neural2DMinSumDecoder type 2", "rcq": "RCQMinSumDecoder bc=3", "wrcq1": "WeightedRCQ type 1 bc=3",
            "basic": "BasicMinSumDecoder f64 factor 0.7"}[args.decoder]
     return f"{dec}, {T_ITERS} iters, {shape}, AWGN {SNR_DB} dB reference sign convention"

@@ -84,6 +84,7 @@ struct ldpc_graph {
     std::vector<int32_t> chk_var;
     int nonempty_checks = 0;
     int cn_wide_begin = 0, cn_wide_end = 0;   // cn_items [begin, end): check degree 9..64
+    int vn_wide_begin = 0, vn_wide_end = 0, vn_wide_max_deg = 0;   // vn_items [begin, end): variable degree 9..64
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
@@ -250,6 +251,14 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             pos = end;
         }
     }
+    g->vn_wide_begin = g->vn_wide_end = (int)g->vn_items.size();
+    for (size_t i = 0; i < g->vn_items.size(); ++i) {
+        const int deg = g->vn_items[i].deg;
+        if (deg > 8 && g->vn_wide_begin == (int)g->vn_items.size()) g->vn_wide_begin = (int)i;
+        if (deg > 64) { g->vn_wide_end = (int)i; break; }
+        if (deg > 8) g->vn_wide_max_deg = deg;
+    }
+    if (g->vn_wide_end < g->vn_wide_begin) g->vn_wide_begin = g->vn_wide_end;   // no degree in 9..64
     // ---- upload ----
     DeviceGuard guard(device);
     if (!guard.ok) {
@@ -585,6 +594,10 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.Bp = Bp;
     vn.final_pass = final_pass ? 1 : 0;
     vn.freeze = want_post ? 1 : 0;
+    vn.items_wide_begin = g->vn_wide_begin;
+    vn.items_wide_end = g->vn_wide_end;
+    vn.wide_max_deg = g->vn_wide_max_deg;
+    vn.wide_stage = d->wide_ring;
 }
 
 // Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node pass: the

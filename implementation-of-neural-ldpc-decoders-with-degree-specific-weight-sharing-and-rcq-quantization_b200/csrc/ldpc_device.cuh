@@ -239,14 +239,176 @@ __device__ double np_sum_dynamic(Get get, int k) {
     return res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same two reduction orders on whole frame packs (all V frames of a lane at once), with a run-time
+// length: used where a node's inputs are staged in shared memory (variable degrees above 8).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+struct PackAcc {
+    Pack<T, V> v;
+    bool has;
+    __device__ __forceinline__ PackAcc() : has(false) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v.v[i] = T(0);
+    }
+    __device__ __forceinline__ void add(const Pack<T, V>& x) {
+        if (has) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) v.v[i] = Arith<T>::add(v.v[i], x.v[i]);
+        } else {
+            v = x;
+            has = true;
+        }
+    }
+    __device__ __forceinline__ void add(const PackAcc& o) {
+        if (o.has) add(o.v);
+    }
+};
+
+template <int V, typename Get>
+__device__ __forceinline__ Pack<float, V> torch_sum_dynamic_pack(Get get, int k) {
+    if (k < 8) {
+        PackAcc<float, V> a[4];
+        const int g = k / 4;
+        for (int i = 0; i < g; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q].add(get(4 * i + q));
+        }
+        for (int r = 4 * g; r < k; ++r) a[0].add(get(r));
+        a[0].add(a[1]);
+        a[0].add(a[2]);
+        a[0].add(a[3]);
+        return a[0].v;
+    }
+    const int nv = k / 8;
+    PackAcc<float, V> r;
+    for (int t = 8 * nv; t < k; ++t) r.add(get(t));
+    const int g = nv / 4;
+    for (int l = 0; l < 8; ++l) {
+        PackAcc<float, V> a[4];
+        for (int i = 0; i < g; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q].add(get(8 * (4 * i + q) + l));
+        }
+        for (int v = 4 * g; v < nv; ++v) a[0].add(get(8 * v + l));
+        a[0].add(a[1]);
+        a[0].add(a[2]);
+        a[0].add(a[3]);
+        r.add(a[0]);
+    }
+    return r.v;
+}
+
+template <int V, typename Get>
+__device__ __forceinline__ Pack<double, V> np_sum_dynamic_pack(Get get, int k) {
+    PackAcc<double, V> res;
+    if (k < 8) {
+        for (int i = 0; i < k; ++i) res.add(get(i));
+        return res.v;
+    }
+    PackAcc<double, V> r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q].add(get(q));
+    const int full = k - (k % 8);
+    for (int i = 8; i < full; i += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q].add(get(i + q));
+    }
+    r[0].add(r[1]);
+    r[2].add(r[3]);
+    r[4].add(r[5]);
+    r[6].add(r[7]);
+    r[0].add(r[2]);
+    r[4].add(r[6]);
+    r[0].add(r[4]);
+    for (int i = full; i < k; ++i) r[0].add(get(i));
+    return r[0].v;
+}
+
+// Compile-time lengths: everything unrolls, the `has` flags fold away and `get(i)` sees constant indices.
+template <int K, int V, typename Get>
+__device__ __forceinline__ Pack<float, V> torch_sum_static_pack(Get get) {
+    if constexpr (K < 8) {
+        PackAcc<float, V> a[4];
+        constexpr int g = K / 4;
+#pragma unroll
+        for (int i = 0; i < g; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q].add(get(4 * i + q));
+        }
+#pragma unroll
+        for (int r = 4 * g; r < K; ++r) a[0].add(get(r));
+        a[0].add(a[1]);
+        a[0].add(a[2]);
+        a[0].add(a[3]);
+        return a[0].v;
+    } else {
+        constexpr int nv = K / 8;
+        constexpr int g = nv / 4;
+        PackAcc<float, V> r;
+#pragma unroll
+        for (int t = 8 * nv; t < K; ++t) r.add(get(t));
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            PackAcc<float, V> a[4];
+#pragma unroll
+            for (int i = 0; i < g; ++i) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q].add(get(8 * (4 * i + q) + l));
+            }
+#pragma unroll
+            for (int v = 4 * g; v < nv; ++v) a[0].add(get(8 * v + l));
+            a[0].add(a[1]);
+            a[0].add(a[2]);
+            a[0].add(a[3]);
+            r.add(a[0]);
+        }
+        return r.v;
+    }
+}
+
+template <int K, int V, typename Get>
+__device__ __forceinline__ Pack<double, V> np_sum_static_pack(Get get) {
+    if constexpr (K < 8) {
+        PackAcc<double, V> res;
+#pragma unroll
+        for (int i = 0; i < K; ++i) res.add(get(i));
+        return res.v;
+    } else {
+        PackAcc<double, V> r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q].add(get(q));
+        constexpr int full = K - (K % 8);
+#pragma unroll
+        for (int i = 8; i < full; i += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q].add(get(i + q));
+        }
+        r[0].add(r[1]);
+        r[2].add(r[3]);
+        r[4].add(r[5]);
+        r[6].add(r[7]);
+        r[0].add(r[2]);
+        r[4].add(r[6]);
+        r[0].add(r[4]);
+#pragma unroll
+        for (int i = full; i < K; ++i) r[0].add(get(i));
+        return r[0].v;
+    }
+}
+
 template <typename T> struct LibSum;
 template <> struct LibSum<float> {
     template <int K, typename Get> static __device__ __forceinline__ float stat(Get g) { return torch_sum_static<K>(g); }
     template <typename Get> static __device__ __forceinline__ float dyn(Get g, int k) { return torch_sum_dynamic(g, k); }
+    template <int V, typename Get> static __device__ __forceinline__ Pack<float, V> dyn_pack(Get g, int k) { return torch_sum_dynamic_pack<V>(g, k); }
+    template <int K, int V, typename Get> static __device__ __forceinline__ Pack<float, V> stat_pack(Get g) { return torch_sum_static_pack<K, V>(g); }
 };
 template <> struct LibSum<double> {
     template <int K, typename Get> static __device__ __forceinline__ double stat(Get g) { return np_sum_static<K>(g); }
     template <typename Get> static __device__ __forceinline__ double dyn(Get g, int k) { return np_sum_dynamic(g, k); }
+    template <int V, typename Get> static __device__ __forceinline__ Pack<double, V> dyn_pack(Get g, int k) { return np_sum_dynamic_pack<V>(g, k); }
+    template <int K, int V, typename Get> static __device__ __forceinline__ Pack<double, V> stat_pack(Get g) { return np_sum_static_pack<K, V>(g); }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -66,6 +66,10 @@ struct VnLaunch {
     int64_t Bp;
     int final_pass;
     int freeze;                 // 1: stopped frames keep their v2c / c2v
+    int items_wide_begin;       // items [begin, end) hold variables of degree 9..64 (sorted by degree)
+    int items_wide_end;
+    int wide_max_deg;           // largest degree among them (rows of the shared-memory stage)
+    int wide_stage;             // 1: those items run in vn_wide_kernel
 };
 
 struct SynLaunch {

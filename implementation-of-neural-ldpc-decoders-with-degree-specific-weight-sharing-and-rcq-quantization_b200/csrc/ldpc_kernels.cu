@@ -1156,7 +1156,8 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
 
 // FREEZE: stopped frames keep their v2c (forward()'s posterior output); otherwise their stores are plain.
 template <typename Real, bool QUANT, bool FINAL, bool FREEZE>
-__global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb) {
+__global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb,
+                                                                                                   const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ float s_lut[];
     if (QUANT) {
@@ -1165,7 +1166,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
         __syncthreads();
     }
     const int fb = blockIdx.x % nfb;
-    const int item_id = blockIdx.x / nfb;
+    const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
     // Stopped frames keep their messages and their packed decisions in place; only forward()'s posterior
@@ -1215,6 +1216,173 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
                 vn_node_generic<Real, QUANT, FINAL>(p, vpos, lbase, it.deg, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
     }
 #undef LDPC_VN_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variables of degree 9..64 (`vn_wide_kernel`).  Every leave-one-out sum has its own summation order (the
+// library orders depend on the positions), so a node of degree dv needs dv * (dv - 1) element reads; taking
+// them from global memory again (the generic path) ran at 0.09 of the HBM roofline.  Here a thread copies
+// the dv message segments of its frames ONCE, with per-thread async copies (cp.async, no register staging:
+// all dv loads are in flight together), into its own column of a shared-memory stage, and the sums read that
+// column (LDS.128 per element for the four frames).  A column belongs to one thread: no barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kVnWideThreads = 128;
+constexpr int kVnWideMaxDeg = 64;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_own(void* smem_dst, const void* gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Sums of one staged variable: DVS > 0 = compile-time degree (unrolled, constant stage offsets), 0 = run-time.
+template <typename Real, bool FINAL, int DVS>
+__device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real, FramesPerLane<Real>::value>* __restrict__ s_val,
+                                             int dv, const Pack<Real, FramesPerLane<Real>::value>& L, Real alpha, bool has_alpha,
+                                             int64_t lbase, Real* __restrict__ v2c, uint32_t real_stride, uint32_t smask,
+                                             uint32_t dmask, Pack<Real, FramesPerLane<Real>::value>& post,
+                                             bool (&bit)[FramesPerLane<Real>::value]) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using PackR = Pack<Real, V>;
+    auto elem = [&](int i) -> PackR { return s_val[(size_t)i * kVnWideThreads]; };
+    PackR tot;
+    if constexpr (DVS > 0) tot = LibSum<Real>::template stat_pack<DVS, V>(elem);
+    else tot = LibSum<Real>::template dyn_pack<V>(elem, dv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        post.v[v] = Arith<Real>::add(L.v[v], tot.v[v]);
+        bit[v] = (post.v[v] < Real(0)) && !((dmask >> v) & 1u);
+    }
+    if constexpr (!FINAL) {
+        auto emit = [&](int d, const PackR& sum) {
+            PackR out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                Real sv = sum.v[v];
+                if (has_alpha) sv = Arith<Real>::mul(alpha, sv);
+                out.v[v] = Arith<Real>::add(L.v[v], sv);
+            }
+            const uint32_t sd = (uint32_t)__ldg(p.vslots + lbase + d);
+            store_masked<Real, V>(row_at(v2c, sd, real_stride), out, smask);
+        };
+        if constexpr (DVS > 0) {
+#pragma unroll
+            for (int d = 0; d < DVS; ++d) {
+                auto others = [&](int i) -> PackR { return s_val[(size_t)(i < d ? i : i + 1) * kVnWideThreads]; };
+                emit(d, LibSum<Real>::template stat_pack<DVS - 1, V>(others));
+            }
+        } else {
+            for (int d = 0; d < dv; ++d) {
+                auto others = [&](int i) -> PackR { return s_val[(size_t)(i < d ? i : i + 1) * kVnWideThreads]; };
+                emit(d, LibSum<Real>::template dyn_pack<V>(others, dv - 1));
+            }
+        }
+    }
+}
+
+template <typename Real, bool QUANT, bool FINAL, bool FREEZE>
+__global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch p, const int nfb, const int item0,
+                                                                  const int stage_rows) {
+    constexpr int V = FramesPerLane<Real>::value;
+    using InT = typename CnOut<Real, QUANT>::type;
+    using PackR = Pack<Real, V>;
+    using PackIn = Pack<InT, V>;
+    extern __shared__ __align__(16) unsigned char vn_stage[];
+    // stage: values [stage_rows][threads] PackR, then (QUANT) raw codes [stage_rows][threads] PackIn, then the LUT
+    PackR* __restrict__ s_val = reinterpret_cast<PackR*>(vn_stage) + threadIdx.x;
+    PackIn* __restrict__ s_code = reinterpret_cast<PackIn*>(vn_stage + (size_t)stage_rows * kVnWideThreads * sizeof(PackR)) + threadIdx.x;
+    float* s_lut = reinterpret_cast<float*>(vn_stage + (size_t)stage_rows * kVnWideThreads * (sizeof(PackR) + (QUANT ? sizeof(PackIn) : 0)));
+    if (QUANT) {
+        const int nl = p.n_quant << p.bc;
+        for (int i = threadIdx.x; i < nl; i += blockDim.x) s_lut[i] = p.lut[i];
+        __syncthreads();
+    }
+    const int fb = blockIdx.x % nfb;
+    const int item_id = item0 + blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * kVnWideThreads + threadIdx.x) * V;
+    if (f0 >= p.Bp) return;   // whole warps
+    uint32_t dmask = 0;
+    if (!FINAL || p.postT == nullptr) {
+        dmask = load_done_mask<V>(p.done, f0);
+        if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    }
+    const uint32_t keepw = keep_word<V>(dmask);
+    const uint32_t smask = FREEZE ? dmask : 0u;
+    int lutbase[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        lutbase[v] = 0;
+        if (QUANT) {
+            int q = p.q_now;
+            if (FINAL) {
+                const int itv = __ldg(p.iters + f0 + v);
+                q = __ldg(p.q_of_iter + (itv > 0 ? itv - 1 : 0));
+            }
+            lutbase[v] = q << p.bc;
+        }
+    }
+    const uint32_t lutmask = (1u << p.bc) - 1u;
+    const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
+    const int64_t wbase = (warp_f0 / (32 * V)) * V;
+    const WorkItem it = p.items[item_id];
+    const int dv = it.deg;
+    const uint32_t in_stride = (uint32_t)p.Bp * (uint32_t)sizeof(InT), real_stride = (uint32_t)p.Bp * (uint32_t)sizeof(Real);
+    const InT* __restrict__ c2v = static_cast<const InT*>(p.c2v) + f0;
+    Real* __restrict__ v2c = static_cast<Real*>(p.v2c) + f0;
+    const Real* __restrict__ llr0 = static_cast<const Real*>(p.llrT) + f0;
+    const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
+    int64_t lbase = it.first_slot;
+    int32_t vpos = it.first_node;
+    for (int c = 0; c < it.count; ++c, lbase += dv, ++vpos) {
+        const uint32_t j = (uint32_t)__ldg(p.vpos_var + vpos);
+        for (int i = 0; i < dv; ++i) {
+            const uint32_t slot = (uint32_t)__ldg(p.vslots + lbase + i);
+            if constexpr (QUANT) cp_async_own<sizeof(PackIn)>(s_code + (size_t)i * kVnWideThreads, row_at(c2v, slot, in_stride));
+            else cp_async_own<sizeof(PackR)>(s_val + (size_t)i * kVnWideThreads, row_at(c2v, slot, in_stride));
+        }
+        const PackR L = ld_stream<PackR>(row_at(llr0, j, real_stride));
+        Real alpha = Real(1);
+        if (has_alpha) alpha = __ldg(static_cast<const Real*>(p.alpha_t) + (p.aidx ? __ldg(p.aidx + vpos) : 0));
+        cp_async_wait_all();
+        if constexpr (QUANT) {   // decode the codes once
+            for (int i = 0; i < dv; ++i) {
+                const PackIn code = s_code[(size_t)i * kVnWideThreads];
+                PackR val;
+#pragma unroll
+                for (int v = 0; v < V; ++v) val.v[v] = (Real)s_lut[lutbase[v] + (code.v[v] & lutmask)];
+                s_val[(size_t)i * kVnWideThreads] = val;
+            }
+        }
+        PackR post;
+        bool bit[V];
+        bool handled = false;
+#define LDPC_VNW_CASE(D)                                                                                              \
+    case D:                                                                                                           \
+        vn_wide_sums<Real, FINAL, D>(p, s_val, D, L, alpha, has_alpha, lbase, v2c, real_stride, smask, dmask, post, bit); \
+        handled = true;                                                                                               \
+        break;
+        switch (dv) {
+            LDPC_VNW_CASE(9)
+            LDPC_VNW_CASE(10)
+            LDPC_VNW_CASE(11)
+            LDPC_VNW_CASE(12)
+            LDPC_VNW_CASE(13)
+            LDPC_VNW_CASE(14)
+            LDPC_VNW_CASE(15)
+            LDPC_VNW_CASE(16)
+            default: break;
+        }
+#undef LDPC_VNW_CASE
+        if (!handled) vn_wide_sums<Real, FINAL, 0>(p, s_val, dv, L, alpha, has_alpha, lbase, v2c, real_stride, smask, dmask, post, bit);
+        if constexpr (FINAL) {
+            if (p.postT) st_stream<PackR>(row_at(static_cast<Real*>(p.postT) + f0, j, real_stride), post);
+        }
+        write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1757,30 +1925,62 @@ cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, i
     return cudaGetLastError();
 }
 
+namespace {
+
+template <typename Real, bool QUANT>
+cudaError_t launch_vn_range(const VnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
+    if (item1 <= item0) return cudaSuccess;
+    constexpr int V = FramesPerLane<Real>::value;
+    if (wide) {
+        using InT = typename CnOut<Real, QUANT>::type;
+        const int rows = p.wide_max_deg;
+        const size_t smem = (size_t)rows * kVnWideThreads * (sizeof(Pack<Real, V>) + (QUANT ? sizeof(Pack<InT, V>) : 0)) +
+                            (QUANT ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0);
+        const int64_t nfb = (p.Bp + (int64_t)kVnWideThreads * V - 1) / ((int64_t)kVnWideThreads * V);
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+#define LDPC_VNW(FINAL, FREEZE)                                                                                        \
+    do {                                                                                                               \
+        cudaError_t e_ = cudaFuncSetAttribute(vn_wide_kernel<Real, QUANT, FINAL, FREEZE>,                              \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+        if (e_ != cudaSuccess) return e_;                                                                              \
+        vn_wide_kernel<Real, QUANT, FINAL, FREEZE><<<(unsigned)grid, kVnWideThreads, smem, stream>>>(p, (int)nfb, item0, rows); \
+    } while (0)
+        if (p.final_pass) LDPC_VNW(true, false);
+        else if (p.freeze) LDPC_VNW(false, true);
+        else LDPC_VNW(false, false);
+#undef LDPC_VNW
+    } else {
+        const int threads = threads_for(p.Bp, V);
+        const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
+        const unsigned g = (unsigned)grid;
+        const int nf = (int)nfb;
+        if (p.final_pass) vn_kernel<Real, QUANT, true, false><<<g, threads, smem, stream>>>(p, nf, item0);
+        else if (p.freeze) vn_kernel<Real, QUANT, false, true><<<g, threads, smem, stream>>>(p, nf, item0);
+        else vn_kernel<Real, QUANT, false, false><<<g, threads, smem, stream>>>(p, nf, item0);
+    }
+    return cudaGetLastError();
+}
+
+template <typename Real, bool QUANT>
+cudaError_t launch_vn_all(const VnLaunch& p, cudaStream_t stream) {
+    // items are sorted by degree: [0, wide0) degree <= 8, [wide0, wide1) degree 9..64 (shared-memory stage), rest > 64
+    const int wide0 = p.wide_stage ? p.items_wide_begin : p.n_items, wide1 = p.wide_stage ? p.items_wide_end : p.n_items;
+    cudaError_t e = launch_vn_range<Real, QUANT>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_vn_range<Real, QUANT>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_vn_range<Real, QUANT>(p, wide1, p.n_items, false, stream);
+    return e;
+}
+
+}  // namespace
+
 cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream) {
     if (p.n_items == 0) return cudaSuccess;
-    const int V = dtype == 0 ? 4 : 2;
-    const int threads = threads_for(p.Bp, V);
-    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
-    const int64_t grid = nfb * p.n_items;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
-    const unsigned g = (unsigned)grid;
-    const int nf = (int)nfb;
-#define LDPC_VN_LAUNCH(REAL, Q)                                                                              \
-    do {                                                                                                     \
-        if (p.final_pass) vn_kernel<REAL, Q, true, false><<<g, threads, smem, stream>>>(p, nf);              \
-        else if (p.freeze) vn_kernel<REAL, Q, false, true><<<g, threads, smem, stream>>>(p, nf);             \
-        else vn_kernel<REAL, Q, false, false><<<g, threads, smem, stream>>>(p, nf);                          \
-    } while (0)
-    if (dtype == 0) {
-        if (p.bc) LDPC_VN_LAUNCH(float, true);
-        else LDPC_VN_LAUNCH(float, false);
-    } else {
-        LDPC_VN_LAUNCH(double, false);
-    }
-#undef LDPC_VN_LAUNCH
-    return cudaGetLastError();
+    if (dtype == 0) return p.bc ? launch_vn_all<float, true>(p, stream) : launch_vn_all<float, false>(p, stream);
+    return launch_vn_all<double, false>(p, stream);
 }
 
 cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream) {

@@ -113,3 +113,65 @@ def test_wide_ring_matches_register_streaming_kernel(built_lib, monkeypatch):
     b1, p1, i1 = run()
     assert torch.equal(b0, b1) and torch.equal(p0, p1) and torch.equal(i0, i1)
     assert len(set(i1.tolist())) > 1   # frames stop at different iterations (frozen messages, masked stores)
+
+
+@pytest.mark.parametrize("B", [3, 200, 700])
+def test_wide_variables_stage_kernel_vs_oracle(built_lib, B):
+    """Variables of degree 9..64 run in vn_wide_kernel (inputs staged once in shared memory, library summation
+    orders evaluated from the stage): every boundary degree (8 | 9, 64 | 65), all decoder families, posterior
+    output (frozen messages), early stop, float64."""
+    from oracle import capi as O
+    from oracle.restatement import MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule
+    L = built_lib
+    rng = np.random.default_rng(7 + B)
+    T = 8
+    m, degs = 90, [8, 9, 9, 10, 12, 13, 15, 16, 17, 24, 31, 32, 33, 40, 63, 64, 65, 70] + [2, 3, 4] * 14
+    n = len(degs)
+    H = np.zeros((m, n), dtype=np.int64)
+    for j, d in enumerate(degs):
+        H[rng.choice(m, d, replace=False), j] = 1
+    code = L.LDPCCode(n, max(1, n - m), H, max_iterations=T)
+    og = SparseGraph.from_dense(H)
+    llr = 1.5 + 2.5 * rng.standard_normal((B, n))
+    llr[: B // 2] = 5.0 + 1.0 * rng.standard_normal((B // 2, n))
+    llr32 = llr.astype(np.float32)
+
+    torch.manual_seed(B)
+    for wtype in (1, 3):                                  # type 1: beta(dc, dv); type 3: alpha(dv)
+        d2 = L.Neural2DMinSumDecoder(code, wtype, T)
+        with torch.no_grad():
+            if d2._beta_table is not None:
+                d2._beta_table.uniform_(0.2, 0.6)         # many inputs per variable: keep the messages small
+            if d2._alpha_table is not None:
+                d2._alpha_table.uniform_(0.2, 0.5)
+        b, p, i = d2(torch.from_numpy(llr32).cuda())       # forward(): posterior wanted -> FREEZE variants
+        beta = (d2._beta_table.detach().numpy()[:, d2._beta_index] if d2._beta_table is not None
+                else np.full((T, og.E), np.float32(0.7)))
+        alpha = d2._alpha_table.detach().numpy()[:, d2._alpha_index] if d2._alpha_table is not None else None
+        ref = O.decode(og, llr32, T=T, beta=beta, alpha=alpha, nthreads=8)
+        assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+        assert np.array_equal(p.cpu().numpy(), ref.posterior)
+        _, _, it2, su2 = d2._engine(0).decode_device(torch.from_numpy(llr32).cuda())   # no posterior: mask-free variants
+        assert np.array_equal(it2.cpu().numpy(), ref.iterations) and np.array_equal(su2.cpu().numpy().astype(bool), ref.success)
+
+    bb, ss, ii = L.BasicMinSumDecoder(code, 0.3).decode(llr)
+    ref = O.decode(og, llr, T=T, dtype=np.float64, beta=np.full((T, og.E), 0.3), nthreads=8)
+    assert np.array_equal(bb, ref.bits) and np.array_equal(ii, ref.iterations) and np.array_equal(ss, ref.success)
+
+    for bc, qp in ((3, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]), (5, [(6.0, 1.1), (9.0, 1.0)])):
+        rcq = L.RCQMinSumDecoder(code, bc, 8, qp, max_iterations=T)
+        thr = np.array([q.thresholds for q in rcq.quantizers]).astype(np.float32)
+        qoi = quantizer_schedule(T, len(qp))
+        b, s, i = rcq.decode(torch.from_numpy(llr32).cuda())
+        ref = O.decode(og, llr32, T=T, mode=MODE_RCQ, bc=bc, thresholds=thr, quantizer_of_iter=qoi, nthreads=8)
+        assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+        w = L.WeightedRCQDecoder(code, bc, 8, qp, weight_sharing_type=2, max_iterations=T)
+        with torch.no_grad():
+            w._beta_table.uniform_(0.2, 0.5)
+        b, p, i = w(torch.from_numpy(llr32).cuda())
+        ref = O.decode(og, llr32, T=T, mode=MODE_WRCQ, bc=bc, thresholds=thr, quantizer_of_iter=qoi,
+                       beta=w._beta_table.detach().numpy()[:, w._beta_index],
+                       alpha=(w._alpha_table.detach().numpy()[:, w._alpha_index] if w._alpha_table is not None
+                              else np.ones((T, n), np.float32)), nthreads=8)
+        assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+        assert np.array_equal(p.cpu().numpy(), ref.posterior)
