@@ -7,16 +7,18 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "ldpc_kernels.cu"), os.path.join(HERE, "ldpc_api.cu")]
-HEADERS = [os.path.join(HERE, "ldpc_device.cuh"), os.path.join(HERE, "ldpc_internal.h"),
-           os.path.join(os.path.dirname(PKG), "include", "ldpc_b200.h")]
+SOURCES = [os.path.join(HERE, f) for f in ("ldpc_cn.cu", "ldpc_vn.cu", "ldpc_misc.cu", "ldpc_api.cu")]
+HEADERS = [os.path.join(HERE, "ldpc_device.cuh"), os.path.join(HERE, "ldpc_kernel_common.cuh"),
+           os.path.join(HERE, "ldpc_internal.h"), os.path.join(os.path.dirname(PKG), "include", "ldpc_b200.h")]
+OBJDIR = os.path.join(HERE, "build")
 OUT = os.path.join(PKG, "libldpc_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",               # parity: llr + alpha*s and beta*raw round the product first
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def nvcc_path() -> str:
@@ -33,12 +35,30 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(p) <= t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
+def _compile_all(out: str, defines, verbose: bool, tag: str) -> str:
+    """One nvcc process per translation unit (they run in parallel), then one link step."""
+    objdir = os.path.join(OBJDIR, tag)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = nvcc_path()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", "-o", obj, src])
+        procs.append((cmd, obj, subprocess.Popen(cmd)))
+    objs = []
+    for cmd, obj, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+        objs.append(obj)
+    subprocess.run([nvcc] + LINK_FLAGS + ["-o", out] + objs, check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
-    subprocess.run(cmd, check=True)
-    return OUT
+    return _compile_all(OUT, [], verbose, "main")
 
 
 def build_variant(name: str, defines: list) -> str:
@@ -46,10 +66,7 @@ def build_variant(name: str, defines: list) -> str:
     at run time with LDPC_B200_LIB=<path>.  Not used by the product path."""
     outdir = os.path.join(os.path.dirname(PKG), "tuning")
     os.makedirs(outdir, exist_ok=True)
-    out = os.path.join(outdir, f"libldpc_b200_{name}.so")
-    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SOURCES
-    subprocess.run(cmd, check=True)
-    return out
+    return _compile_all(os.path.join(outdir, f"libldpc_b200_{name}.so"), list(defines), False, "variant_" + name)
 
 
 if __name__ == "__main__":
