@@ -218,6 +218,25 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host
+    buffer is allocated, so that the end-to-end leg's staging memory is local to the GPU's PCIe root.  With
+    several ranks per box the host-to-device copies otherwise share one socket's memory controllers."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -317,6 +336,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -456,7 +476,8 @@ def run_ours(args):
             "config": {"workload": workload_name(args), "frames_per_gpu": B, "global_frames": world * B,
                        "n": g.n, "k": code.k, "E": g.E, "iterations": T_ITERS, "early_stop": True,
                        "l2": "inputs larger than L2 (message arrays %.1f GB per GPU)" % (2 * 4 * g.E * Bp / 1e9),
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "host_affinity": (f"{len(numa)} CPUs next to the GPU (NVML)" if numa else "unbound")},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "early_stop_mc": early,
             "gpu_launches": int(prof["launches"]),
             "clocks": clocks,
