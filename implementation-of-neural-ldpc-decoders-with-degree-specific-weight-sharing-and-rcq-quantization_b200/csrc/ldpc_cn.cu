@@ -546,7 +546,14 @@ struct RowRing {
     }
 };
 
-template <typename Real, bool QUANT, int NTH, typename MaskT>
+// offset min-sum rule (defined with cn_offset_kernel below)
+template <typename Real>
+__device__ __forceinline__ Real offset_value(Real raw, Real beta, bool has_beta, Real alpha, bool has_alpha,
+                                             uint32_t signbits, bool zero_others);
+template <typename Real>
+__device__ __forceinline__ void offset_weights(const CnLaunch& p, int64_t slot, Real beta_check, Real& beta, Real& alpha);
+
+template <typename Real, bool QUANT, int NTH, typename MaskT, bool OFFSET>
 __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& ring, int64_t slot0, int dc, int64_t f0,
                                               uint32_t dmask, bool active, const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
@@ -586,6 +593,30 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
         ring.release();
     }
     if (!active) return;
+    if constexpr (OFFSET) {
+        // c2v = prod(other signs) * (relu(raw - beta) - alpha[variable]); a zero among the OTHER inputs gives 0
+#pragma unroll
+        for (int v = 0; v < V; ++v) neg[v] = SignMask<MaskT>::align(neg[v], dc);
+        Real beta_check = Real(0);
+        if (p.beta_t && !p.beta_per_edge) beta_check = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+        Real* __restrict__ orow = static_cast<Real*>(p.dst) + slot0 * p.Bp + f0;
+        for (int k = 0; k < dc; ++k, orow += p.Bp) {
+            Real beta, alpha;
+            offset_weights<Real>(p, slot0 + k, beta_check, beta, alpha);
+            Pack<Real, V> out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t sb = SignMask<MaskT>::top(neg[v]);
+                neg[v] <<= 1;
+                const bool is_min = (k == st[v].k0);
+                const bool zero_others = st[v].m2 == Real(0) || (st[v].m1 == Real(0) && !is_min);
+                out.v[v] = offset_value<Real>(is_min ? st[v].m2 : st[v].m1, beta, p.beta_t != nullptr, alpha,
+                                              p.alpha_t != nullptr, st[v].par ^ sb, zero_others);
+            }
+            store_masked<Real, V>(orow, out, dmask);
+        }
+        return;
+    }
     CheckOut<Real, QUANT> co[V];
     if (!p.beta_per_edge) {
         Real beta = Real(1);
@@ -645,7 +676,7 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
     }
 }
 
-template <typename Real, bool QUANT, int NTH, bool FREEZE>
+template <typename Real, bool QUANT, int NTH, bool FREEZE, bool OFFSET = false>
 __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ __align__(128) unsigned char wide_smem[];
@@ -690,10 +721,10 @@ __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(con
     int64_t slot = it.first_slot;
     if (it.deg <= 32) {
         for (int c = 0; c < it.count; ++c, slot += it.deg)
-            cn_wide_check<Real, QUANT, NTH, uint32_t>(p, ring, slot, it.deg, f0, dmask, active, qz);
+            cn_wide_check<Real, QUANT, NTH, uint32_t, OFFSET>(p, ring, slot, it.deg, f0, dmask, active, qz);
     } else {
         for (int c = 0; c < it.count; ++c, slot += it.deg)
-            cn_wide_check<Real, QUANT, NTH, uint64_t>(p, ring, slot, it.deg, f0, dmask, active, qz);
+            cn_wide_check<Real, QUANT, NTH, uint64_t, OFFSET>(p, ring, slot, it.deg, f0, dmask, active, qz);
     }
 }
 
@@ -791,10 +822,10 @@ __device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t
 }
 
 template <typename Real, bool FREEZE>
-__global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb) {
+__global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     const int fb = blockIdx.x % nfb;
-    const int item_id = blockIdx.x / nfb;
+    const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
     const uint32_t done_mask = load_done_mask<V>(p.done, f0);
@@ -924,21 +955,45 @@ cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
     return launch_cn_all<double, false, 0>(p, stream);
 }
 
-cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
-    if (p.n_items == 0) return cudaSuccess;
-    const int V = dtype == 0 ? 4 : 2;
-    const int threads = threads_for(p.Bp, V);
-    const int64_t nfb = (p.Bp / V + threads - 1) / threads;
-    const int64_t grid = nfb * p.n_items;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (dtype == 0) {
-        if (p.freeze) cn_offset_kernel<float, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
-        else cn_offset_kernel<float, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+namespace {
+
+template <typename Real, bool FREEZE>
+cudaError_t launch_cn_offset_range(const CnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
+    if (item1 <= item0) return cudaSuccess;
+    constexpr int V = FramesPerLane<Real>::value;
+    if (wide) {
+        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, false, 0, FREEZE, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+        if (e != cudaSuccess) return e;
+        const int64_t nfb = (p.Bp + (int64_t)kWideThreads * V - 1) / ((int64_t)kWideThreads * V);
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        cn_wide_kernel<Real, false, 0, FREEZE, true><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
     } else {
-        if (p.freeze) cn_offset_kernel<double, true><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
-        else cn_offset_kernel<double, false><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb);
+        const int threads = threads_for(p.Bp, V);
+        const int64_t nfb = (p.Bp / V + threads - 1) / threads;
+        const int64_t grid = nfb * (item1 - item0);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        cn_offset_kernel<Real, FREEZE><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
     }
     return cudaGetLastError();
+}
+
+template <typename Real, bool FREEZE>
+cudaError_t launch_cn_offset_all(const CnLaunch& p, cudaStream_t stream) {
+    const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
+    cudaError_t e = launch_cn_offset_range<Real, FREEZE>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_cn_offset_range<Real, FREEZE>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_cn_offset_range<Real, FREEZE>(p, wide1, p.n_items, false, stream);
+    return e;
+}
+
+}  // namespace
+
+cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
+    if (p.n_items == 0) return cudaSuccess;
+    if (dtype == 0) return p.freeze ? launch_cn_offset_all<float, true>(p, stream) : launch_cn_offset_all<float, false>(p, stream);
+    return p.freeze ? launch_cn_offset_all<double, true>(p, stream) : launch_cn_offset_all<double, false>(p, stream);
 }
 
 cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,

@@ -168,6 +168,53 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
 
+// four standard normal samples of (variable group jg, global frame gf): Box-Muller on one Philox block
+__device__ __forceinline__ void awgn_normals(uint32_t jg, uint64_t gf, uint64_t seed, float (&z)[4]) {
+    uint32_t r[4];
+    philox4x32_10(jg, (uint32_t)gf, (uint32_t)(gf >> 32), 0x4c445043u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    float rad = sqrtf(-2.f * logf(u01(r[0])));
+    float s, c;
+    sincospif(2.f * u01(r[1]), &s, &c);
+    z[0] = rad * c;
+    z[1] = rad * s;
+    rad = sqrtf(-2.f * logf(u01(r[2])));
+    sincospif(2.f * u01(r[3]), &s, &c);
+    z[2] = rad * c;
+    z[3] = rad * s;
+}
+
+// Row-major output [B][n] (ldpc_awgn_llr): consecutive lanes own consecutive variable groups, so a warp writes
+// 512 contiguous bytes of one frame's row; frames stride over gridDim.y.
+__global__ void __launch_bounds__(128) awgn_rows_kernel(float* __restrict__ out, int32_t n, int64_t B, uint64_t frame0,
+                                                        uint64_t seed, float sigma, float inv_sigma2_x2, float llr_sign,
+                                                        const uint8_t* __restrict__ codeword) {
+    const int32_t jg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t j0 = 4 * jg;
+    if (j0 >= n) return;
+    float sym[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float cw = (codeword && j0 + i < n) ? (float)codeword[j0 + i] : 0.f;
+        sym[i] = llr_sign * (1.f - 2.f * cw);
+    }
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    for (int64_t f = blockIdx.y; f < B; f += gridDim.y) {
+        float z[4];
+        awgn_normals((uint32_t)jg, frame0 + (uint64_t)f, seed, z);
+        float val[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) val[i] = __fmul_rn(__fadd_rn(sym[i], __fmul_rn(sigma, z[i])), inv_sigma2_x2);
+        float* row = out + f * n + j0;
+        if (vec) {
+            *reinterpret_cast<float4*>(row) = make_float4(val[0], val[1], val[2], val[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (j0 + i < n) row[i] = val[i];
+        }
+    }
+}
+
 template <typename Real, bool ROW_MAJOR>
 __global__ void awgn_kernel(void* __restrict__ out_, int32_t n, int64_t B, int64_t Bp, uint64_t frame0, uint64_t seed,
                             float sigma, float inv_sigma2_x2, float llr_sign, const uint8_t* __restrict__ codeword) {
@@ -178,22 +225,8 @@ __global__ void awgn_kernel(void* __restrict__ out_, int32_t n, int64_t B, int64
     float val[4][4];  // [variable in group][frame]
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        uint64_t gf = frame0 + (uint64_t)(f0 + v);
-        uint32_t r[4];
-        philox4x32_10((uint32_t)jg, (uint32_t)gf, (uint32_t)(gf >> 32), 0x4c445043u, (uint32_t)seed,
-                      (uint32_t)(seed >> 32), r);
         float z[4];
-        {
-            float rad = sqrtf(-2.f * logf(u01(r[0])));
-            float s, c;
-            sincospif(2.f * u01(r[1]), &s, &c);
-            z[0] = rad * c;
-            z[1] = rad * s;
-            rad = sqrtf(-2.f * logf(u01(r[2])));
-            sincospif(2.f * u01(r[3]), &s, &c);
-            z[2] = rad * c;
-            z[3] = rad * s;
-        }
+        awgn_normals((uint32_t)jg, frame0 + (uint64_t)(f0 + v), seed, z);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int32_t j = 4 * jg + i;
@@ -505,8 +538,11 @@ cudaError_t launch_awgn(int dtype, int row_major, void* out, int32_t n, int64_t 
     const int64_t F = row_major ? B : Bp;
     const int threads = 128;
     dim3 grid((unsigned)((F / 4 + (F % 4 != 0) + threads - 1) / threads), (unsigned)((n + 3) / 4));
-    if (row_major) awgn_kernel<float, true><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
-    else if (dtype == 0) awgn_kernel<float, false><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
+    if (row_major) {
+        const int ng = (n + 3) / 4;
+        dim3 rgrid((unsigned)((ng + 127) / 128), (unsigned)(B < 32768 ? B : 32768));
+        awgn_rows_kernel<<<rgrid, 128, 0, stream>>>(static_cast<float*>(out), n, B, frame0, seed, sigma, k, sgn, codeword);
+    } else if (dtype == 0) awgn_kernel<float, false><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
     else awgn_kernel<double, false><<<grid, threads, 0, stream>>>(out, n, B, Bp, frame0, seed, sigma, k, sgn, codeword);
     return cudaGetLastError();
 }

@@ -35,10 +35,10 @@ def _random_graph(rng):
     return H
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(36))
 def test_random_configurations_vs_oracle(built_lib, monkeypatch, seed):
     from oracle import capi as O
-    from oracle.restatement import MODE_NMS, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule
+    from oracle.restatement import MODE_NMS, MODE_OFFSET, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule
     L = built_lib
     rng = np.random.default_rng(9000 + seed)
     monkeypatch.setenv("LDPC_COMPACT_MIN_FRAMES", "128")
@@ -52,7 +52,7 @@ def test_random_configurations_vs_oracle(built_lib, monkeypatch, seed):
     llr = scale * (1.0 + 1.2 * rng.standard_normal((B, n)))
     llr[rng.random((B, n)) < 0.02] = 0.0              # exact zeros (three-valued sign in the reference)
     llr32 = llr.astype(np.float32)
-    kind = ["n2d", "nnms", "basic", "rcq", "wrcq"][seed % 5]
+    kind = ["n2d", "nnms", "basic", "rcq", "wrcq", "oms"][seed % 6]
     torch.manual_seed(seed)
     x = torch.from_numpy(llr32).cuda()
     if kind == "n2d":
@@ -76,6 +76,22 @@ def test_random_configurations_vs_oracle(built_lib, monkeypatch, seed):
         with torch.no_grad():
             dec._beta_table.uniform_(0.2, 0.9)
         ref = O.decode(og, llr32, T=T, mode=MODE_NMS, beta=dec._beta_table.detach().numpy(), nthreads=8)
+        b, p, i = dec(x)
+        assert np.array_equal(p.cpu().numpy(), ref.posterior)
+    elif kind == "oms":                                   # offset rule: three-valued sign, alpha at the check node
+        if rng.random() < 0.5:
+            dec = L.Neural2DOffsetMinSumDecoder(code, int(rng.integers(1, 5)), T)
+        else:
+            dec = L.NeuralOffsetMinSumDecoder(code, T)
+        with torch.no_grad():
+            if dec._beta_table is not None:
+                dec._beta_table.uniform_(-0.1, 0.6)
+            if dec._alpha_table is not None:
+                dec._alpha_table.uniform_(-0.05, 0.2)
+        bt, at = dec._tables()
+        beta = bt[:, dec._beta_index] if bt is not None else None
+        alpha = at[:, dec._alpha_index] if at is not None else None
+        ref = O.decode(og, llr32, T=T, mode=MODE_OFFSET, beta=beta, alpha=alpha, nthreads=8)
         b, p, i = dec(x)
         assert np.array_equal(p.cpu().numpy(), ref.posterior)
     elif kind == "basic":
