@@ -79,20 +79,23 @@ struct ldpc_graph {
     std::vector<int32_t> vslots;         // slot lists by degree-sorted variable position
     std::vector<int32_t> vpos_var;       // [n] position -> variable
     std::vector<int32_t> var_vpos;       // [n] variable -> position
-    std::vector<WorkItem> cn_items, vn_items;
+    // work items: [0] coarse (8 nodes per item, large batches), [1] fine (1 node per item: small batches are
+    // latency-bound, so the serial chain inside an item is what a half iteration takes)
+    struct ItemList {
+        std::vector<WorkItem> items;
+        WorkItem* d = nullptr;
+        int wide_begin = 0, wide_end = 0, wide_max_deg = 0;   // items [begin, end): degree 9..64
+    };
+    ItemList cn[2], vn[2];
     std::vector<int64_t> chk_ptr;        // original CSR (layered schedule walks checks in index order)
     std::vector<int32_t> chk_var;
     int nonempty_checks = 0;
-    int cn_wide_begin = 0, cn_wide_end = 0;   // cn_items [begin, end): check degree 9..64
-    int vn_wide_begin = 0, vn_wide_end = 0, vn_wide_max_deg = 0;   // vn_items [begin, end): variable degree 9..64
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
     int32_t* d_slot_var = nullptr;
     int32_t* d_vslots = nullptr;
     int32_t* d_vpos_var = nullptr;
-    WorkItem* d_cn_items = nullptr;
-    WorkItem* d_vn_items = nullptr;
 };
 
 extern "C" int ldpc_version(void) { return LDPC_B200_VERSION; }
@@ -187,7 +190,7 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
                 it.count = (int32_t)std::min<size_t>(kCnChunk, end - c);
                 it.first_node = (int32_t)c;
                 it.first_slot = slot + (int32_t)((c - pos) * (size_t)deg);
-                g->cn_items.push_back(it);
+                g->cn[0].items.push_back(it);
             }
             for (size_t c = pos; c < end; ++c) {
                 int32_t i = corder[c];
@@ -201,12 +204,6 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             pos = end;
         }
     }
-    g->cn_wide_begin = g->cn_wide_end = (int)g->cn_items.size();
-    for (size_t i = 0; i < g->cn_items.size(); ++i) {
-        if (g->cn_items[i].deg > 8 && g->cn_wide_begin == (int)g->cn_items.size()) g->cn_wide_begin = (int)i;
-        if (g->cn_items[i].deg > 64) { g->cn_wide_end = (int)i; break; }
-    }
-    if (g->cn_wide_end < g->cn_wide_begin) g->cn_wide_begin = g->cn_wide_end;   // no degree in 9..64
     // ---- variable side: stable sort by degree; slot lists in ascending check index ----
     std::vector<int32_t> vorder(n);
     for (int32_t j = 0; j < n; ++j) vorder[j] = j;
@@ -246,19 +243,34 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
                 it.count = std::min<int32_t>(kVnChunk, end - c);
                 it.first_node = c;
                 it.first_slot = (int32_t)lbase[vorder[c]];
-                g->vn_items.push_back(it);
+                g->vn[0].items.push_back(it);
             }
             pos = end;
         }
     }
-    g->vn_wide_begin = g->vn_wide_end = (int)g->vn_items.size();
-    for (size_t i = 0; i < g->vn_items.size(); ++i) {
-        const int deg = g->vn_items[i].deg;
-        if (deg > 8 && g->vn_wide_begin == (int)g->vn_items.size()) g->vn_wide_begin = (int)i;
-        if (deg > 64) { g->vn_wide_end = (int)i; break; }
-        if (deg > 8) g->vn_wide_max_deg = deg;
+    // fine lists (one node per item) and the degree ranges of both
+    for (ldpc_graph::ItemList* pair : {g->cn, g->vn}) {
+        for (const WorkItem& it : pair[0].items)
+            for (int c = 0; c < it.count; ++c) {
+                WorkItem f = it;
+                f.count = 1;
+                f.first_node = it.first_node + c;
+                f.first_slot = it.first_slot + c * it.deg;
+                pair[1].items.push_back(f);
+            }
+        for (int k = 0; k < 2; ++k) {
+            ldpc_graph::ItemList& L = pair[k];
+            const int nitems = (int)L.items.size();
+            L.wide_begin = L.wide_end = nitems;
+            for (int i = 0; i < nitems; ++i) {
+                const int deg = L.items[(size_t)i].deg;
+                if (deg > 8 && L.wide_begin == nitems) L.wide_begin = i;
+                if (deg > 64) { L.wide_end = i; break; }
+                if (deg > 8) L.wide_max_deg = deg;
+            }
+            if (L.wide_end < L.wide_begin) L.wide_begin = L.wide_end;   // no degree in 9..64
+        }
     }
-    if (g->vn_wide_end < g->vn_wide_begin) g->vn_wide_begin = g->vn_wide_end;   // no degree in 9..64
     // ---- upload ----
     DeviceGuard guard(device);
     if (!guard.ok) {
@@ -268,8 +280,10 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     int rc = upload(&g->d_slot_var, g->slot_var);
     if (!rc) rc = upload(&g->d_vslots, g->vslots);
     if (!rc) rc = upload(&g->d_vpos_var, g->vpos_var);
-    if (!rc) rc = upload(&g->d_cn_items, g->cn_items);
-    if (!rc) rc = upload(&g->d_vn_items, g->vn_items);
+    for (int k = 0; k < 2 && !rc; ++k) {
+        rc = upload(&g->cn[k].d, g->cn[k].items);
+        if (!rc) rc = upload(&g->vn[k].d, g->vn[k].items);
+    }
     if (!rc) rc = upload(&g->d_chk_ptr, g->chk_ptr);
     if (!rc) rc = upload(&g->d_chk_var, g->chk_var);
     if (rc) {
@@ -286,8 +300,10 @@ extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
     cudaFree(g->d_slot_var);
     cudaFree(g->d_vslots);
     cudaFree(g->d_vpos_var);
-    cudaFree(g->d_cn_items);
-    cudaFree(g->d_vn_items);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(g->cn[k].d);
+        cudaFree(g->vn[k].d);
+    }
     cudaFree(g->d_chk_ptr);
     cudaFree(g->d_chk_var);
     delete g;
@@ -415,6 +431,7 @@ struct ldpc_decoder {
     int64_t scan_cap = 0;
     int32_t* d_total = nullptr;   // device int32
     int32_t* h_total = nullptr;   // pinned host int32
+    int64_t fine_items_max_frames = 128;    // batches up to this size (single-frame calls) use one-node work items
     int compact = 1;              // LDPC_COMPACT=0 switches compaction and the all-done exit off
     int64_t compact_min_frames = 512;
     int64_t stat_compactions = 0, stat_early_exits = 0;
@@ -430,6 +447,9 @@ struct ldpc_decoder {
 namespace {
 
 int64_t pad_frames(int64_t B) { return (B + kFrameAlign - 1) / kFrameAlign * kFrameAlign; }
+
+// which work-item list a launch on Bp frames uses: fine (1) for small batches, coarse (0) otherwise
+int item_set(const ldpc_decoder* d, int64_t Bp) { return Bp <= d->fine_items_max_frames ? 1 : 0; }
 
 int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     if (ws.cap >= Bp) return LDPC_OK;
@@ -518,8 +538,8 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
             sy.hardw = ws.hardw;
             sy.Wn = Wn;
             sy.slot_var = g->d_slot_var;
-            sy.items = g->d_cn_items;
-            sy.n_items = (int)g->cn_items.size();
+            sy.items = g->cn[item_set(d, Bp)].d;
+            sy.n_items = (int)g->cn[item_set(d, Bp)].items.size();
             sy.unsat = cur;
             LAUNCH(K_OTHER, launch_syndrome(sy, stream));
             LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
@@ -556,10 +576,11 @@ void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool want_post, 
     cn.bc = d->bc;
     cn.mono = d->bc ? d->mono[q] : 1;
     cn.done = ws.done;
-    cn.items = g->d_cn_items;
-    cn.n_items = (int)g->cn_items.size();
-    cn.items_wide_begin = g->cn_wide_begin;
-    cn.items_wide_end = g->cn_wide_end;
+    const ldpc_graph::ItemList& il = g->cn[item_set(d, Bp)];
+    cn.items = il.d;
+    cn.n_items = (int)il.items.size();
+    cn.items_wide_begin = il.wide_begin;
+    cn.items_wide_end = il.wide_end;
     cn.wide_ring = d->wide_ring;
     cn.freeze = want_post ? 1 : 0;
     cn.Bp = Bp;
@@ -589,14 +610,15 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.hardw = ws.hardw;
     vn.Wn = Bp / 32;
     vn.done = ws.done;
-    vn.items = g->d_vn_items;
-    vn.n_items = (int)g->vn_items.size();
+    const ldpc_graph::ItemList& il = g->vn[item_set(d, Bp)];
+    vn.items = il.d;
+    vn.n_items = (int)il.items.size();
     vn.Bp = Bp;
     vn.final_pass = final_pass ? 1 : 0;
     vn.freeze = want_post ? 1 : 0;
-    vn.items_wide_begin = g->vn_wide_begin;
-    vn.items_wide_end = g->vn_wide_end;
-    vn.wide_max_deg = g->vn_wide_max_deg;
+    vn.items_wide_begin = il.wide_begin;
+    vn.items_wide_end = il.wide_end;
+    vn.wide_max_deg = il.wide_max_deg;
     vn.wide_stage = d->wide_ring;
 }
 
@@ -623,8 +645,8 @@ int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool wa
             sy.hardw = ws.hardw;
             sy.Wn = Wn;
             sy.slot_var = g->d_slot_var;
-            sy.items = g->d_cn_items;
-            sy.n_items = (int)g->cn_items.size();
+            sy.items = g->cn[item_set(d, Bp)].d;
+            sy.n_items = (int)g->cn[item_set(d, Bp)].items.size();
             sy.unsat = cur;
             LAUNCH(K_OTHER, launch_syndrome(sy, stream));
             LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
@@ -863,6 +885,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
+    if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
     DeviceGuard guard(g->device);
@@ -874,7 +897,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (cfg->n_beta > 0 && cfg->beta_index) {
         std::vector<int32_t> bidx((size_t)E);
         for (int64_t e = 0; e < E; ++e) bidx[(size_t)g->slot_of_edge[(size_t)e]] = cfg->beta_index[e];
-        for (const WorkItem& it : g->cn_items)   // does any check mix columns?
+        for (const WorkItem& it : g->cn[0].items)   // does any check mix columns?
             for (int c = 0; c < it.count && !d->beta_per_edge; ++c)
                 for (int k = 1; k < it.deg; ++k)
                     if (bidx[(size_t)it.first_slot + (size_t)c * it.deg + k] != bidx[(size_t)it.first_slot + (size_t)c * it.deg]) {

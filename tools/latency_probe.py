@@ -19,7 +19,7 @@ for cname, code in (("(7,4)", L.create_test_ldpc_code()), ("dvbs2-shaped", L.cod
     dec = L.Neural2DMinSumDecoder(code, 2, 10)
     with torch.no_grad():
         dec._beta_table.fill_(0.8); dec._alpha_table.fill_(1.0)
-    for B in (1, 128, 1024):
+    for B in (1, 128, 1024, 2048, 4096):
         for snr, tag in ((1.0, "no stop"), (6.0, "early stop")):
             llr = L.awgn_llr(code.n, B, snr, seed=1, llr_sign=1 if tag == "early stop" else -1)
             probe(f"{cname} N-2D T=10 {tag}", dec, llr if B > 1 else llr[0])
