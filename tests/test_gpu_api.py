@@ -246,3 +246,36 @@ def test_full_size_named_configs_properties_and_oracle_sample(built_lib, kind, c
     assert np.array_equal(succ_h[pick], ref.success.astype(bool))
     if post is not None:
         assert np.array_equal(post[pick].cpu().numpy(), ref.posterior)
+
+
+@pytest.mark.parametrize("H", [np.zeros((3, 5), dtype=np.int64), np.array([[1]]), np.array([[1, 0, 0], [0, 0, 0]]),
+                               np.zeros((0, 4), dtype=np.int64), np.ones((2, 1), dtype=np.int64)],
+                         ids=["no-edges", "1x1", "one-edge", "no-checks", "one-variable"])
+def test_degenerate_graphs(built_lib, H):
+    """Empty / trivial Tanner graphs: no edges at all (every frame 'succeeds' after one iteration with
+    bits = llr < 0), a single edge, zero checks, a single variable -- against the oracle."""
+    from oracle import capi as O
+    from oracle.restatement import MODE_RCQ, SparseGraph, quantizer_schedule
+    L = built_lib
+    m, n = H.shape
+    T = 3
+    code = L.LDPCCode(n, max(n - m, 0), H, max_iterations=T)
+    og = SparseGraph.from_dense(H)
+    rng = np.random.default_rng(m * 10 + n)
+    llr = (rng.standard_normal((5, n)) * 2).astype(np.float32)
+    llr[0, 0] = 0.0
+    dec = L.Neural2DMinSumDecoder(code, 4, T)
+    b, p, i = dec(torch.from_numpy(llr).cuda())
+    ref = O.decode(og, llr, T=T, beta=np.full((T, og.E), np.float32(0.7)))
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+    assert np.array_equal(p.cpu().numpy(), ref.posterior)
+    bb, ss, ii = L.BasicMinSumDecoder(code, 0.7).decode(llr.astype(np.float64))
+    ref = O.decode(og, llr.astype(np.float64), T=T, dtype=np.float64, beta=np.full((T, og.E), 0.7))
+    assert np.array_equal(bb, ref.bits) and np.array_equal(ii, ref.iterations) and np.array_equal(ss, ref.success)
+    qp = [(3.0, 1.3)]
+    rcq = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T)
+    b, s, i = rcq.decode(torch.from_numpy(llr).cuda())
+    thr = np.array([q.thresholds for q in rcq.quantizers]).astype(np.float32)
+    ref = O.decode(og, llr, T=T, mode=MODE_RCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 1))
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+    assert np.array_equal(s.cpu().numpy().astype(bool), ref.success)
