@@ -431,6 +431,22 @@ struct ldpc_decoder {
     int64_t scan_cap = 0;
     int32_t* d_total = nullptr;   // device int32
     int32_t* h_total = nullptr;   // pinned host int32
+    // launch-bound decodes (tiny codes / tiny batches): the whole T-iteration launch sequence is captured once
+    // into a CUDA graph per (workspace, B, posterior) and replayed with one launch
+    struct GraphEntry {
+        const void* llrT = nullptr;   // identifies the workspace allocation the nodes point into
+        int64_t B = 0, Bp = 0;
+        bool want_post = false;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0, cn_launches = 0, vn_launches = 0;
+        uint64_t stamp = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    uint64_t graph_clock = 0;
+    int use_graphs = 1;                 // LDPC_GRAPHS=0 switches the replay path off
+    int64_t graph_max_iter_bytes = (int64_t)128 << 20;   // "launch-bound": one iteration moves less than this
+    int64_t stat_graph_replays = 0;
     int64_t fine_items_max_frames = 128;    // batches up to this size (single-frame calls) use one-node work items
     int compact = 1;              // LDPC_COMPACT=0 switches compaction and the all-done exit off
     int64_t compact_min_frames = 512;
@@ -454,6 +470,9 @@ int item_set(const ldpc_decoder* d, int64_t Bp) { return Bp <= d->fine_items_max
 int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     if (ws.cap >= Bp) return LDPC_OK;
     if (Bp > ((int64_t)1 << 28)) return fail(LDPC_ERR_UNSUPPORTED, "more than 2^28 frames per call (32-bit row strides)");
+    for (auto& ge : d->graphs)   // captured graphs point into workspace allocations: drop them all
+        if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    d->graphs.clear();
     ws.release();
     const ldpc_graph* g = d->g;
     const size_t rows_v2c = (size_t)std::max<int64_t>(std::max<int64_t>(g->E, g->n), 1);
@@ -716,6 +735,75 @@ int scan_ensure(ldpc_decoder* d, int64_t Bp) {
     return LDPC_OK;
 }
 
+// A decode is launch-bound when one iteration moves so few bytes (tiny code or tiny batch) that the ~4 kernel
+// launches per iteration cost more than their work, and the remaining iterations of an all-stopped batch are
+// cheaper to replay than a host round trip per checkpoint.
+bool launch_bound(const ldpc_decoder* d, int64_t Bp) {
+    if (!d->use_graphs || d->prof_mode != 0 || d->T > 24) return false;
+    const ldpc_graph* g = d->g;
+    const int64_t per_frame = (int64_t)(4 * g->E + g->n) * (int64_t)d->rsz;   // 16E + 4n bytes for float32
+    return Bp * per_frame <= d->graph_max_iter_bytes;
+}
+
+// reset + iterations 0..T-1 as ONE graph launch.  The graph is captured on an internal stream (the caller's may
+// be the legacy default stream, which cannot be captured) and its nodes point into `ws`, so an entry is keyed by
+// the workspace allocation, B (pad frames are born done), Bp and the posterior flag.  Early stop still works
+// inside the replay (done masks; warps of stopped frames exit at once), there are just no checkpoints.
+int replay_graph(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
+    ldpc_decoder::GraphEntry* hit = nullptr;
+    for (auto& ge : d->graphs)
+        if (ge.exec && ge.llrT == ws.llrT && ge.B == B && ge.Bp == Bp && ge.want_post == want_post) hit = &ge;
+    if (!hit) {
+        if (!d->cap_stream) CU(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+        if (d->graphs.size() >= 8) {   // evict the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < d->graphs.size(); ++i)
+                if (d->graphs[i].stamp < d->graphs[lru].stamp) lru = i;
+            if (d->graphs[lru].exec) cudaGraphExecDestroy(d->graphs[lru].exec);
+            d->graphs.erase(d->graphs.begin() + (long)lru);
+        }
+        const ldpc_profile before = d->prof;
+        cudaStream_t cs = d->cap_stream;
+        CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        int rc = LDPC_OK;
+        {
+            cudaStream_t stream = cs;   // LAUNCH enqueues on `stream`
+            cudaError_t le = launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream);
+            d->prof.launches++;
+            if (le != cudaSuccess) rc = fail(LDPC_ERR_CUDA, "reset (capture): %s", cudaGetErrorString(le));
+            if (!rc) rc = run_span(d, ws, Bp, 0, d->T, want_post, stream);
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t ee = cudaStreamEndCapture(cs, &graph);
+        ldpc_decoder::GraphEntry ge;
+        ge.launches = d->prof.launches - before.launches;
+        ge.cn_launches = d->prof.cn_launches - before.cn_launches;
+        ge.vn_launches = d->prof.vn_launches - before.vn_launches;
+        d->prof = before;              // nothing ran yet: the replay below does the counting
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ee != cudaSuccess) return fail(LDPC_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
+        ee = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ee != cudaSuccess) return fail(LDPC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ee));
+        ge.llrT = ws.llrT;
+        ge.B = B;
+        ge.Bp = Bp;
+        ge.want_post = want_post;
+        d->graphs.push_back(ge);
+        hit = &d->graphs.back();
+    }
+    hit->stamp = ++d->graph_clock;
+    CU(cudaGraphLaunch(hit->exec, stream));
+    d->prof.launches += hit->launches;
+    d->prof.cn_launches += hit->cn_launches;
+    d->prof.vn_launches += hit->vn_launches;
+    d->stat_graph_replays++;
+    return LDPC_OK;
+}
+
 // The whole decode of the frames resident as llrT [n][Bp] in `root`, results delivered per OutSpec.
 //
 // Flooding with early stop runs in spans between checkpoints.  At a checkpoint the number of running frames
@@ -731,6 +819,11 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
     }
     const ldpc_graph* g = d->g;
+    if (launch_bound(d, Bp)) {
+        int rc = replay_graph(d, root, B, Bp, want_post, stream);
+        if (rc) return rc;
+        return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
+    }
     LAUNCH(K_OTHER, launch_reset_state(root.done, root.iters, root.success, root.unsat, B, Bp, d->T, stream));
     const bool checkpoints = d->early_stop && d->compact && d->T > 2;
     Workspace* ws = &root;
@@ -886,6 +979,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
     if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);
+    if (const char* gr = getenv("LDPC_GRAPHS")) d->use_graphs = atoi(gr) != 0;
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
     DeviceGuard guard(g->device);
@@ -983,6 +1077,9 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
         cudaFree(lv.idx);
         cudaFree(lv.map);
     }
+    for (auto& ge : d->graphs)
+        if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
     cudaFree(d->d_scan);
     cudaFree(d->d_total);
     if (d->h_total) cudaFreeHost(d->h_total);
@@ -1178,9 +1275,10 @@ extern "C" int ldpc_decoder_profile_read(ldpc_decoder* d, ldpc_profile* out, int
     }
     d->prof.compactions = d->stat_compactions;
     d->prof.early_exits = d->stat_early_exits;
+    d->prof.graph_replays = d->stat_graph_replays;
     *out = d->prof;
     if (reset) {
-        d->stat_compactions = d->stat_early_exits = 0;
+        d->stat_compactions = d->stat_early_exits = d->stat_graph_replays = 0;
         int64_t fp = d->prof.frames_padded;
         d->prof = ldpc_profile{};
         d->prof.frames_padded = fp;

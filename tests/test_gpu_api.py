@@ -279,3 +279,46 @@ def test_degenerate_graphs(built_lib, H):
     ref = O.decode(og, llr, T=T, mode=MODE_RCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 1))
     assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
     assert np.array_equal(s.cpu().numpy().astype(bool), ref.success)
+
+
+def test_launch_bound_decodes_replay_a_cuda_graph(built_lib, monkeypatch):
+    """Tiny codes / tiny batches are launch-bound: the T-iteration launch sequence is captured once and replayed
+    (profile.graph_replays), with identical results to the plain launch path (LDPC_GRAPHS=0), also after the
+    weights change and after the workspace is re-allocated for a larger batch."""
+    L = built_lib
+    code = L.create_test_ldpc_code()
+    rng = np.random.default_rng(3)
+    llr = torch.from_numpy((rng.standard_normal((300, 7)) * 2 + 0.7).astype(np.float32)).cuda()
+
+    def make():
+        torch.manual_seed(1)
+        d = L.Neural2DMinSumDecoder(code, 2, 10)
+        with torch.no_grad():
+            d._beta_table.uniform_(0.5, 1.0)
+            d._alpha_table.uniform_(0.8, 1.0)
+        return d
+
+    monkeypatch.setenv("LDPC_GRAPHS", "0")
+    plain = make()
+    ref = [plain(llr), plain(llr[:5]), plain(llr[7])]
+    assert plain._engine(0).profile_read()["graph_replays"] == 0
+    monkeypatch.setenv("LDPC_GRAPHS", "1")
+    dec = make()
+    for _ in range(3):
+        out = [dec(llr), dec(llr[:5]), dec(llr[7])]
+        for a, b in zip(ref, out):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+            assert (a[2] == b[2]) if isinstance(a[2], int) else torch.equal(a[2], b[2])
+    prof = dec._engine(0).profile_read()
+    assert prof["graph_replays"] == 9 and prof["cn_launches"] == 90, prof
+    with torch.no_grad():                      # new weights: same graph, new table contents
+        dec._beta_table.mul_(0.9)
+        plain._beta_table.mul_(0.9)
+    a, b = plain(llr), dec(llr)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    big = torch.from_numpy((rng.standard_normal((5000, 7)) * 2 + 0.7).astype(np.float32)).cuda()
+    a, b = plain(big), dec(big)                # workspace grows: cached graphs are dropped and re-captured
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    a, b = plain(llr), dec(llr)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert dec._engine(0).profile_read()["graph_replays"] == 3
