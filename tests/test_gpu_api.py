@@ -322,3 +322,49 @@ def test_launch_bound_decodes_replay_a_cuda_graph(built_lib, monkeypatch):
     a, b = plain(llr), dec(llr)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert dec._engine(0).profile_read()["graph_replays"] == 3
+
+
+@pytest.mark.parametrize("kind", ["n2d2", "rcq", "basic"])
+def test_encode_channel_symmetry_round_trip_full_size(built_lib, kind):
+    """Size-independent property at the full (16200,7200) shape: encode random information bits (the code is
+    IRA: parity = running XOR of the information syndromes), send the codeword c instead of the all-zero word
+    over the same noise (llr_c = llr_0 * (1 - 2c)), and the decoder must return bits_0 XOR c with the same
+    iteration counts and the sign-flipped posteriors, bit for bit (min-sum is symmetric; negation is exact)."""
+    L = built_lib
+    T = 10
+    code = L.codes.dvbs2_shaped(max_iterations=T)
+    g = code.graph
+    n, k, m = g.n, code.k, g.m
+    B = 1536
+    rng = np.random.default_rng(12)
+    H = code.H.tocsr()
+    info = rng.integers(0, 2, size=(B, k)).astype(np.int64)
+    s = (H[:, :k] @ info.T) % 2                       # [m, B] information part of every check
+    par = np.cumsum(s, axis=0) % 2                    # p_i = p_{i-1} xor s_i (dual-diagonal parity part)
+    cw = np.concatenate([info, par.T], axis=1).astype(np.uint8)
+    assert not g.syndrome(cw[:64]).any() and cw.any()
+    llr0 = torch.cat([L.awgn_llr(n, B // 2, 2.2, seed=3, llr_sign=1), L.awgn_llr(n, B - B // 2, 3.0, seed=4, llr_sign=1)])
+    flip = torch.from_numpy(1.0 - 2.0 * cw.astype(np.float32)).cuda()
+    llrc = llr0 * flip
+    if kind == "n2d2":
+        dec = L.Neural2DMinSumDecoder(code, 2, T)
+        with torch.no_grad():
+            dec._beta_table.fill_(0.8)
+            dec._alpha_table.fill_(0.97)
+        b0, p0, i0 = dec(llr0)
+        bc, pc, ic = dec(llrc)
+        assert torch.equal(pc, p0 * flip)
+    elif kind == "rcq":
+        dec = L.RCQMinSumDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], max_iterations=T)
+        b0, s0, i0 = dec.decode(llr0)
+        bc, sc, ic = dec.decode(llrc)
+        assert torch.equal(s0, sc)
+    else:
+        dec = L.BasicMinSumDecoder(code, 0.8)
+        b0, s0, i0 = dec.decode(llr0.double())
+        bc, sc, ic = dec.decode(llrc.double())
+        assert torch.equal(s0, sc)
+    cwt = torch.from_numpy(cw).to(b0.device)
+    assert torch.equal(i0, ic) and len(set(i0.tolist())) > 2
+    # (a posterior of exactly 0 would decide bit 0 on both sides; with continuous noise that does not occur)
+    assert torch.equal(bc.to(torch.uint8), b0.to(torch.uint8) ^ cwt)
