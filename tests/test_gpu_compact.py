@@ -69,6 +69,20 @@ def test_compacted_decode_vs_oracle(built_lib, monkeypatch, B):
     assert np.array_equal(s.cpu().numpy(), ref.success)
     assert rcq._engine(0).profile_read()["compactions"] >= 1
 
+    # W-RCQ forward(): posterior of stopped frames from their frozen codes with the quantiser of THEIR last iteration
+    from oracle.restatement import MODE_WRCQ
+    w = L.WeightedRCQDecoder(code, bc=4, bv=8, quantizer_params=qp, weight_sharing_type=2, max_iterations=T)
+    with torch.no_grad():
+        w._beta_table.uniform_(0.8, 1.0)
+    b, p, i = w(torch.from_numpy(llr32).cuda())
+    thr4 = np.array([q.thresholds for q in w.quantizers], dtype=np.float64).astype(np.float32)
+    ref = O.decode(og, llr32, T=T, mode=MODE_WRCQ, bc=4, thresholds=thr4, quantizer_of_iter=quantizer_schedule(T, 3),
+                   beta=w._beta_table.detach().numpy()[:, w._beta_index],
+                   alpha=(w._alpha_table.detach().numpy()[:, w._alpha_index] if w._alpha_table is not None
+                          else np.ones((T, g.n), np.float32)), nthreads=8)
+    assert np.array_equal(i.cpu().numpy(), ref.iterations) and np.array_equal(b.cpu().numpy(), ref.bits)
+    assert np.array_equal(p.cpu().numpy(), ref.posterior)
+
     basic = L.BasicMinSumDecoder(code, factor=0.8)
     bb, ss, ii = basic.decode(llr)
     ref = O.decode(og, llr, T=T, dtype=np.float64, beta=np.full((T, g.E), 0.8), nthreads=8)

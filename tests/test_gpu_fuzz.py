@@ -42,6 +42,7 @@ def test_random_configurations_vs_oracle(built_lib, monkeypatch, seed):
     L = built_lib
     rng = np.random.default_rng(9000 + seed)
     monkeypatch.setenv("LDPC_COMPACT_MIN_FRAMES", "128")
+    monkeypatch.setenv("LDPC_GRAPHS", str(seed % 2))    # odd: graph replay; even: checkpoints + frame compaction
     H = _random_graph(rng)
     m, n = H.shape
     T = int(rng.integers(1, 14))
