@@ -450,6 +450,8 @@ struct ldpc_decoder {
     int64_t fine_items_max_frames = 128;    // batches up to this size (single-frame calls) use one-node work items
     int compact = 1;              // LDPC_COMPACT=0 switches compaction and the all-done exit off
     int64_t compact_min_frames = 512;
+    int compact_percent = 60;     // compact when at most this share of the level's lanes still runs
+    int checkpoint_step = 1;      // iterations between checkpoints for batches of >= 16384 frames
     int64_t stat_compactions = 0, stat_early_exits = 0;
     // instrumentation
     int prof_mode = 0;
@@ -707,12 +709,13 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
 }
 
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
-// Large batches can afford a look every other iteration (an iteration is milliseconds long); small ones
+// Large batches can afford a look after every iteration (an iteration is milliseconds long); smaller ones
 // space the checkpoints out so that the syncs stay a small part of the decode.  `quiet` counts the
 // checkpoints in a row at which no frame had stopped yet: until the first frame stops the interval is doubled.
-int next_checkpoint(int t, int T, int64_t Bp, int quiet) {
+int next_checkpoint(int t, int T, int64_t Bp, int quiet, int big_step) {
     int step;
-    if (Bp >= 4096) step = t < 20 ? 2 : 4;
+    if (Bp >= 16384) step = t < 20 ? big_step : 2 * big_step;   // an iteration is milliseconds long: look every time
+    else if (Bp >= 4096) step = t < 20 ? 2 : 4;
     else if (t < 8) step = 2;
     else if (t < 24) step = 4;
     else step = 8;
@@ -837,7 +840,7 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
     }
     int quiet = 0;
     while (true) {
-        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp, quiet) : d->T;
+        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp, quiet, d->checkpoint_step) : d->T;
         int rc = run_span(d, *ws, curBp, t, t1, want_post, stream);
         if (rc) return rc;
         t = t1;
@@ -855,13 +858,13 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
             }
             return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
         }
-        if (curBp < d->compact_min_frames || pending * 10 > curBp * 6 || level >= kMaxLevels) continue;
+        if (curBp < d->compact_min_frames || pending * 100 > curBp * d->compact_percent || level >= kMaxLevels) continue;
         // ---- move the running frames to a dense child level ----
         if (d->levels.size() <= level) d->levels.emplace_back();   // capacity reserved at creation: no reallocation
         ldpc_decoder::Level& lv = d->levels[level];
         const int64_t childBp = pad_frames(pending);
         if (lv.cap < childBp) {
-            const int64_t cap = std::max(childBp, pad_frames((curBp * 6 + 9) / 10));   // any later count of this level fits
+            const int64_t cap = std::max(childBp, pad_frames((curBp * d->compact_percent + 99) / 100));   // any later count of this level fits
             cudaFree(lv.idx);
             cudaFree(lv.map);
             lv.idx = lv.map = nullptr;
@@ -870,7 +873,7 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
             CU(cudaMalloc((void**)&lv.map, (size_t)cap * sizeof(int32_t)));
             lv.cap = cap;
         }
-        rc = ws_ensure(d, lv.ws, std::max(childBp, std::min(lv.cap, pad_frames((curBp * 6 + 9) / 10))));
+        rc = ws_ensure(d, lv.ws, std::max(childBp, std::min(lv.cap, pad_frames((curBp * d->compact_percent + 99) / 100))));
         if (rc == LDPC_ERR_NOMEM) {   // no room for a child level: carry on uncompacted
             cudaGetLastError();
             lv.ws.release();
@@ -980,6 +983,8 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
     if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);
     if (const char* gr = getenv("LDPC_GRAPHS")) d->use_graphs = atoi(gr) != 0;
+    if (const char* cf = getenv("LDPC_COMPACT_PERCENT")) d->compact_percent = std::min(95, std::max(5, atoi(cf)));
+    if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
     DeviceGuard guard(g->device);
