@@ -372,8 +372,11 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
 }
 
 // resident CTAs per SM the check-node kernel is compiled for: the RCQ variant is issue-bound and gains from
-// 4 (64 registers); float32 / float64 stream at the HBM roofline with 3 / 2
-#define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : 2))
+// 4 (64 registers); float32 / float64 stream at the HBM roofline with 3 (80 registers)
+#ifndef LDPC_CN_F64_MINCTAS
+#define LDPC_CN_F64_MINCTAS 3
+#endif
+#define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : LDPC_CN_F64_MINCTAS))
 // FREEZE: stopped frames keep their c2v (forward()'s posterior output); otherwise the stores carry no mask code.
 template <typename Real, bool QUANT, int NTH, bool FREEZE>
 __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const int item0) {
