@@ -21,7 +21,7 @@ def golden_cases():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         stem = os.path.splitext(os.path.basename(f))[0]
-        if stem == "quantizer_kat" or stem.endswith("_next"):
+        if stem == "quantizer_kat" or stem.endswith("_next") or stem.startswith("fullsize_"):
             continue
         z = np.load(f)
         for c in sorted(set(k.split("/")[0] for k in z.files)):
@@ -54,3 +54,35 @@ def built_lib():
         ge.build()
     import ldpc_b200
     return ldpc_b200
+
+
+FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc"]
+
+
+def load_fullsize(case):
+    """(record, code) of a full-size golden case (tests/golden/make_golden_fullsize.py), or a pytest skip when the
+    file is absent.  The graph is rebuilt from the package's seeded generator and checked against the stored hash."""
+    import hashlib
+    path = os.path.join(GOLDEN_DIR, f"fullsize_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    import ldpc_b200 as L
+    z = np.load(path)
+    T = int(z["T"])
+    code = L.codes.dvbs2_shaped(max_iterations=T) if case.endswith("dvbs2") else L.codes.qc_shaped(max_iterations=T)
+    g = code.graph
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(g.check_ptr).tobytes())
+    h.update(np.ascontiguousarray(g.check_var).tobytes())
+    assert h.hexdigest() == str(z["graph_sha256"]), "code generator changed: regenerate the full-size golden vectors"
+    return z, code
+
+
+def fullsize_tables(z, dec):
+    """Load the recorded reference weights into our module; returns per-edge beta / per-variable alpha for the oracle."""
+    import torch
+    state = {str(k): torch.tensor([float(v)]) for k, v in zip(z["weight_keys"], z["weight_vals"])}
+    dec.load_reference_state_dict(state)
+    beta = dec._beta_table.detach().numpy()[:, dec._beta_index] if dec._beta_table is not None else None
+    alpha = dec._alpha_table.detach().numpy()[:, dec._alpha_index] if dec._alpha_table is not None else None
+    return beta, alpha

@@ -219,3 +219,32 @@ def test_batch_equals_single_frames_and_host_equals_device(built_lib):
     for f in range(0, 40, 7):
         b, p, i = dec(torch.from_numpy(llr[f]).cuda())
         assert torch.equal(b, B[f]) and torch.equal(p, P[f]) and i == int(I[f])
+
+
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc"])
+def test_fullsize_reference_vectors(built_lib, case):
+    """The CUDA path against frames decoded by the LIVE reference at BASELINE's full code sizes."""
+    from conftest import fullsize_tables, load_fullsize
+    z, code = load_fullsize(case)
+    L = built_lib
+    T = int(z["T"])
+    x = torch.from_numpy(z["llr"]).cuda()
+    if case.startswith("n2d2"):
+        dec = L.Neural2DMinSumDecoder(code, 2, T)
+        fullsize_tables(z, dec)
+        b, p, i = dec(x)
+        assert np.array_equal(p.cpu().numpy(), z["posterior"])
+    elif case.startswith("rcq"):
+        dec = L.RCQMinSumDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], max_iterations=T)
+        b, s, i = dec.decode(x)
+        assert np.array_equal(s.cpu().numpy().astype(bool), z["success"])
+    else:
+        dec = L.WeightedRCQDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], weight_sharing_type=1, max_iterations=T)
+        fullsize_tables(z, dec)
+        b, p, i = dec(x)
+        assert np.array_equal(p.cpu().numpy(), z["posterior"])
+    assert np.array_equal(b.cpu().numpy().astype(np.uint8), z["bits"])
+    assert np.array_equal(i.cpu().numpy(), z["iterations"])
+    # single-frame call, as the reference is driven
+    out = dec.decode(x[0]) if case.startswith("rcq") else dec(x[0])
+    assert np.array_equal(out[0].cpu().numpy().astype(np.uint8), z["bits"][0]) and out[2] == int(z["iterations"][0])

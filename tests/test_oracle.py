@@ -195,3 +195,37 @@ def test_next_rows_match_live_reference(stem, case, impl):
         assert np.array_equal(res.posterior, g["posterior"])
     if "success" in g:
         assert np.array_equal(res.success, g["success"])
+
+
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc"])
+def test_oracle_reproduces_fullsize_reference_vectors(case):
+    """BASELINE's full code sizes: frames decoded by the LIVE reference (minutes per frame,
+    tests/golden/make_golden_fullsize.py) against the C port -- bits, iterations, success, posteriors bit for bit."""
+    from conftest import fullsize_tables, load_fullsize
+    z, code = load_fullsize(case)
+    import ldpc_b200 as L
+    from oracle import capi as O
+    from oracle.restatement import MODE_NMS, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule
+    g = code.graph
+    og = SparseGraph.from_coo(g.n, g.m, g.edge_check, g.check_var)
+    T = int(z["T"])
+    x = z["llr"]
+    if case.startswith("n2d2"):
+        dec = L.Neural2DMinSumDecoder(code, 2, T)
+        beta, alpha = fullsize_tables(z, dec)
+        ref = O.decode(og, x, T=T, mode=MODE_NMS, beta=beta, alpha=alpha, nthreads=4)
+    else:
+        thr = z["thresholds"].astype(np.float32)
+        kw = dict(T=T, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
+        if case.startswith("rcq"):
+            ref = O.decode(og, x, mode=MODE_RCQ, **kw)
+        else:
+            dec = L.WeightedRCQDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], weight_sharing_type=1, max_iterations=T)
+            beta, alpha = fullsize_tables(z, dec)
+            ref = O.decode(og, x, mode=MODE_WRCQ, beta=beta,
+                           alpha=alpha if alpha is not None else np.ones((T, g.n), np.float32), **kw)
+    assert np.array_equal(ref.bits, z["bits"]) and np.array_equal(ref.iterations, z["iterations"])
+    if "success" in z.files:
+        assert np.array_equal(ref.success, z["success"])
+    if "posterior" in z.files:
+        assert np.array_equal(ref.posterior, z["posterior"])
