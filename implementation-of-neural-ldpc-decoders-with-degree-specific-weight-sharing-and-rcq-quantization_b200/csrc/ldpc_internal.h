@@ -102,7 +102,7 @@ cudaError_t launch_pack(int dtype, const void* llr, void* llrT, int64_t B, int64
 cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, uint32_t* unsat2,
                                int64_t B, int64_t Bp, int32_t T, cudaStream_t stream);
 // hardw -> bits [B][n] uint8
-// `map` (may be nullptr): output row of local frame f is map[f] (frames of a re-decode level)
+// `map` (may be nullptr): output row of local frame f is map[f] (frames of a compacted level)
 cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B,
                                int32_t n, const int32_t* map, cudaStream_t stream);
 // postT [n][Bp] -> post [B][n]
