@@ -1156,15 +1156,28 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
     }
     int rc = ws_ensure(d, pp.ws, pad_frames(chunk));
     if (rc) return rc;
-    // chunk boundaries: the first chunks are ramped (1/8, 1/4, 1/2 of a chunk) so the kernels start while most of
-    // the input is still crossing PCIe; the un-overlapped head of the pipeline shrinks accordingly
+    // chunk boundaries.  The link delivers a chunk's LLRs a little faster than the kernels consume them, so
+    // the first chunks grow geometrically (x1.5 from 1/8 of a chunk: each input copy then lands before the
+    // previous chunk's decode ends and the kernels start ~1 ms into the call); the rest of the batch is split
+    // into equal chunks so that no small remainder is left for the un-overlapped tail.
     std::vector<std::pair<int64_t, int64_t>> chunks;   // (offset, frames)
-    for (int64_t off = 0, i = 0; off < B; ++i) {
-        int64_t want = chunk;
-        if (B > 2 * chunk && i < 3) want = std::max<int64_t>(kFrameAlign, (chunk >> (3 - i)) / kFrameAlign * kFrameAlign);
-        const int64_t b = std::min<int64_t>(want, B - off);
-        chunks.emplace_back(off, b);
-        off += b;
+    {
+        int64_t off = 0;
+        if (B > 2 * chunk) {
+            for (int64_t c = std::max<int64_t>(kFrameAlign, chunk / 8); c < chunk && B - off > 2 * chunk; c = c * 3 / 2) {
+                const int64_t b = std::max<int64_t>(kFrameAlign, c / kFrameAlign * kFrameAlign);
+                chunks.emplace_back(off, b);
+                off += b;
+            }
+        }
+        while (off < B) {   // equal parts, each a multiple of 128 frames (except the last) and at most `chunk`
+            const int64_t left = B - off;
+            const int64_t parts = (left + chunk - 1) / chunk;
+            int64_t b = ((left + parts - 1) / parts + kFrameAlign - 1) / kFrameAlign * kFrameAlign;
+            b = std::min<int64_t>(std::min<int64_t>(b, chunk), left);
+            chunks.emplace_back(off, b);
+            off += b;
+        }
     }
     // The input copy of chunk i+1 is enqueued BEFORE the decode of chunk i: the decode may block the host at
     // its checkpoints (frame compaction), and the copy engine should be busy meanwhile.
@@ -1176,6 +1189,16 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         CU(cudaEventRecord(bf.in_ready, pp.s_in));
         return LDPC_OK;
     };
+    const bool trace = getenv("LDPC_PIPE_TRACE") != nullptr;   // debug: per-chunk timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    mark(pp.s_in);
     rc = enqueue_input(0);
     for (size_t i = 0; i < chunks.size() && !rc; ++i) {
         const int64_t off = chunks[i].first, b = chunks[i].second;
@@ -1187,10 +1210,12 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         }
         CU(cudaStreamWaitEvent(pp.s_run, bf.in_ready, 0));
         if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_run, bf.out_done, 0));    // staging outputs copied out
+        mark(pp.s_run);
         rc = decode_on_device(d, pp.ws, bf.d_llr, b, bits ? bf.d_bits : nullptr, posterior ? bf.d_post : nullptr,
                               bf.d_it, bf.d_su, pp.s_run);
         if (rc) break;
         CU(cudaEventRecord(bf.run_done, pp.s_run));
+        mark(pp.s_run);
         CU(cudaStreamWaitEvent(pp.s_out, bf.run_done, 0));
         if (bits) CU(cudaMemcpyAsync(bits + (size_t)off * n, bf.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, pp.s_out));
         if (posterior)
@@ -1199,10 +1224,22 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         if (iterations) CU(cudaMemcpyAsync(iterations + off, bf.d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, pp.s_out));
         if (success) CU(cudaMemcpyAsync(success + off, bf.d_su, (size_t)b, cudaMemcpyDeviceToHost, pp.s_out));
         CU(cudaEventRecord(bf.out_done, pp.s_out));
+        mark(pp.s_out);
     }
     for (cudaStream_t st : {pp.s_in, pp.s_run, pp.s_out}) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess && !rc) rc = fail(LDPC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    }
+    if (trace && tev.size() >= 1) {
+        for (size_t i = 0; i + 3 < tev.size() + 0 && 1 + 3 * i + 2 < tev.size(); ++i) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]);
+            cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * i]);
+            cudaEventElapsedTime(&c, tev[0], tev[3 + 3 * i]);
+            fprintf(stderr, "chunk %2zu frames %6lld: decode start %7.2f ms  end %7.2f ms (%.2f)  outputs copied %7.2f ms\n", i,
+                    (long long)chunks[i].second, a, b, b - a, c);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return rc;
 }
