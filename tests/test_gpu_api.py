@@ -368,3 +368,46 @@ def test_encode_channel_symmetry_round_trip_full_size(built_lib, kind):
     assert torch.equal(i0, ic) and len(set(i0.tolist())) > 2
     # (a posterior of exactly 0 would decide bit 0 on both sides; with continuous noise that does not occur)
     assert torch.equal(bc.to(torch.uint8), b0.to(torch.uint8) ^ cwt)
+
+
+def test_one_decoder_many_calls_of_changing_shape(built_lib, monkeypatch):
+    """One handle, 60 calls with changing batch sizes, entry points and output sets (workspace growth, graph
+    cache eviction and invalidation, compaction levels of changing size, host pipeline staging re-allocation):
+    every call must equal a fresh handle's answer for the same frames."""
+    L = built_lib
+    monkeypatch.setenv("LDPC_COMPACT_MIN_FRAMES", "128")
+    monkeypatch.setenv("LDPC_HOST_CHUNK", "512")
+    T = 16
+    code = L.codes.dvbs2_shaped(max_iterations=T, scale=20)
+    rng = np.random.default_rng(77)
+
+    def make():
+        torch.manual_seed(5)
+        d = L.Neural2DMinSumDecoder(code, 2, T)
+        with torch.no_grad():
+            d._beta_table.uniform_(0.7, 0.9)
+            d._alpha_table.uniform_(0.95, 1.0)
+        return d
+
+    dec = make()
+    pool = torch.cat([L.awgn_llr(code.n, 1500, snr, seed=30 + k, llr_sign=1) for k, snr in enumerate((1.0, 2.5, 3.5, 6.0))])
+    pool = pool[torch.randperm(pool.shape[0], generator=torch.Generator().manual_seed(1)).cuda()]
+    sizes = [1, 3000, 7, 128, 129, 2, 5000, 640, 1, 333] + [int(x) for x in rng.integers(1, 4000, size=50)]
+    for k, B in enumerate(sizes):
+        off = int(rng.integers(0, pool.shape[0] - B + 1))
+        x = pool[off:off + B]
+        mode = k % 3
+        fresh = make()
+        if mode == 0:                                   # device, with posterior
+            a, b = dec(x), fresh(x)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), (k, B)
+        elif mode == 1:                                 # device, decisions only (mask-free kernels)
+            a = dec._engine(0).decode_device(x)
+            b = fresh._engine(0).decode_device(x)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), (k, B)
+        else:                                           # host pipeline (chunks of 512 frames)
+            a, b = dec(x.cpu()), fresh(x.cpu())
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), (k, B)
+        del fresh
+    prof = dec._engine(0).profile_read()
+    assert prof["graph_replays"] > 0 and prof["compactions"] > 0, prof
