@@ -348,8 +348,10 @@ struct Workspace {
     int32_t* iters = nullptr;
     uint8_t* success = nullptr;
     int32_t* fcnt = nullptr;    // [Bp] per-frame bit-error scratch of the Monte-Carlo count
+    void* post = nullptr;       // [n][cap] posterior rows; allocated the first time a posterior is asked for
     void release() {
         cudaFree(fcnt);
+        cudaFree(post);
         cudaFree(llrT); cudaFree(v2c); cudaFree(c2v); cudaFree(hardw); cudaFree(unsat);
         cudaFree(done); cudaFree(iters); cudaFree(success);
         *this = Workspace();
@@ -415,7 +417,6 @@ struct ldpc_decoder {
     void* d_alpha = nullptr;               // [T][n_alpha]
     float* d_thr = nullptr;                // [Q][nth]
     float* d_lut = nullptr;                // [Q][2^bc]
-    int32_t* d_q_of_iter = nullptr;        // [T]
     Workspace ws;
     HostPipe pipe;
     int64_t host_chunk = 0;
@@ -494,6 +495,13 @@ int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     return LDPC_OK;
 }
 
+// forward()'s posterior rows, [n][cap] like llrT (only decoders that are asked for posteriors pay for them)
+int post_ensure(ldpc_decoder* d, Workspace& ws) {
+    if (ws.post) return LDPC_OK;
+    CU(cudaMalloc(&ws.post, (size_t)d->g->n * (size_t)ws.cap * d->rsz));
+    return LDPC_OK;
+}
+
 // ---- instrumentation helpers ----
 enum { K_CN = 0, K_VN = 1, K_OTHER = 2 };
 
@@ -541,7 +549,7 @@ struct Timed {
 
 // The flooding schedule on frames already resident as llrT [n][Bp] in `ws`.
 // After it returns (stream order): ws.hardw holds the final hard decisions of every frame,
-// ws.iters / ws.success the per-frame results, and ws.v2c holds postT [n][Bp] if want_post.
+// ws.iters / ws.success the per-frame results, and ws.post holds postT [n][Bp] if want_post.
 // Layered RCQ (rcq_decoder.py:281-350): the posteriors live in ws.llrT and are updated in place.
 int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
@@ -566,7 +574,7 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
             LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
         }
     }
-    if (want_post) CU(cudaMemcpyAsync(ws.v2c, ws.llrT, (size_t)g->n * Bp * d->rsz, cudaMemcpyDeviceToDevice, stream));
+    if (want_post) CU(cudaMemcpyAsync(ws.post, ws.llrT, (size_t)g->n * Bp * d->rsz, cudaMemcpyDeviceToDevice, stream));
     return LDPC_OK;
 }
 
@@ -583,7 +591,7 @@ struct OutSpec {
     int32_t* frame_iters = nullptr;
 };
 
-void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool want_post, CnLaunch& cn) {
+void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, CnLaunch& cn) {
     const ldpc_graph* g = d->g;
     const int q = d->bc ? d->q_of_iter[t] : 0;
     cn.src = (t == 0) ? ws.llrT : ws.v2c;
@@ -603,7 +611,6 @@ void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool want_post, 
     cn.items_wide_begin = il.wide_begin;
     cn.items_wide_end = il.wide_end;
     cn.wide_ring = d->wide_ring;
-    cn.freeze = want_post ? 1 : 0;
     cn.Bp = Bp;
     if (d->check_rule == LDPC_RULE_OFFSET) {
         cn.aidx_slot = d->d_aidx_slot;
@@ -616,7 +623,7 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.c2v = ws.c2v;
     vn.v2c = ws.v2c;
     vn.llrT = ws.llrT;
-    vn.postT = (final_pass && want_post) ? ws.v2c : nullptr;  // v2c is dead once the final pass runs
+    vn.postT = want_post ? ws.post : nullptr;   // running frames refresh their posterior every iteration
     vn.vslots = g->d_vslots;
     vn.vpos_var = g->d_vpos_var;
     vn.aidx = d->d_aidx;
@@ -626,8 +633,6 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.bc = d->bc;
     vn.n_quant = d->Q;
     vn.q_now = d->bc ? d->q_of_iter[t] : 0;
-    vn.q_of_iter = d->d_q_of_iter;
-    vn.iters = ws.iters;
     vn.hardw = ws.hardw;
     vn.Wn = Bp / 32;
     vn.done = ws.done;
@@ -636,23 +641,22 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.n_items = (int)il.items.size();
     vn.Bp = Bp;
     vn.final_pass = final_pass ? 1 : 0;
-    vn.freeze = want_post ? 1 : 0;
     vn.items_wide_begin = il.wide_begin;
     vn.items_wide_end = il.wide_end;
     vn.wide_max_deg = il.wide_max_deg;
     vn.wide_stage = d->wide_ring;
 }
 
-// Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node pass: the
-// dead v2c update of iteration T-1 is not written, and when posteriors are wanted it recomputes them for EVERY
-// frame from its frozen c2v (frames that stopped at iteration t kept c2v(t)); packed decisions of stopped
-// frames stay in place from the iteration they stopped at.
+// Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node variant (its
+// dead v2c update is not written).  Stopped frames are never touched again: their packed decisions stay in
+// place from the iteration they stopped at, and so does their posterior row entry when posteriors are wanted
+// (running frames refresh theirs every iteration).
 int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool want_post, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
     const int64_t Wn = Bp / 32;
     for (int t = t0; t < t1; ++t) {
         CnLaunch cn{};
-        fill_cn(d, ws, Bp, t, want_post, cn);
+        fill_cn(d, ws, Bp, t, cn);
         if (d->check_rule == LDPC_RULE_OFFSET) LAUNCH(K_CN, launch_cn_offset(d->dtype, cn, stream));
         else LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
         const bool last = (t == d->T - 1);
@@ -676,15 +680,6 @@ int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool wa
     return LDPC_OK;
 }
 
-// The final pass on its own, for forward()'s posterior output (a level whose frames have all stopped, or whose
-// running frames are about to move to a compacted level): posteriors of every frame from its frozen c2v.
-int run_final_pass(ldpc_decoder* d, Workspace& ws, int64_t Bp, bool want_post, cudaStream_t stream) {
-    VnLaunch vn{};
-    fill_vn(d, ws, Bp, d->T - 1, true, want_post, vn);
-    LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
-    return LDPC_OK;
-}
-
 // Results of one level -> the caller's buffers.  `map` (nullptr = identity) gives the caller's frame of each
 // frame of the level; `only_done` != nullptr leaves the running frames to the next level.
 int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int32_t* map, const uint8_t* only_done,
@@ -697,7 +692,7 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
     }
     // running frames of a parent level also write their (unfinished) rows here; the next level overwrites them
     if (o.bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, o.bits, B, g->n, map, stream));
-    if (o.post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.v2c, o.post, B, Bp, g->n, map, stream));
+    if (o.post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.post, o.post, B, Bp, g->n, map, stream));
     if (map) {
         if (o.iters || o.success)
             LAUNCH(K_OTHER, launch_scatter_frames(ws.iters, ws.success, o.iters, o.success, map, B, stream));
@@ -816,6 +811,10 @@ int replay_graph(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool wan
 // sees exactly the arithmetic of the uncompacted schedule (columns are independent), so results are identical.
 int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
     const bool want_post = o.post != nullptr;
+    if (want_post) {
+        int rc = post_ensure(d, root);
+        if (rc) return rc;
+    }
     if (d->schedule == LDPC_SCHEDULE_LAYERED) {
         int rc = run_layered(d, root, B, Bp, want_post, stream);
         if (rc) return rc;
@@ -851,11 +850,7 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
         const int64_t pending = *d->h_total;
         quiet = (pending >= curB) ? quiet + 1 : 0;
         if (pending == 0) {
-            d->stat_early_exits++;
-            if (want_post) {   // decisions of stopped frames are already in place; posteriors are not
-                rc = run_final_pass(d, *ws, curBp, want_post, stream);
-                if (rc) return rc;
-            }
+            d->stat_early_exits++;   // decisions (and posteriors) of stopped frames are already in place
             return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
         }
         if (curBp < d->compact_min_frames || pending * 100 > curBp * d->compact_percent || level >= kMaxLevels) continue;
@@ -880,16 +875,16 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
             continue;
         }
         if (rc) return rc;
+        if (want_post) {
+            rc = post_ensure(d, lv.ws);
+            if (rc) return rc;
+        }
         LAUNCH(K_OTHER, launch_pending_indices(ws->done, curBp, d->d_scan, lv.idx, stream));
         LAUNCH(K_OTHER, launch_compose_map(lv.idx, map, lv.map, pending, stream));
         LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->llrT, curBp, lv.ws.llrT, childBp, lv.idx, pending, g->n, stream));
         LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->v2c, curBp, lv.ws.v2c, childBp, lv.idx, pending, g->E, stream));
         LAUNCH(K_OTHER, launch_reset_state(lv.ws.done, lv.ws.iters, lv.ws.success, lv.ws.unsat, pending, childBp, d->T, stream));
-        // the parent's finished frames: final pass (after the gather: it reuses v2c for the posteriors) and delivery
-        if (want_post) {
-            rc = run_final_pass(d, *ws, curBp, want_post, stream);
-            if (rc) return rc;
-        }
+        // the parent delivers its stopped frames (their decisions / posteriors are in place)
         rc = emit_level(d, *ws, curB, curBp, map, ws->done, o, stream);
         if (rc) return rc;
         d->stat_compactions++;
@@ -1047,7 +1042,6 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
             if (d->q_of_iter[t] < 0 || d->q_of_iter[t] >= d->Q) rc = fail(LDPC_ERR_INVALID, "quantizer_of_iter[%d] out of range", t);
         if (!rc) rc = upload(&d->d_thr, thr);
         if (!rc) rc = upload(&d->d_lut, lut);
-        if (!rc) rc = upload(&d->d_q_of_iter, d->q_of_iter);
     }
     if (rc) {
         ldpc_decoder_destroy(d);
@@ -1099,7 +1093,6 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     cudaFree(d->d_alpha);
     cudaFree(d->d_thr);
     cudaFree(d->d_lut);
-    cudaFree(d->d_q_of_iter);
     delete d;
     return LDPC_OK;
 }

@@ -175,7 +175,7 @@ struct CheckOut4 {
 };
 
 template <typename Real, bool QUANT, int NTH, int DC>
-__device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask,
+__device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0, int64_t f0,
                                                const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
@@ -224,7 +224,7 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
                 *reinterpret_cast<uint32_t*>(&out[k]) = c4.emit(min4, neg4);
             }
 #pragma unroll
-            for (int k = 0; k < DC; ++k) store_masked<OutT, V>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k], dmask);
+            for (int k = 0; k < DC; ++k) st_stream<Pack<OutT, V>>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k]);
             return;
         }
     }
@@ -263,13 +263,13 @@ __device__ __forceinline__ void cn_check_small(const CnLaunch& p, int64_t slot0,
         }
     }
 #pragma unroll
-    for (int k = 0; k < DC; ++k) store_masked<OutT, V>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k], dmask);
+    for (int k = 0; k < DC; ++k) st_stream<Pack<OutT, V>>(row_at(dst, (uint32_t)(slot0 + k), out_stride), out[k]);
 }
 
 // Checks of degree 9..32: stream the inputs once, keeping min1/min2/first-argmin/parity and one sign
 // bit per edge in a 32-bit shift register (funnel shift: one instruction per edge and frame).
 template <typename Real, bool QUANT, int NTH>
-__device__ void cn_check_mask32(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
+__device__ void cn_check_mask32(const CnLaunch& p, int64_t slot0, int dc, int64_t f0,
                                 const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
@@ -318,14 +318,14 @@ __device__ void cn_check_mask32(const CnLaunch& p, int64_t slot0, int dc, int64_
                 out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
             }
         }
-        store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+        st_stream<Pack<OutT, V>>(dst + (slot0 + k) * p.Bp + f0, out);
     }
 }
 
 // Checks of degree > 32: same streaming pass, then the inputs are read again (they were just fetched)
 // for their signs and for the "is the minimum" test.
 template <typename Real, bool QUANT, int NTH>
-__device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask,
+__device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_t f0,
                                 const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
@@ -367,7 +367,7 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
                 out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
             }
         }
-        store_masked<OutT, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+        st_stream<Pack<OutT, V>>(dst + (slot0 + k) * p.Bp + f0, out);
     }
 }
 
@@ -377,8 +377,9 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
 #define LDPC_CN_F64_MINCTAS 3
 #endif
 #define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : LDPC_CN_F64_MINCTAS))
-// FREEZE: stopped frames keep their c2v (forward()'s posterior output); otherwise the stores carry no mask code.
-template <typename Real, bool QUANT, int NTH, bool FREEZE>
+// Messages of stopped frames are never read again (their decisions and posteriors were delivered at the
+// iteration they stopped at), so the stores carry no mask code; warps whose frames have all stopped exit.
+template <typename Real, bool QUANT, int NTH>
 __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     __shared__ float s_thr[kMaxQuantLevels];
@@ -394,13 +395,12 @@ __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const 
     if (f0 >= p.Bp) return;  // whole warps: Bp is a multiple of 32*V
     const uint32_t done_mask = load_done_mask<V>(p.done, f0);
     if (__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u))) return;
-    const uint32_t dmask = FREEZE ? done_mask : 0u;   // otherwise nobody reads the messages of stopped frames
     const WorkItem it = p.items[item_id];
     int64_t slot = it.first_slot;
 #define LDPC_CN_CASE(D)                                                                   \
     case D:                                                                               \
         for (int c = 0; c < it.count; ++c, slot += D)                                     \
-            cn_check_small<Real, QUANT, NTH, D>(p, slot, f0, dmask, qz);                  \
+            cn_check_small<Real, QUANT, NTH, D>(p, slot, f0, qz);                  \
         break;
     switch (it.deg) {
         LDPC_CN_CASE(1)
@@ -414,10 +414,10 @@ __global__ void LDPC_CN_BOUNDS cn_kernel(const CnLaunch p, const int nfb, const 
         default:
             if (it.deg <= 32) {
                 for (int c = 0; c < it.count; ++c, slot += it.deg)
-                    cn_check_mask32<Real, QUANT, NTH>(p, slot, it.deg, f0, dmask, qz);
+                    cn_check_mask32<Real, QUANT, NTH>(p, slot, it.deg, f0, qz);
             } else {
                 for (int c = 0; c < it.count; ++c, slot += it.deg)
-                    cn_check_reread<Real, QUANT, NTH>(p, slot, it.deg, f0, dmask, qz);
+                    cn_check_reread<Real, QUANT, NTH>(p, slot, it.deg, f0, qz);
             }
     }
 #undef LDPC_CN_CASE
@@ -558,7 +558,7 @@ __device__ __forceinline__ void offset_weights(const CnLaunch& p, int64_t slot, 
 
 template <typename Real, bool QUANT, int NTH, typename MaskT, bool OFFSET>
 __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& ring, int64_t slot0, int dc, int64_t f0,
-                                              uint32_t dmask, bool active, const Quantizer<NTH>& qz) {
+                                              bool active, const Quantizer<NTH>& qz) {
     constexpr int V = FramesPerLane<Real>::value;
     using OutT = typename CnOut<Real, QUANT>::type;
     const bool has_beta = p.beta_t != nullptr;
@@ -616,7 +616,7 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
                 out.v[v] = offset_value<Real>(is_min ? st[v].m2 : st[v].m1, beta, p.beta_t != nullptr, alpha,
                                               p.alpha_t != nullptr, st[v].par ^ sb, zero_others);
             }
-            store_masked<Real, V>(orow, out, dmask);
+            st_stream<Pack<Real, V>>(orow, out);
         }
         return;
     }
@@ -651,7 +651,7 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
                         const uint32_t neg4 = spread_byte_signs(S << i);
                         Pack<OutT, V> out;
                         *reinterpret_cast<uint32_t*>(&out) = c4.emit(min4, neg4);
-                        store_masked<OutT, V>(out_row, out, dmask);
+                        st_stream<Pack<OutT, V>>(out_row, out);
                         out_row += p.Bp;
                     }
                 }
@@ -675,11 +675,11 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
                 out.v[v] = cn_emit<Real, QUANT, NTH>(raw, beta, st[v].par ^ sb, qz, p.bc);
             }
         }
-        store_masked<OutT, V>(out_row, out, dmask);
+        st_stream<Pack<OutT, V>>(out_row, out);
     }
 }
 
-template <typename Real, bool QUANT, int NTH, bool FREEZE, bool OFFSET = false>
+template <typename Real, bool QUANT, int NTH, bool OFFSET = false>
 __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ __align__(128) unsigned char wide_smem[];
@@ -703,7 +703,6 @@ __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(con
     if (f0 < p.Bp) done_mask = load_done_mask<V>(p.done, f0);
     const bool active = !__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u));   // warp-uniform
     if (!__syncthreads_or(active ? 1 : 0)) return;   // also publishes the barriers and s_thr
-    const uint32_t dmask = FREEZE ? done_mask : 0u;
     if (QUANT) qz.load(s_thr, p.nth, p.mono != 0);
     const WorkItem it = p.items[item_id];
     RowRing<Real> ring;
@@ -724,10 +723,10 @@ __global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(con
     int64_t slot = it.first_slot;
     if (it.deg <= 32) {
         for (int c = 0; c < it.count; ++c, slot += it.deg)
-            cn_wide_check<Real, QUANT, NTH, uint32_t, OFFSET>(p, ring, slot, it.deg, f0, dmask, active, qz);
+            cn_wide_check<Real, QUANT, NTH, uint32_t, OFFSET>(p, ring, slot, it.deg, f0, active, qz);
     } else {
         for (int c = 0; c < it.count; ++c, slot += it.deg)
-            cn_wide_check<Real, QUANT, NTH, uint64_t, OFFSET>(p, ring, slot, it.deg, f0, dmask, active, qz);
+            cn_wide_check<Real, QUANT, NTH, uint64_t, OFFSET>(p, ring, slot, it.deg, f0, active, qz);
     }
 }
 
@@ -757,7 +756,7 @@ __device__ __forceinline__ void offset_weights(const CnLaunch& p, int64_t slot, 
 }
 
 template <typename Real, int DC>
-__device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0, int64_t f0, uint32_t dmask) {
+__device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0, int64_t f0) {
     constexpr int V = FramesPerLane<Real>::value;
     const Real* __restrict__ src = static_cast<const Real*>(p.src);
     Real* __restrict__ dst = static_cast<Real*>(p.dst);
@@ -788,11 +787,11 @@ __device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0
         }
     }
 #pragma unroll
-    for (int k = 0; k < DC; ++k) store_masked<Real, V>(dst + (slot0 + k) * p.Bp + f0, out[k], dmask);
+    for (int k = 0; k < DC; ++k) st_stream<Pack<Real, V>>(dst + (slot0 + k) * p.Bp + f0, out[k]);
 }
 
 template <typename Real>
-__device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t f0, uint32_t dmask) {
+__device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t f0) {
     constexpr int V = FramesPerLane<Real>::value;
     const Real* __restrict__ src = static_cast<const Real*>(p.src);
     Real* __restrict__ dst = static_cast<Real*>(p.dst);
@@ -820,11 +819,11 @@ __device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t
             out.v[v] = offset_value<Real>(is_min ? st[v].m2 : st[v].m1, beta, p.beta_t != nullptr, alpha,
                                           p.alpha_t != nullptr, st[v].par ^ Arith<Real>::hi(x.v[v]), zero_others);
         }
-        store_masked<Real, V>(dst + (slot0 + k) * p.Bp + f0, out, dmask);
+        st_stream<Pack<Real, V>>(dst + (slot0 + k) * p.Bp + f0, out);
     }
 }
 
-template <typename Real, bool FREEZE>
+template <typename Real>
 __global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     const int fb = blockIdx.x % nfb;
@@ -833,13 +832,12 @@ __global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, c
     if (f0 >= p.Bp) return;
     const uint32_t done_mask = load_done_mask<V>(p.done, f0);
     if (__all_sync(0xffffffffu, done_mask == ((1u << V) - 1u))) return;
-    const uint32_t dmask = FREEZE ? done_mask : 0u;
     const WorkItem it = p.items[item_id];
     int64_t slot = it.first_slot;
 #define LDPC_CNO_CASE(D)                                                \
     case D:                                                             \
         for (int c = 0; c < it.count; ++c, slot += D)                   \
-            cn_offset_small<Real, D>(p, slot, f0, dmask);               \
+            cn_offset_small<Real, D>(p, slot, f0);               \
         break;
     switch (it.deg) {
         LDPC_CNO_CASE(1)
@@ -851,7 +849,7 @@ __global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, c
         LDPC_CNO_CASE(7)
         LDPC_CNO_CASE(8)
         default:
-            for (int c = 0; c < it.count; ++c, slot += it.deg) cn_offset_wide<Real>(p, slot, it.deg, f0, dmask);
+            for (int c = 0; c < it.count; ++c, slot += it.deg) cn_offset_wide<Real>(p, slot, it.deg, f0);
     }
 #undef LDPC_CNO_CASE
 }
@@ -904,42 +902,37 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-template <typename Real, bool QUANT, int NTH, bool FREEZE>
+template <typename Real, bool QUANT, int NTH>
 cudaError_t launch_cn_range(const CnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
     if (item1 <= item0) return cudaSuccess;
     constexpr int V = FramesPerLane<Real>::value;
     if (wide) {
         // per device and cheap, so simply repeated on every launch
-        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, QUANT, NTH, FREEZE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, QUANT, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kWideSmem);
         if (e != cudaSuccess) return e;
         const int64_t nfb = (p.Bp + (int64_t)kWideThreads * V - 1) / ((int64_t)kWideThreads * V);
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_wide_kernel<Real, QUANT, NTH, FREEZE><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
+        cn_wide_kernel<Real, QUANT, NTH><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
     } else {
         const int threads = threads_for(p.Bp, V);
         const int64_t nfb = (p.Bp / V + threads - 1) / threads;
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_kernel<Real, QUANT, NTH, FREEZE><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
+        cn_kernel<Real, QUANT, NTH><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
     }
     return cudaGetLastError();
 }
 
-template <typename Real, bool QUANT, int NTH, bool FREEZE>
-cudaError_t launch_cn_frz(const CnLaunch& p, cudaStream_t stream) {
-    // items are sorted by degree: [0, wide0) degree <= 8, [wide0, wide1) degree 9..64 (row ring), rest > 64
-    const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
-    cudaError_t e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, 0, wide0, false, stream);
-    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, wide0, wide1, true, stream);
-    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH, FREEZE>(p, wide1, p.n_items, false, stream);
-    return e;
-}
-
 template <typename Real, bool QUANT, int NTH>
 cudaError_t launch_cn_all(const CnLaunch& p, cudaStream_t stream) {
-    return p.freeze ? launch_cn_frz<Real, QUANT, NTH, true>(p, stream) : launch_cn_frz<Real, QUANT, NTH, false>(p, stream);
+    // items are sorted by degree: [0, wide0) degree <= 8, [wide0, wide1) degree 9..64 (row ring), rest > 64
+    const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
+    cudaError_t e = launch_cn_range<Real, QUANT, NTH>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_cn_range<Real, QUANT, NTH>(p, wide1, p.n_items, false, stream);
+    return e;
 }
 
 }  // namespace
@@ -960,34 +953,34 @@ cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream) {
 
 namespace {
 
-template <typename Real, bool FREEZE>
+template <typename Real>
 cudaError_t launch_cn_offset_range(const CnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
     if (item1 <= item0) return cudaSuccess;
     constexpr int V = FramesPerLane<Real>::value;
     if (wide) {
-        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, false, 0, FREEZE, true>,
+        cudaError_t e = cudaFuncSetAttribute(cn_wide_kernel<Real, false, 0, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
         if (e != cudaSuccess) return e;
         const int64_t nfb = (p.Bp + (int64_t)kWideThreads * V - 1) / ((int64_t)kWideThreads * V);
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_wide_kernel<Real, false, 0, FREEZE, true><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
+        cn_wide_kernel<Real, false, 0, true><<<(unsigned)grid, kWideThreads, kWideSmem, stream>>>(p, (int)nfb, item0);
     } else {
         const int threads = threads_for(p.Bp, V);
         const int64_t nfb = (p.Bp / V + threads - 1) / threads;
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        cn_offset_kernel<Real, FREEZE><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
+        cn_offset_kernel<Real><<<(unsigned)grid, threads, 0, stream>>>(p, (int)nfb, item0);
     }
     return cudaGetLastError();
 }
 
-template <typename Real, bool FREEZE>
+template <typename Real>
 cudaError_t launch_cn_offset_all(const CnLaunch& p, cudaStream_t stream) {
     const int wide0 = p.wide_ring ? p.items_wide_begin : p.n_items, wide1 = p.wide_ring ? p.items_wide_end : p.n_items;
-    cudaError_t e = launch_cn_offset_range<Real, FREEZE>(p, 0, wide0, false, stream);
-    if (e == cudaSuccess) e = launch_cn_offset_range<Real, FREEZE>(p, wide0, wide1, true, stream);
-    if (e == cudaSuccess) e = launch_cn_offset_range<Real, FREEZE>(p, wide1, p.n_items, false, stream);
+    cudaError_t e = launch_cn_offset_range<Real>(p, 0, wide0, false, stream);
+    if (e == cudaSuccess) e = launch_cn_offset_range<Real>(p, wide0, wide1, true, stream);
+    if (e == cudaSuccess) e = launch_cn_offset_range<Real>(p, wide1, p.n_items, false, stream);
     return e;
 }
 
@@ -995,8 +988,7 @@ cudaError_t launch_cn_offset_all(const CnLaunch& p, cudaStream_t stream) {
 
 cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
     if (p.n_items == 0) return cudaSuccess;
-    if (dtype == 0) return p.freeze ? launch_cn_offset_all<float, true>(p, stream) : launch_cn_offset_all<float, false>(p, stream);
-    return p.freeze ? launch_cn_offset_all<double, true>(p, stream) : launch_cn_offset_all<double, false>(p, stream);
+    return dtype == 0 ? launch_cn_offset_all<float>(p, stream) : launch_cn_offset_all<double>(p, stream);
 }
 
 cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,

@@ -39,7 +39,6 @@ struct CnLaunch {
     int items_wide_begin;       // items [begin, end) hold checks of degree 9..64 (sorted by degree)
     int items_wide_end;
     int wide_ring;              // 1: those items run in the bulk-async row-ring kernel
-    int freeze;                 // 1: stopped frames keep their c2v (their posterior is still to be delivered)
     int64_t Bp;
 };
 
@@ -47,7 +46,7 @@ struct VnLaunch {
     const void* c2v;            // Real [E][Bp] or uint8 codes
     void* v2c;                  // Real [E][Bp] (ignored by the final pass)
     const void* llrT;           // Real [n][Bp]
-    void* postT;                // final pass: Real [n][Bp] or nullptr
+    void* postT;                // Real [n][Bp] or nullptr: posterior rows, refreshed by running frames every iteration
     const int32_t* vslots;      // slot lists, ascending check index inside a variable
     const int32_t* vpos_var;    // variable id at each degree-sorted position
     const int32_t* aidx;        // per-position column of alpha, or nullptr (column 0)
@@ -56,8 +55,6 @@ struct VnLaunch {
     int bc;
     int n_quant;
     int q_now;                  // quantiser of this iteration (non-final)
-    const int32_t* q_of_iter;   // final pass: quantiser by iteration, selected through iters[]
-    const int32_t* iters;       // [Bp] iterations executed per frame (final pass)
     uint32_t* hardw;            // [n][Wn] packed hard decisions
     int64_t Wn;                 // Bp / 32
     const uint8_t* done;
@@ -65,7 +62,6 @@ struct VnLaunch {
     int n_items;
     int64_t Bp;
     int final_pass;
-    int freeze;                 // 1: stopped frames keep their v2c / c2v
     int items_wide_begin;       // items [begin, end) hold variables of degree 9..64 (sorted by degree)
     int items_wide_end;
     int wide_max_deg;           // largest degree among them (rows of the shared-memory stage)

@@ -45,9 +45,9 @@ __device__ __forceinline__ Real c2v_value(const void* __restrict__ c2v, int64_t 
 // U consecutive variables of degree DV at once: all loads of the group are issued before the first use,
 // which is what keeps enough bytes in flight for the low-degree classes (a degree-2 variable on its own
 // has only 3 loads to overlap; RCQ code rows are just 128 bytes per warp).
-template <typename Real, bool QUANT, bool FINAL, int DV, int U>
+template <typename Real, bool QUANT, bool FINAL, bool POST, int DV, int U>
 __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, int64_t lbase, int64_t f0,
-                                              uint32_t dmask, uint32_t smask, uint32_t keepw, int64_t wbase,
+                                              uint32_t dmask, uint32_t keepw, int64_t wbase,
                                               const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
     constexpr int D1 = DV > 0 ? DV : 1;
@@ -109,18 +109,19 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
         }
         if constexpr (!FINAL) {
 #pragma unroll
-            for (int d = 0; d < DV; ++d) store_masked<Real, V>(row_at(v2c, slot[u][d], real_stride), out[d], smask);
-        } else {
-            if (p.postT) st_stream<Pack<Real, V>>(row_at(static_cast<Real*>(p.postT) + f0, j[u], real_stride), post);
+            for (int d = 0; d < DV; ++d) st_stream<Pack<Real, V>>(row_at(v2c, slot[u][d], real_stride), out[d]);
         }
+        // forward(): the posterior of a frame is the one of the iteration it stops at -- running frames refresh
+        // their entry every iteration, stopped frames keep theirs
+        if constexpr (POST) store_masked<Real, V>(row_at(static_cast<Real*>(p.postT) + f0, j[u], real_stride), post, dmask);
         write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit, keepw);
     }
 }
 
 // All variables of one work item, in groups of U (remainder one by one).
-template <typename Real, bool QUANT, bool FINAL, int DV>
+template <typename Real, bool QUANT, bool FINAL, bool POST, int DV>
 __device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem& it, int64_t f0, uint32_t dmask,
-                                              uint32_t smask, uint32_t keepw, int64_t wbase, const float* s_lut,
+                                              uint32_t keepw, int64_t wbase, const float* s_lut,
                                               const int (&lutbase)[FramesPerLane<Real>::value]) {
     // byte-wide RCQ code rows need more rows in flight than 16-byte float rows
     constexpr int U = QUANT ? ((DV <= 2) ? LDPC_VN_UQ_LO : ((DV <= 4) ? LDPC_VN_UQ_MID : LDPC_VN_UQ_HI))
@@ -130,15 +131,15 @@ __device__ __forceinline__ void vn_item_small(const VnLaunch& p, const WorkItem&
     int c = 0;
     if constexpr (U > 1) {
         for (; c + U <= it.count; c += U, lbase += U * DV, vpos += U)
-            vn_node_small<Real, QUANT, FINAL, DV, U>(p, vpos, lbase, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
+            vn_node_small<Real, QUANT, FINAL, POST, DV, U>(p, vpos, lbase, f0, dmask, keepw, wbase, s_lut, lutbase);
     }
     for (; c < it.count; ++c, lbase += DV, ++vpos)
-        vn_node_small<Real, QUANT, FINAL, DV, 1>(p, vpos, lbase, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
+        vn_node_small<Real, QUANT, FINAL, POST, DV, 1>(p, vpos, lbase, f0, dmask, keepw, wbase, s_lut, lutbase);
 }
 
-template <typename Real, bool QUANT, bool FINAL>
+template <typename Real, bool QUANT, bool FINAL, bool POST>
 __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, int dv, int64_t f0, uint32_t dmask,
-                                uint32_t smask, uint32_t keepw, int64_t wbase, const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
+                                uint32_t keepw, int64_t wbase, const float* s_lut, const int (&lutbase)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c);
     const int64_t j = __ldg(p.vpos_var + vpos);
@@ -178,16 +179,17 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
                 out.v[v] = Arith<Real>::add(L.v[v], s);
             }
             int64_t sd = __ldg(p.vslots + lbase + d);
-            store_masked<Real, V>(v2c + sd * p.Bp + f0, out, smask);
+            st_stream<Pack<Real, V>>(v2c + sd * p.Bp + f0, out);
         }
-    } else {
-        if (p.postT) *reinterpret_cast<Pack<Real, V>*>(static_cast<Real*>(p.postT) + j * p.Bp + f0) = post;
     }
+    if constexpr (POST) store_masked<Real, V>(static_cast<Real*>(p.postT) + j * p.Bp + f0, post, dmask);
     write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
 }
 
-// FREEZE: stopped frames keep their v2c (forward()'s posterior output); otherwise their stores are plain.
-template <typename Real, bool QUANT, bool FINAL, bool FREEZE>
+// FINAL: iteration T-1 (the dead v2c update is not written).  POST: forward()'s posterior output -- running
+// frames write their posterior row entries every iteration, so a stopped frame's entry is the posterior of the
+// iteration it stopped at; messages and decisions of stopped frames are never touched again either way.
+template <typename Real, bool QUANT, bool FINAL, bool POST>
 __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb,
                                                                                                    const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
@@ -201,29 +203,12 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
     const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
-    // Stopped frames keep their messages and their packed decisions in place; only forward()'s posterior
-    // output makes the final pass recompute them (posterior of the iteration a frame stopped at, from its
-    // frozen c2v).
-    uint32_t dmask = 0;
-    if (!FINAL || p.postT == nullptr) {
-        dmask = load_done_mask<V>(p.done, f0);
-        if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
-    }
+    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
     const uint32_t keepw = keep_word<V>(dmask);
-    const uint32_t smask = FREEZE ? dmask : 0u;
     int lutbase[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        lutbase[v] = 0;
-        if (QUANT) {
-            int q = p.q_now;
-            if (FINAL) {
-                int itv = __ldg(p.iters + f0 + v);
-                q = __ldg(p.q_of_iter + (itv > 0 ? itv - 1 : 0));
-            }
-            lutbase[v] = q << p.bc;
-        }
-    }
+    for (int v = 0; v < V; ++v) lutbase[v] = QUANT ? (p.q_now << p.bc) : 0;
     const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
     const int64_t wbase = (warp_f0 / (32 * V)) * V;
     const WorkItem it = p.items[item_id];
@@ -231,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
     int32_t vpos = it.first_node;
 #define LDPC_VN_CASE(D)                                                                               \
     case D:                                                                                           \
-        vn_item_small<Real, QUANT, FINAL, D>(p, it, f0, dmask, smask, keepw, wbase, s_lut, lutbase);  \
+        vn_item_small<Real, QUANT, FINAL, POST, D>(p, it, f0, dmask, keepw, wbase, s_lut, lutbase);   \
         break;
     switch (it.deg) {
         LDPC_VN_CASE(0)
@@ -245,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
         LDPC_VN_CASE(8)
         default:
             for (int c = 0; c < it.count; ++c, lbase += it.deg, ++vpos)
-                vn_node_generic<Real, QUANT, FINAL>(p, vpos, lbase, it.deg, f0, dmask, smask, keepw, wbase, s_lut, lutbase);
+                vn_node_generic<Real, QUANT, FINAL, POST>(p, vpos, lbase, it.deg, f0, dmask, keepw, wbase, s_lut, lutbase);
     }
 #undef LDPC_VN_CASE
 }
@@ -274,7 +259,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <typename Real, bool FINAL, int DVS>
 __device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real, FramesPerLane<Real>::value>* __restrict__ s_val,
                                              int dv, const Pack<Real, FramesPerLane<Real>::value>& L, Real alpha, bool has_alpha,
-                                             int64_t lbase, Real* __restrict__ v2c, uint32_t real_stride, uint32_t smask,
+                                             int64_t lbase, Real* __restrict__ v2c, uint32_t real_stride,
                                              uint32_t dmask, Pack<Real, FramesPerLane<Real>::value>& post,
                                              bool (&bit)[FramesPerLane<Real>::value]) {
     constexpr int V = FramesPerLane<Real>::value;
@@ -298,7 +283,7 @@ __device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real,
                 out.v[v] = Arith<Real>::add(L.v[v], sv);
             }
             const uint32_t sd = (uint32_t)__ldg(p.vslots + lbase + d);
-            store_masked<Real, V>(row_at(v2c, sd, real_stride), out, smask);
+            st_stream<PackR>(row_at(v2c, sd, real_stride), out);
         };
         if constexpr (DVS > 0) {
 #pragma unroll
@@ -315,7 +300,7 @@ __device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real,
     }
 }
 
-template <typename Real, bool QUANT, bool FINAL, bool FREEZE>
+template <typename Real, bool QUANT, bool FINAL, bool POST>
 __global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch p, const int nfb, const int item0,
                                                                   const int stage_rows) {
     constexpr int V = FramesPerLane<Real>::value;
@@ -336,26 +321,12 @@ __global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch 
     const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * kVnWideThreads + threadIdx.x) * V;
     if (f0 >= p.Bp) return;   // whole warps
-    uint32_t dmask = 0;
-    if (!FINAL || p.postT == nullptr) {
-        dmask = load_done_mask<V>(p.done, f0);
-        if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
-    }
+    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
     const uint32_t keepw = keep_word<V>(dmask);
-    const uint32_t smask = FREEZE ? dmask : 0u;
     int lutbase[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        lutbase[v] = 0;
-        if (QUANT) {
-            int q = p.q_now;
-            if (FINAL) {
-                const int itv = __ldg(p.iters + f0 + v);
-                q = __ldg(p.q_of_iter + (itv > 0 ? itv - 1 : 0));
-            }
-            lutbase[v] = q << p.bc;
-        }
-    }
+    for (int v = 0; v < V; ++v) lutbase[v] = QUANT ? (p.q_now << p.bc) : 0;
     const uint32_t lutmask = (1u << p.bc) - 1u;
     const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
     const int64_t wbase = (warp_f0 / (32 * V)) * V;
@@ -393,7 +364,7 @@ __global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch 
         bool handled = false;
 #define LDPC_VNW_CASE(D)                                                                                              \
     case D:                                                                                                           \
-        vn_wide_sums<Real, FINAL, D>(p, s_val, D, L, alpha, has_alpha, lbase, v2c, real_stride, smask, dmask, post, bit); \
+        vn_wide_sums<Real, FINAL, D>(p, s_val, D, L, alpha, has_alpha, lbase, v2c, real_stride, dmask, post, bit); \
         handled = true;                                                                                               \
         break;
         switch (dv) {
@@ -408,10 +379,8 @@ __global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch 
             default: break;
         }
 #undef LDPC_VNW_CASE
-        if (!handled) vn_wide_sums<Real, FINAL, 0>(p, s_val, dv, L, alpha, has_alpha, lbase, v2c, real_stride, smask, dmask, post, bit);
-        if constexpr (FINAL) {
-            if (p.postT) st_stream<PackR>(row_at(static_cast<Real*>(p.postT) + f0, j, real_stride), post);
-        }
+        if (!handled) vn_wide_sums<Real, FINAL, 0>(p, s_val, dv, L, alpha, has_alpha, lbase, v2c, real_stride, dmask, post, bit);
+        if constexpr (POST) store_masked<Real, V>(row_at(static_cast<Real*>(p.postT) + f0, j, real_stride), post, dmask);
         write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
     }
 }
@@ -445,16 +414,15 @@ cudaError_t launch_vn_range(const VnLaunch& p, int item0, int item1, bool wide, 
         const int64_t nfb = (p.Bp + (int64_t)kVnWideThreads * V - 1) / ((int64_t)kVnWideThreads * V);
         const int64_t grid = nfb * (item1 - item0);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-#define LDPC_VNW(FINAL, FREEZE)                                                                                        \
+#define LDPC_VNW(FINAL, POST)                                                                                          \
     do {                                                                                                               \
-        cudaError_t e_ = cudaFuncSetAttribute(vn_wide_kernel<Real, QUANT, FINAL, FREEZE>,                              \
+        cudaError_t e_ = cudaFuncSetAttribute(vn_wide_kernel<Real, QUANT, FINAL, POST>,                                \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
         if (e_ != cudaSuccess) return e_;                                                                              \
-        vn_wide_kernel<Real, QUANT, FINAL, FREEZE><<<(unsigned)grid, kVnWideThreads, smem, stream>>>(p, (int)nfb, item0, rows); \
+        vn_wide_kernel<Real, QUANT, FINAL, POST><<<(unsigned)grid, kVnWideThreads, smem, stream>>>(p, (int)nfb, item0, rows);   \
     } while (0)
-        if (p.final_pass) LDPC_VNW(true, false);
-        else if (p.freeze) LDPC_VNW(false, true);
-        else LDPC_VNW(false, false);
+        if (p.final_pass) { if (p.postT) LDPC_VNW(true, true); else LDPC_VNW(true, false); }
+        else { if (p.postT) LDPC_VNW(false, true); else LDPC_VNW(false, false); }
 #undef LDPC_VNW
     } else {
         const int threads = threads_for(p.Bp, V);
@@ -464,9 +432,13 @@ cudaError_t launch_vn_range(const VnLaunch& p, int item0, int item1, bool wide, 
         const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
         const unsigned g = (unsigned)grid;
         const int nf = (int)nfb;
-        if (p.final_pass) vn_kernel<Real, QUANT, true, false><<<g, threads, smem, stream>>>(p, nf, item0);
-        else if (p.freeze) vn_kernel<Real, QUANT, false, true><<<g, threads, smem, stream>>>(p, nf, item0);
-        else vn_kernel<Real, QUANT, false, false><<<g, threads, smem, stream>>>(p, nf, item0);
+        if (p.final_pass) {
+            if (p.postT) vn_kernel<Real, QUANT, true, true><<<g, threads, smem, stream>>>(p, nf, item0);
+            else vn_kernel<Real, QUANT, true, false><<<g, threads, smem, stream>>>(p, nf, item0);
+        } else {
+            if (p.postT) vn_kernel<Real, QUANT, false, true><<<g, threads, smem, stream>>>(p, nf, item0);
+            else vn_kernel<Real, QUANT, false, false><<<g, threads, smem, stream>>>(p, nf, item0);
+        }
     }
     return cudaGetLastError();
 }
