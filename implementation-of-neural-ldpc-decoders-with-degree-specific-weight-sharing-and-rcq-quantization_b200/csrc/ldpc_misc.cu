@@ -102,22 +102,44 @@ __global__ void __launch_bounds__(256) pack_kernel(const Real* __restrict__ llr,
     }
 }
 
-template <typename Real>
-__global__ void unpack_post_kernel(const Real* __restrict__ postT, Real* __restrict__ post, int64_t B, int64_t Bp,
-                                   int32_t n, const int32_t* __restrict__ map) {
-    __shared__ Real tile[32][33];
-    const int64_t f_base = (int64_t)blockIdx.x * 32;
-    const int32_t j_base = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int32_t j = j_base + r;
-        int64_t f = f_base + threadIdx.x;
-        tile[r][threadIdx.x] = (j < n && f < Bp) ? postT[(int64_t)j * Bp + f] : Real(0);
+// postT [n][Bp] -> post [B][n] (row map[f] when a frame map is given): the mirror image of pack_kernel,
+// 64 variables x 64 frames per CTA, two elements per lane on both sides.
+template <typename Real, bool PAIR>
+__global__ void __launch_bounds__(256) unpack_post_kernel(const Real* __restrict__ postT, Real* __restrict__ post, int64_t B,
+                                                           int64_t Bp, int32_t n, const int32_t* __restrict__ map) {
+    __shared__ Real tile[64][65];   // [frame][variable]
+    const int64_t f_base = (int64_t)blockIdx.x * 64;
+    const int32_t j_base = blockIdx.y * 64;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    for (int c = wy; c < 64; c += 8) {
+        const int32_t j = j_base + c;
+        const int64_t f = f_base + 2 * lane;   // Bp is a multiple of 128
+        Real a = Real(0), b = Real(0);
+        if (j < n && f < Bp) {
+            const Pack<Real, 2> v = *reinterpret_cast<const Pack<Real, 2>*>(postT + (int64_t)j * Bp + f);
+            a = v.v[0];
+            b = v.v[1];
+        }
+        tile[2 * lane][c] = a;
+        tile[2 * lane + 1][c] = b;
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        int64_t f = f_base + r;
-        int32_t j = j_base + threadIdx.x;
-        if (f < B && j < n) post[(map ? (int64_t)map[f] : f) * n + j] = tile[threadIdx.x][r];
+    for (int r = wy; r < 64; r += 8) {
+        const int64_t f = f_base + r;
+        if (f >= B) continue;
+        const int32_t j = j_base + 2 * lane;
+        Real* row = post + (map ? (int64_t)map[f] : f) * n + j;
+        if (PAIR) {
+            if (j < n) {
+                Pack<Real, 2> v;
+                v.v[0] = tile[r][2 * lane];
+                v.v[1] = tile[r][2 * lane + 1];
+                *reinterpret_cast<Pack<Real, 2>*>(row) = v;
+            }
+        } else {
+            if (j < n) row[0] = tile[r][2 * lane];
+            if (j + 1 < n) row[1] = tile[r][2 * lane + 1];
+        }
     }
 }
 
@@ -521,10 +543,15 @@ cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t
 
 cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp, int32_t n,
                                const int32_t* map, cudaStream_t stream) {
-    dim3 block(32, 8);
-    dim3 grid((unsigned)((B + 31) / 32), (unsigned)((n + 31) / 32));
-    if (dtype == 0) unpack_post_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n, map);
-    else unpack_post_kernel<double><<<grid, block, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n, map);
+    dim3 grid((unsigned)((B + 63) / 64), (unsigned)((n + 63) / 64));
+    const bool pair = (n % 2 == 0) && (reinterpret_cast<uintptr_t>(post) % (dtype == 0 ? 8 : 16) == 0);
+    if (dtype == 0) {
+        if (pair) unpack_post_kernel<float, true><<<grid, 256, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n, map);
+        else unpack_post_kernel<float, false><<<grid, 256, 0, stream>>>(static_cast<const float*>(postT), static_cast<float*>(post), B, Bp, n, map);
+    } else {
+        if (pair) unpack_post_kernel<double, true><<<grid, 256, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n, map);
+        else unpack_post_kernel<double, false><<<grid, 256, 0, stream>>>(static_cast<const double*>(postT), static_cast<double*>(post), B, Bp, n, map);
+    }
     return cudaGetLastError();
 }
 
