@@ -300,8 +300,16 @@ __device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real,
     }
 }
 
+// resident CTAs per SM the staged kernel is compiled for (RCQ 6 -> 80 registers: 0.71 -> 0.85 of the
+// roofline on a dv-12 code; float 5 -> 96 registers: 0.91 -> 0.97)
+#ifndef LDPC_VNW_Q_MINCTAS
+#define LDPC_VNW_Q_MINCTAS 6
+#endif
+#ifndef LDPC_VNW_F_MINCTAS
+#define LDPC_VNW_F_MINCTAS 5
+#endif
 template <typename Real, bool QUANT, bool FINAL, bool POST>
-__global__ void __launch_bounds__(kVnWideThreads) vn_wide_kernel(const VnLaunch p, const int nfb, const int item0,
+__global__ void __launch_bounds__(kVnWideThreads, QUANT ? LDPC_VNW_Q_MINCTAS : LDPC_VNW_F_MINCTAS) vn_wide_kernel(const VnLaunch p, const int nfb, const int item0,
                                                                   const int stage_rows) {
     constexpr int V = FramesPerLane<Real>::value;
     using InT = typename CnOut<Real, QUANT>::type;
