@@ -376,7 +376,10 @@ __device__ void cn_check_reread(const CnLaunch& p, int64_t slot0, int dc, int64_
 #ifndef LDPC_CN_F64_MINCTAS
 #define LDPC_CN_F64_MINCTAS 3
 #endif
-#define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? 4 : (sizeof(Real) == 4 ? 3 : LDPC_CN_F64_MINCTAS))
+#ifndef LDPC_CN_Q_MINCTAS
+#define LDPC_CN_Q_MINCTAS 4
+#endif
+#define LDPC_CN_BOUNDS __launch_bounds__(kThreads, QUANT ? LDPC_CN_Q_MINCTAS : (sizeof(Real) == 4 ? 3 : LDPC_CN_F64_MINCTAS))
 // Messages of stopped frames are never read again (their decisions and posteriors were delivered at the
 // iteration they stopped at), so the stores carry no mask code; warps whose frames have all stopped exit.
 template <typename Real, bool QUANT, int NTH>
@@ -441,6 +444,9 @@ constexpr int kWideThreads = 128;
 #endif
 #ifndef LDPC_WIDE_SLABS
 #define LDPC_WIDE_SLABS 4
+#endif
+#ifndef LDPC_WIDE_Q_MINCTAS
+#define LDPC_WIDE_Q_MINCTAS 6
 #endif
 #ifndef LDPC_WIDE_MINCTAS
 #define LDPC_WIDE_MINCTAS 6
@@ -680,7 +686,7 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
 }
 
 template <typename Real, bool QUANT, int NTH, bool OFFSET = false>
-__global__ void __launch_bounds__(kWideThreads, kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
+__global__ void __launch_bounds__(kWideThreads, QUANT ? LDPC_WIDE_Q_MINCTAS : kWideMinCtas) cn_wide_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ __align__(128) unsigned char wide_smem[];
     __shared__ __align__(8) uint64_t bars[kWideSlabs];
