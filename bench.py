@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU per step")
     ap.add_argument("--code", default="dvbs2", choices=["dvbs2", "qc", "dv12"])
-    ap.add_argument("--decoder", default="n2d2", choices=["n2d2", "n2d1", "nnms", "rcq", "wrcq1", "basic"])
+    ap.add_argument("--decoder", default="n2d2", choices=["n2d2", "n2d1", "nnms", "oms2", "rcq", "wrcq1", "basic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mc", action="store_true", help="skip the early-stop Monte-Carlo leg (T=50, frames converge)")
@@ -74,7 +74,7 @@ def make_code(L, name):
 def workload_name(args):
     shape = {"dvbs2": "(16200,7200)-shaped E=48599", "qc": "(9472,8192)-shaped QC E=37888",
              "dv12": "(16200,6480) IRA dv 12/3/2 E=53459"}[args.code]
-    dec = {"n2d2": "Neural2DMinSumDecoder type 2", "n2d1": "Neural2DMinSumDecoder type 1", "nnms": "NeuralMinSumDecoder (per-edge weights)", "rcq": "RCQMinSumDecoder bc=3", "wrcq1": "WeightedRCQ type 1 bc=3",
+    dec = {"n2d2": "Neural2DMinSumDecoder type 2", "n2d1": "Neural2DMinSumDecoder type 1", "nnms": "NeuralMinSumDecoder (per-edge weights)", "oms2": "Neural2DOffsetMinSumDecoder type 2", "rcq": "RCQMinSumDecoder bc=3", "wrcq1": "WeightedRCQ type 1 bc=3",
            "basic": "BasicMinSumDecoder f64 factor 0.7"}[args.decoder]
     return f"{dec}, {T_ITERS} iters, {shape}, AWGN {SNR_DB} dB reference sign convention"
 
@@ -97,6 +97,11 @@ def build_decoder(L, code, kind):
         dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=1, max_iterations=T_ITERS)
         with torch.no_grad():
             dec._beta_table.copy_(torch.from_numpy(b)[:, None].expand_as(dec._beta_table))
+    elif kind == "oms2":
+        dec = L.Neural2DOffsetMinSumDecoder(code, weight_sharing_type=2, max_iterations=T_ITERS)
+        with torch.no_grad():
+            dec._beta_table.fill_(0.15)
+            dec._alpha_table.fill_(0.02)
     elif kind == "nnms":
         dec = L.NeuralMinSumDecoder(code, max_iterations=T_ITERS)
         with torch.no_grad():
@@ -134,6 +139,9 @@ def oracle_setup(L, code, kind):
         kw.update(mode=MODE_NMS, beta=np.tile(b[:, None], (1, g.E)), alpha=np.tile(a[:, None], (1, g.n)))
     elif kind in ("n2d1", "nnms"):
         kw.update(mode=MODE_NMS, beta=np.tile(b[:, None], (1, g.E)))
+    elif kind == "oms2":
+        from oracle.restatement import MODE_OFFSET
+        kw.update(mode=MODE_OFFSET, beta=np.full((T_ITERS, g.E), np.float32(0.15)), alpha=np.full((T_ITERS, g.n), np.float32(0.02)))
     elif kind == "rcq":
         kw.update(mode=MODE_RCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T_ITERS, 3))
     elif kind == "wrcq1":

@@ -770,12 +770,16 @@ __device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0
     Real beta[DC], alpha[DC];
     Real beta_check = Real(0);
     if (p.beta_t && !p.beta_per_edge) beta_check = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
+    const uint32_t stride = (uint32_t)p.Bp * (uint32_t)sizeof(Real);
+    src += f0;
+    dst += f0;
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
-        int64_t row = p.row_map ? (int64_t)__ldg(p.row_map + slot0 + k) : slot0 + k;
-        x[k] = ld_stream<Pack<Real, V>>(src + row * p.Bp + f0);
-        offset_weights<Real>(p, slot0 + k, beta_check, beta[k], alpha[k]);
+        const uint32_t row = p.row_map ? (uint32_t)__ldg(p.row_map + slot0 + k) : (uint32_t)(slot0 + k);
+        x[k] = ld_stream<Pack<Real, V>>(row_at(src, row, stride));
     }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) offset_weights<Real>(p, slot0 + k, beta_check, beta[k], alpha[k]);
     Pack<Real, V> out[DC];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -793,7 +797,7 @@ __device__ __forceinline__ void cn_offset_small(const CnLaunch& p, int64_t slot0
         }
     }
 #pragma unroll
-    for (int k = 0; k < DC; ++k) st_stream<Pack<Real, V>>(dst + (slot0 + k) * p.Bp + f0, out[k]);
+    for (int k = 0; k < DC; ++k) st_stream<Pack<Real, V>>(row_at(dst, (uint32_t)(slot0 + k), stride), out[k]);
 }
 
 template <typename Real>
@@ -830,7 +834,7 @@ __device__ void cn_offset_wide(const CnLaunch& p, int64_t slot0, int dc, int64_t
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(kThreads) cn_offset_kernel(const CnLaunch p, const int nfb, const int item0) {
+__global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? 3 : 2) cn_offset_kernel(const CnLaunch p, const int nfb, const int item0) {
     constexpr int V = FramesPerLane<Real>::value;
     const int fb = blockIdx.x % nfb;
     const int item_id = item0 + blockIdx.x / nfb;
