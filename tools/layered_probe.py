@@ -1,14 +1,14 @@
+"""Layered RCQ schedule: throughput against batch size (one thread per frame: latency-bound per frame)."""
 import sys, time, torch, numpy as np
 sys.path.insert(0, ".")
 import ldpc_b200 as L
 code = L.codes.dvbs2_shaped(max_iterations=10)
 qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-for layered in (False, True):
+for layered, B in ((False, 32768), (True, 32768), (True, 131072), (True, 262144)):
     dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=10, layered=layered)
-    B = 32768
     llr = L.awgn_llr(code.n, B, 2.0, seed=1, llr_sign=-1)
     for _ in range(2): dec.decode(llr)
     torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(3): out = dec.decode(llr)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 3
-    print("layered" if layered else "flooding", f"{dt*1e3:.1f} ms  {B/dt/1e3:.0f} K frames/s  avg it {out[2].float().mean().item():.2f}")
+    print("layered" if layered else "flooding", B, f"{dt*1e3:.1f} ms  {B/dt/1e3:.0f} K frames/s  avg it {out[2].float().mean().item():.2f}")
