@@ -478,13 +478,15 @@ int ws_ensure(ldpc_decoder* d, Workspace& ws, int64_t Bp) {
     d->graphs.clear();
     ws.release();
     const ldpc_graph* g = d->g;
-    const size_t rows_v2c = (size_t)std::max<int64_t>(std::max<int64_t>(g->E, g->n), 1);
-    const size_t rows_c2v = (size_t)std::max<int64_t>(g->E, 1);
+    // the layered schedule works in place on the posteriors (llrT): it has no message arrays
+    const bool layered = d->schedule == LDPC_SCHEDULE_LAYERED;
+    const size_t rows_v2c = layered ? 0 : (size_t)std::max<int64_t>(g->E, 1);
+    const size_t rows_c2v = layered ? 0 : (size_t)std::max<int64_t>(g->E, 1);
     const size_t c2v_elt = d->bc ? 1 : d->rsz;
     const int64_t Wn = Bp / 32;
     CU(cudaMalloc(&ws.llrT, (size_t)g->n * Bp * d->rsz));
-    CU(cudaMalloc(&ws.v2c, rows_v2c * Bp * d->rsz));
-    CU(cudaMalloc(&ws.c2v, rows_c2v * Bp * c2v_elt));
+    CU(cudaMalloc(&ws.v2c, std::max<size_t>(rows_v2c * Bp * d->rsz, 16)));
+    CU(cudaMalloc(&ws.c2v, std::max<size_t>(rows_c2v * Bp * c2v_elt, 16)));
     CU(cudaMalloc((void**)&ws.hardw, (size_t)g->n * Wn * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&ws.unsat, (size_t)2 * Wn * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&ws.done, (size_t)Bp));
