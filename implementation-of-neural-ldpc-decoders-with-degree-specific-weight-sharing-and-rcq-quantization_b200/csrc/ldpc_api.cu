@@ -358,14 +358,14 @@ struct Workspace {
     }
 };
 
-constexpr int kPipeDepth = 3;
+constexpr int kPipeDepth = 4;   // staging buffers: two chunks decoding, one arriving, one leaving
 constexpr size_t kMaxLevels = 32;   // compaction levels (each at most 60 % of its parent)
 
 // Host-buffer pipeline: three streams (H2D copies, kernels, D2H copies) over kPipeDepth staging buffers
 // and ONE message workspace, so that the copy of chunk i+1, the decode of chunk i and the copy-out of
 // chunk i-1 overlap while kernels of different chunks never compete for the SMs.
 struct HostPipe {
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_run2 = nullptr, s_out = nullptr;
     struct Buf {
         void* d_llr = nullptr;
         uint8_t* d_bits = nullptr;
@@ -374,7 +374,6 @@ struct HostPipe {
         uint8_t* d_su = nullptr;
         cudaEvent_t in_ready = nullptr, run_done = nullptr, out_done = nullptr;
     } buf[kPipeDepth];
-    Workspace ws;
     int64_t cap = 0;
     bool post_cap = false;
     void release() {
@@ -385,11 +384,11 @@ struct HostPipe {
             if (b.out_done) cudaEventDestroy(b.out_done);
             b = Buf();
         }
-        ws.release();
         if (s_in) cudaStreamDestroy(s_in);
         if (s_run) cudaStreamDestroy(s_run);
+        if (s_run2) cudaStreamDestroy(s_run2);
         if (s_out) cudaStreamDestroy(s_out);
-        s_in = s_run = s_out = nullptr;
+        s_in = s_run = s_run2 = s_out = nullptr;
         cap = 0;
         post_cap = false;
     }
@@ -417,9 +416,9 @@ struct ldpc_decoder {
     void* d_alpha = nullptr;               // [T][n_alpha]
     float* d_thr = nullptr;                // [Q][nth]
     float* d_lut = nullptr;                // [Q][2^bc]
-    Workspace ws;
     HostPipe pipe;
     int64_t host_chunk = 0;
+    int host_dual = 1;            // LDPC_HOST_DUAL=0: one chunk decodes at a time in the host pipeline
     // frame compaction (early stop at scale): child workspaces, one per level, plus bookkeeping buffers
     struct Level {
         Workspace ws;
@@ -427,11 +426,18 @@ struct ldpc_decoder {
         int32_t* map = nullptr;   // [cap] frame of this level -> frame of the caller's batch
         int64_t cap = 0;
     };
-    std::vector<Level> levels;
-    int32_t* d_scan = nullptr;    // [scan_cap] per-block counts / offsets
-    int64_t scan_cap = 0;
-    int32_t* d_total = nullptr;   // device int32
-    int32_t* h_total = nullptr;   // pinned host int32
+    // Everything ONE in-flight decode mutates.  cx[0] serves the device-pointer entry points and the Monte-Carlo
+    // round, cx[1] / cx[2] the two chunks the host pipeline keeps in flight (their kernels fill each other's tails).
+    struct Ctx {
+        Workspace root;
+        std::vector<Level> levels;    // capacity reserved at creation: jobs keep pointers into it
+        int32_t* d_scan = nullptr;    // [scan_cap] per-block counts / offsets
+        int64_t scan_cap = 0;
+        int32_t* d_total = nullptr;   // device int32
+        int32_t* h_total = nullptr;   // pinned host int32
+        cudaEvent_t ev = nullptr;     // recorded after a checkpoint's count has been copied to h_total
+    };
+    Ctx cx[3];
     // launch-bound decodes (tiny codes / tiny batches): the whole T-iteration launch sequence is captured once
     // into a CUDA graph per (workspace, B, posterior) and replayed with one launch
     struct GraphEntry {
@@ -721,17 +727,18 @@ int next_checkpoint(int t, int T, int64_t Bp, int quiet, int big_step) {
     return c < T ? c : T;
 }
 
-int scan_ensure(ldpc_decoder* d, int64_t Bp) {
+int scan_ensure(ldpc_decoder::Ctx& cx, int64_t Bp) {
     const int64_t nb = (Bp + 1023) / 1024;
-    if (d->scan_cap < nb) {
-        cudaFree(d->d_scan);
-        d->d_scan = nullptr;
-        d->scan_cap = 0;
-        CU(cudaMalloc((void**)&d->d_scan, (size_t)nb * sizeof(int32_t)));
-        d->scan_cap = nb;
+    if (cx.scan_cap < nb) {
+        cudaFree(cx.d_scan);
+        cx.d_scan = nullptr;
+        cx.scan_cap = 0;
+        CU(cudaMalloc((void**)&cx.d_scan, (size_t)nb * sizeof(int32_t)));
+        cx.scan_cap = nb;
     }
-    if (!d->d_total) CU(cudaMalloc((void**)&d->d_total, sizeof(int32_t)));
-    if (!d->h_total) CU(cudaHostAlloc((void**)&d->h_total, sizeof(int32_t), cudaHostAllocDefault));
+    if (!cx.d_total) CU(cudaMalloc((void**)&cx.d_total, sizeof(int32_t)));
+    if (!cx.h_total) CU(cudaHostAlloc((void**)&cx.h_total, sizeof(int32_t), cudaHostAllocDefault));
+    if (!cx.ev) CU(cudaEventCreateWithFlags(&cx.ev, cudaEventDisableTiming));
     return LDPC_OK;
 }
 
@@ -804,64 +811,101 @@ int replay_graph(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool wan
     return LDPC_OK;
 }
 
-// The whole decode of the frames resident as llrT [n][Bp] in `root`, results delivered per OutSpec.
+// The whole decode of the frames resident as llrT [n][Bp] in the context's root workspace, results delivered per
+// OutSpec, as a RESUMABLE job: start() enqueues up to the first checkpoint, resume() is called once that
+// checkpoint's count has arrived (cx.ev) and enqueues up to the next one.  The plain entry points drive one job
+// to completion; the host pipeline alternates between two.
 //
 // Flooding with early stop runs in spans between checkpoints.  At a checkpoint the number of running frames
 // comes back to the host: zero ends the decode (no empty launches up to T); if at most 60 % of the level's
 // lanes still run, those frames' LLR and V2C columns are gathered into a dense child level that carries on
 // from the same iteration, and the parent level delivers the results of its finished frames.  Every frame
 // sees exactly the arithmetic of the uncompacted schedule (columns are independent), so results are identical.
-int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
-    const bool want_post = o.post != nullptr;
-    if (want_post) {
+struct DecodeJob {
+    ldpc_decoder* d = nullptr;
+    ldpc_decoder::Ctx* cx = nullptr;
+    cudaStream_t stream = nullptr;
+    OutSpec o;
+    bool want_post = false, checkpoints = false;
+    Workspace* ws = nullptr;          // current level
+    const int32_t* map = nullptr;     // its frames -> frames of the caller's batch
+    int64_t curB = 0, curBp = 0;
+    size_t level = 0;
+    int t = 0, quiet = 0;
+    bool waiting = false;             // a checkpoint count is in flight (cx->ev)
+};
+
+// enqueue the next span; either the decode ends with it or a checkpoint is recorded
+int job_enqueue(DecodeJob& j) {
+    ldpc_decoder* d = j.d;
+    cudaStream_t stream = j.stream;
+    const int t1 = j.checkpoints ? next_checkpoint(j.t, d->T, j.curBp, j.quiet, d->checkpoint_step) : d->T;
+    int rc = run_span(d, *j.ws, j.curBp, j.t, t1, j.want_post, stream);
+    if (rc) return rc;
+    j.t = t1;
+    if (j.t >= d->T) return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
+    LAUNCH(K_OTHER, launch_pending_scan(j.ws->done, j.curBp, j.cx->d_scan, j.cx->d_total, stream));
+    CU(cudaMemcpyAsync(j.cx->h_total, j.cx->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(j.cx->ev, stream));
+    j.waiting = true;
+    return LDPC_OK;
+}
+
+int job_start(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
+    j = DecodeJob();
+    j.d = d;
+    j.cx = &cx;
+    j.stream = stream;
+    j.o = o;
+    j.want_post = o.post != nullptr;
+    Workspace& root = cx.root;
+    if (j.want_post) {
         int rc = post_ensure(d, root);
         if (rc) return rc;
     }
     if (d->schedule == LDPC_SCHEDULE_LAYERED) {
-        int rc = run_layered(d, root, B, Bp, want_post, stream);
+        int rc = run_layered(d, root, B, Bp, j.want_post, stream);
         if (rc) return rc;
         return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
     }
-    const ldpc_graph* g = d->g;
     if (launch_bound(d, Bp)) {
-        int rc = replay_graph(d, root, B, Bp, want_post, stream);
+        int rc = replay_graph(d, root, B, Bp, j.want_post, stream);
         if (rc) return rc;
         return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
     }
     LAUNCH(K_OTHER, launch_reset_state(root.done, root.iters, root.success, root.unsat, B, Bp, d->T, stream));
-    const bool checkpoints = d->early_stop && d->compact && d->T > 2;
-    Workspace* ws = &root;
-    const int32_t* map = nullptr;
-    int64_t curB = B, curBp = Bp;
-    size_t level = 0;
-    int t = 0;
-    if (checkpoints) {
-        int rc = scan_ensure(d, Bp);
+    j.checkpoints = d->early_stop && d->compact && d->T > 2;
+    j.ws = &root;
+    j.curB = B;
+    j.curBp = Bp;
+    if (j.checkpoints) {
+        int rc = scan_ensure(cx, Bp);
         if (rc) return rc;
     }
-    int quiet = 0;
-    while (true) {
-        const int t1 = checkpoints ? next_checkpoint(t, d->T, curBp, quiet, d->checkpoint_step) : d->T;
-        int rc = run_span(d, *ws, curBp, t, t1, want_post, stream);
-        if (rc) return rc;
-        t = t1;
-        if (t >= d->T) return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
-        LAUNCH(K_OTHER, launch_pending_scan(ws->done, curBp, d->d_scan, d->d_total, stream));
-        CU(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        const int64_t pending = *d->h_total;
-        quiet = (pending >= curB) ? quiet + 1 : 0;
-        if (pending == 0) {
-            d->stat_early_exits++;   // decisions (and posteriors) of stopped frames are already in place
-            return emit_level(d, *ws, curB, curBp, map, nullptr, o, stream);
-        }
-        if (curBp < d->compact_min_frames || pending * 100 > curBp * d->compact_percent || level >= kMaxLevels) continue;
+    return job_enqueue(j);
+}
+
+// precondition: j.waiting and cx->ev has completed
+int job_resume(DecodeJob& j) {
+    ldpc_decoder* d = j.d;
+    ldpc_decoder::Ctx& cx = *j.cx;
+    cudaStream_t stream = j.stream;
+    const ldpc_graph* g = d->g;
+    j.waiting = false;
+    const int64_t pending = *cx.h_total;
+    j.quiet = (pending >= j.curB) ? j.quiet + 1 : 0;
+    if (pending == 0) {
+        d->stat_early_exits++;   // decisions (and posteriors) of stopped frames are already in place
+        return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
+    }
+    if (j.curBp >= d->compact_min_frames && pending * 100 <= j.curBp * d->compact_percent && j.level < kMaxLevels) {
         // ---- move the running frames to a dense child level ----
-        if (d->levels.size() <= level) d->levels.emplace_back();   // capacity reserved at creation: no reallocation
-        ldpc_decoder::Level& lv = d->levels[level];
+        if (cx.levels.size() <= j.level) cx.levels.emplace_back();   // capacity reserved at creation: no reallocation
+        ldpc_decoder::Level& lv = cx.levels[j.level];
         const int64_t childBp = pad_frames(pending);
+        const int64_t level_cap = pad_frames((j.curBp * d->compact_percent + 99) / 100);   // any later count of this level fits
         if (lv.cap < childBp) {
-            const int64_t cap = std::max(childBp, pad_frames((curBp * d->compact_percent + 99) / 100));   // any later count of this level fits
+            const int64_t cap = std::max(childBp, level_cap);
             cudaFree(lv.idx);
             cudaFree(lv.map);
             lv.idx = lv.map = nullptr;
@@ -870,47 +914,71 @@ int decode_resident(ldpc_decoder* d, Workspace& root, int64_t B, int64_t Bp, con
             CU(cudaMalloc((void**)&lv.map, (size_t)cap * sizeof(int32_t)));
             lv.cap = cap;
         }
-        rc = ws_ensure(d, lv.ws, std::max(childBp, std::min(lv.cap, pad_frames((curBp * d->compact_percent + 99) / 100))));
+        int rc = ws_ensure(d, lv.ws, std::max(childBp, std::min(lv.cap, level_cap)));
         if (rc == LDPC_ERR_NOMEM) {   // no room for a child level: carry on uncompacted
             cudaGetLastError();
             lv.ws.release();
-            continue;
+            return job_enqueue(j);
         }
         if (rc) return rc;
-        if (want_post) {
+        if (j.want_post) {
             rc = post_ensure(d, lv.ws);
             if (rc) return rc;
         }
-        LAUNCH(K_OTHER, launch_pending_indices(ws->done, curBp, d->d_scan, lv.idx, stream));
-        LAUNCH(K_OTHER, launch_compose_map(lv.idx, map, lv.map, pending, stream));
-        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->llrT, curBp, lv.ws.llrT, childBp, lv.idx, pending, g->n, stream));
-        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, ws->v2c, curBp, lv.ws.v2c, childBp, lv.idx, pending, g->E, stream));
+        LAUNCH(K_OTHER, launch_pending_indices(j.ws->done, j.curBp, cx.d_scan, lv.idx, stream));
+        LAUNCH(K_OTHER, launch_compose_map(lv.idx, j.map, lv.map, pending, stream));
+        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, j.ws->llrT, j.curBp, lv.ws.llrT, childBp, lv.idx, pending, g->n, stream));
+        LAUNCH(K_OTHER, launch_gather_cols(d->dtype, j.ws->v2c, j.curBp, lv.ws.v2c, childBp, lv.idx, pending, g->E, stream));
         LAUNCH(K_OTHER, launch_reset_state(lv.ws.done, lv.ws.iters, lv.ws.success, lv.ws.unsat, pending, childBp, d->T, stream));
         // the parent delivers its stopped frames (their decisions / posteriors are in place)
-        rc = emit_level(d, *ws, curB, curBp, map, ws->done, o, stream);
+        rc = emit_level(d, *j.ws, j.curB, j.curBp, j.map, j.ws->done, j.o, stream);
         if (rc) return rc;
         d->stat_compactions++;
-        ws = &lv.ws;
-        map = lv.map;
-        curB = pending;
-        curBp = childBp;
-        ++level;
+        j.ws = &lv.ws;
+        j.map = lv.map;
+        j.curB = pending;
+        j.curBp = childBp;
+        ++j.level;
     }
+    return job_enqueue(j);
 }
 
-int decode_on_device(ldpc_decoder* d, Workspace& ws, const void* llr, int64_t B, uint8_t* bits, void* post,
-                     int32_t* iters, uint8_t* success, cudaStream_t stream) {
+int decode_resident(ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
+    DecodeJob j;
+    int rc = job_start(j, d, cx, B, Bp, o, stream);
+    while (!rc && j.waiting) {
+        CU(cudaEventSynchronize(cx.ev));
+        rc = job_resume(j);
+    }
+    return rc;
+}
+
+// pack + job_start on the context's root workspace
+int job_start_on_device(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits,
+                        void* post, int32_t* iters, uint8_t* success, cudaStream_t stream) {
     const int64_t Bp = pad_frames(B);
-    int rc = ws_ensure(d, ws, Bp);
+    int rc = ws_ensure(d, cx.root, Bp);
     if (rc) return rc;
     d->prof.frames_padded = Bp;
+    Workspace& ws = cx.root;
     LAUNCH(K_OTHER, launch_pack(d->dtype, llr, ws.llrT, B, Bp, d->g->n, ws.done, ws.iters, ws.success, d->T, stream));
     OutSpec o;
     o.bits = bits;
     o.post = post;
     o.iters = iters;
     o.success = success;
-    return decode_resident(d, ws, B, Bp, o, stream);
+    return job_start(j, d, cx, B, Bp, o, stream);
+}
+
+int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits, void* post,
+                     int32_t* iters, uint8_t* success, cudaStream_t stream) {
+    DecodeJob j;
+    int rc = job_start_on_device(j, d, cx, llr, B, bits, post, iters, success, stream);
+    while (!rc && j.waiting) {
+        CU(cudaEventSynchronize(cx.ev));
+        rc = job_resume(j);
+    }
+    return rc;
 }
 
 }  // namespace
@@ -974,8 +1042,9 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->nth = cfg->bc ? (1 << (cfg->bc - 1)) : 0;
     d->check_rule = cfg->check_rule;
     d->schedule = cfg->schedule;
-    d->levels.reserve(kMaxLevels);   // decode_resident keeps pointers into this vector
-    if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);  // tuning knob: frames per pipeline chunk
+    for (auto& cx : d->cx) cx.levels.reserve(kMaxLevels);   // jobs keep pointers into these vectors
+    if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);
+    if (const char* hd = getenv("LDPC_HOST_DUAL")) d->host_dual = atoi(hd) != 0;  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
     if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);
@@ -1071,19 +1140,22 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     if (!d) return LDPC_OK;
     DeviceGuard guard(d->g->device);
     cudaDeviceSynchronize();
-    d->ws.release();
     d->pipe.release();
-    for (auto& lv : d->levels) {
-        lv.ws.release();
-        cudaFree(lv.idx);
-        cudaFree(lv.map);
-    }
     for (auto& ge : d->graphs)
         if (ge.exec) cudaGraphExecDestroy(ge.exec);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
-    cudaFree(d->d_scan);
-    cudaFree(d->d_total);
-    if (d->h_total) cudaFreeHost(d->h_total);
+    for (auto& cx : d->cx) {
+        cx.root.release();
+        for (auto& lv : cx.levels) {
+            lv.ws.release();
+            cudaFree(lv.idx);
+            cudaFree(lv.map);
+        }
+        cudaFree(cx.d_scan);
+        cudaFree(cx.d_total);
+        if (cx.h_total) cudaFreeHost(cx.h_total);
+        if (cx.ev) cudaEventDestroy(cx.ev);
+    }
     for (auto& ev : d->ev_pool) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -1102,7 +1174,7 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
 extern "C" int ldpc_decoder_reserve(ldpc_decoder* d, int64_t frames) {
     if (!d || frames < 1) return fail(LDPC_ERR_INVALID, "bad arguments");
     DeviceGuard guard(d->g->device);
-    return ws_ensure(d, d->ws, pad_frames(frames));
+    return ws_ensure(d, d->cx[0].root, pad_frames(frames));
 }
 
 extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
@@ -1111,7 +1183,7 @@ extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, u
     if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
     DeviceGuard guard(d->g->device);
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
-    return decode_on_device(d, d->ws, llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
+    return decode_on_device(d, d->cx[0], llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
 }
 
 // Host-buffer entry point: chunked three-stage pipeline (see HostPipe).
@@ -1129,6 +1201,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
     if (!pp.s_in) {
         CU(cudaStreamCreateWithFlags(&pp.s_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&pp.s_run, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&pp.s_run2, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&pp.s_out, cudaStreamNonBlocking));
         for (auto& b : pp.buf) {
             CU(cudaEventCreateWithFlags(&b.in_ready, cudaEventDisableTiming));
@@ -1149,33 +1222,46 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         pp.cap = chunk;
         pp.post_cap = posterior != nullptr;
     }
-    int rc = ws_ensure(d, pp.ws, pad_frames(chunk));
-    if (rc) return rc;
+    int rc = LDPC_OK;
     // chunk boundaries.  The link delivers a chunk's LLRs a little faster than the kernels consume them, so
     // the first chunks grow geometrically (x1.5 from 1/8 of a chunk: each input copy then lands before the
     // previous chunk's decode ends and the kernels start ~1 ms into the call); the rest of the batch is split
     // into equal chunks so that no small remainder is left for the un-overlapped tail.
     std::vector<std::pair<int64_t, int64_t>> chunks;   // (offset, frames)
     {
+        // sizes are multiples of one CTA's frame block (256 lanes x V frames) where the batch allows it: a
+        // partly filled last block costs a whole CTA slot (7424-frame chunks ran 9 % slower per frame than 8192)
+        const int64_t blk = (int64_t)256 * d->V;
+        const int64_t align = (chunk % blk == 0 && B >= 4 * blk) ? blk : kFrameAlign;
+        auto round_up = [&](int64_t x) { return (x + align - 1) / align * align; };
         int64_t off = 0;
         if (B > 2 * chunk) {
-            for (int64_t c = std::max<int64_t>(kFrameAlign, chunk / 8); c < chunk && B - off > 2 * chunk; c = c * 3 / 2) {
-                const int64_t b = std::max<int64_t>(kFrameAlign, c / kFrameAlign * kFrameAlign);
-                chunks.emplace_back(off, b);
-                off += b;
+            for (int64_t c = std::max<int64_t>(align, chunk / 8); c < chunk && B - off > 2 * chunk; c = round_up(c * 3 / 2)) {
+                chunks.emplace_back(off, c);
+                off += c;
             }
         }
-        while (off < B) {   // equal parts, each a multiple of 128 frames (except the last) and at most `chunk`
+        while (off < B) {   // equal parts of at most `chunk` frames
             const int64_t left = B - off;
             const int64_t parts = (left + chunk - 1) / chunk;
-            int64_t b = ((left + parts - 1) / parts + kFrameAlign - 1) / kFrameAlign * kFrameAlign;
-            b = std::min<int64_t>(std::min<int64_t>(b, chunk), left);
+            const int64_t b = std::min<int64_t>(std::min<int64_t>(round_up((left + parts - 1) / parts), chunk), left);
             chunks.emplace_back(off, b);
             off += b;
         }
     }
-    // The input copy of chunk i+1 is enqueued BEFORE the decode of chunk i: the decode may block the host at
-    // its checkpoints (frame compaction), and the copy engine should be busy meanwhile.
+    // Two chunks decode at a time (two contexts, two kernel streams): each is a resumable job, the host enqueues
+    // one span per job in turn and blocks on the older of the two outstanding checkpoints, so that while one job
+    // waits for its host round trip -- and while its kernels drain -- the other one keeps the SMs busy.  The
+    // input copy of chunk i+1 is enqueued before chunk i starts, so the copy engine never waits for the host.
+    const int njobs = (d->host_dual && chunks.size() > 2) ? 2 : 1;
+    cudaStream_t run_stream[2] = {pp.s_run, pp.s_run2};
+    struct Slot {
+        DecodeJob job;
+        size_t chunk = 0;
+        bool busy = false;
+        uint64_t cp_seq = 0;   // order of the outstanding checkpoint among both jobs
+    } slot[2];
+    uint64_t seq = 0;
     auto enqueue_input = [&](size_t i) -> int {
         HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
         if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_in, bf.run_done, 0));     // staging input consumed
@@ -1185,32 +1271,21 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         return LDPC_OK;
     };
     const bool trace = getenv("LDPC_PIPE_TRACE") != nullptr;   // debug: per-chunk timeline on stderr
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&](cudaStream_t st) {
+    std::vector<cudaEvent_t> tev(trace ? 1 + 3 * chunks.size() : 0, nullptr);
+    auto mark = [&](size_t idx, cudaStream_t st) {
         if (!trace) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        tev.push_back(e);
+        cudaEventCreate(&tev[idx]);
+        cudaEventRecord(tev[idx], st);
     };
-    mark(pp.s_in);
-    rc = enqueue_input(0);
-    for (size_t i = 0; i < chunks.size() && !rc; ++i) {
+    // everything of this slot's chunk is enqueued: hand its outputs to the copy-out stream
+    auto finish_chunk = [&](int sidx) -> int {
+        Slot& sl = slot[sidx];
+        const size_t i = sl.chunk;
         const int64_t off = chunks[i].first, b = chunks[i].second;
         HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
-        if (i + 1 < chunks.size()) {
-            // buffer (i+1) % depth was last read by the decode of chunk i+1-depth, already enqueued
-            rc = enqueue_input(i + 1);
-            if (rc) break;
-        }
-        CU(cudaStreamWaitEvent(pp.s_run, bf.in_ready, 0));
-        if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_run, bf.out_done, 0));    // staging outputs copied out
-        mark(pp.s_run);
-        rc = decode_on_device(d, pp.ws, bf.d_llr, b, bits ? bf.d_bits : nullptr, posterior ? bf.d_post : nullptr,
-                              bf.d_it, bf.d_su, pp.s_run);
-        if (rc) break;
-        CU(cudaEventRecord(bf.run_done, pp.s_run));
-        mark(pp.s_run);
+        cudaStream_t rs = run_stream[sidx];
+        CU(cudaEventRecord(bf.run_done, rs));
+        mark(2 + 3 * i, rs);
         CU(cudaStreamWaitEvent(pp.s_out, bf.run_done, 0));
         if (bits) CU(cudaMemcpyAsync(bits + (size_t)off * n, bf.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, pp.s_out));
         if (posterior)
@@ -1219,14 +1294,57 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         if (iterations) CU(cudaMemcpyAsync(iterations + off, bf.d_it, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, pp.s_out));
         if (success) CU(cudaMemcpyAsync(success + off, bf.d_su, (size_t)b, cudaMemcpyDeviceToHost, pp.s_out));
         CU(cudaEventRecord(bf.out_done, pp.s_out));
-        mark(pp.s_out);
+        mark(3 + 3 * i, pp.s_out);
+        sl.busy = false;
+        return LDPC_OK;
+    };
+    // resume the job with the OLDER outstanding checkpoint until slot `target` is free (target < 0: all slots)
+    auto pump = [&](int target) -> int {
+        while (true) {
+            if (target >= 0 ? !slot[target].busy : (!slot[0].busy && !slot[1].busy)) return LDPC_OK;
+            int pick = -1;
+            for (int k = 0; k < 2; ++k)
+                if (slot[k].busy && (pick < 0 || slot[k].cp_seq < slot[pick].cp_seq)) pick = k;
+            Slot& sl = slot[pick];
+            CU(cudaEventSynchronize(sl.job.cx->ev));
+            int r = job_resume(sl.job);
+            if (r) return r;
+            if (sl.job.waiting) sl.cp_seq = ++seq;
+            else if ((r = finish_chunk(pick))) return r;
+        }
+    };
+    mark(0, pp.s_in);
+    rc = enqueue_input(0);
+    for (size_t i = 0; i < chunks.size() && !rc; ++i) {
+        const int sidx = (int)(i % (size_t)njobs);
+        rc = pump(sidx);   // the chunk that used this slot is through
+        if (rc) break;
+        if (i + 1 < chunks.size()) {
+            // buffer (i+1) % depth was last used by chunk i+1-depth, finished at least one pump ago
+            rc = enqueue_input(i + 1);
+            if (rc) break;
+        }
+        HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
+        cudaStream_t rs = run_stream[sidx];
+        CU(cudaStreamWaitEvent(rs, bf.in_ready, 0));
+        if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(rs, bf.out_done, 0));    // staging outputs copied out
+        mark(1 + 3 * i, rs);
+        Slot& sl = slot[sidx];
+        sl.chunk = i;
+        sl.busy = true;
+        rc = job_start_on_device(sl.job, d, d->cx[1 + sidx], bf.d_llr, chunks[i].second, bits ? bf.d_bits : nullptr,
+                                 posterior ? bf.d_post : nullptr, bf.d_it, bf.d_su, rs);
+        if (rc) break;
+        if (sl.job.waiting) sl.cp_seq = ++seq;
+        else rc = finish_chunk(sidx);
     }
-    for (cudaStream_t st : {pp.s_in, pp.s_run, pp.s_out}) {
+    if (!rc) rc = pump(-1);
+    for (cudaStream_t st : {pp.s_in, pp.s_run, pp.s_run2, pp.s_out}) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess && !rc) rc = fail(LDPC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
     }
-    if (trace && tev.size() >= 1) {
-        for (size_t i = 0; i + 3 < tev.size() + 0 && 1 + 3 * i + 2 < tev.size(); ++i) {
+    if (trace && !rc) {
+        for (size_t i = 0; i < chunks.size(); ++i) {
             float a = 0, b = 0, c = 0;
             cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]);
             cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * i]);
@@ -1234,8 +1352,9 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
             fprintf(stderr, "chunk %2zu frames %6lld: decode start %7.2f ms  end %7.2f ms (%.2f)  outputs copied %7.2f ms\n", i,
                     (long long)chunks[i].second, a, b, b - a, c);
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
+    for (cudaEvent_t e : tev)
+        if (e) cudaEventDestroy(e);
     return rc;
 }
 
@@ -1261,10 +1380,10 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t Bp = pad_frames(B);
-    int rc = ws_ensure(d, d->ws, Bp);
+    int rc = ws_ensure(d, d->cx[0].root, Bp);
     if (rc) return rc;
     d->prof.frames_padded = Bp;
-    Workspace& ws = d->ws;
+    Workspace& ws = d->cx[0].root;
     LAUNCH(K_OTHER, launch_awgn(d->dtype, 0, ws.llrT, d->g->n, B, Bp, frame0, seed, snr_db, llr_sign, codeword, stream));
     OutSpec o;
     o.count = true;
@@ -1272,7 +1391,7 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     o.counters = counters;
     o.frame_bit_errors = frame_bit_errors;
     o.frame_iters = frame_iterations;
-    return decode_resident(d, ws, B, Bp, o, stream);
+    return decode_resident(d, d->cx[0], B, Bp, o, stream);
 }
 
 extern "C" int ldpc_count_errors(int device, int32_t n, int64_t B, const uint8_t* bits, const uint8_t* codeword,
