@@ -1262,15 +1262,20 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         uint64_t cp_seq = 0;   // order of the outstanding checkpoint among both jobs
     } slot[2];
     uint64_t seq = 0;
+    const bool trace = getenv("LDPC_PIPE_TRACE") != nullptr;   // debug: per-chunk timeline on stderr
+    std::vector<cudaEvent_t> tin(trace ? chunks.size() : 0, nullptr);
     auto enqueue_input = [&](size_t i) -> int {
         HostPipe::Buf& bf = pp.buf[i % kPipeDepth];
         if (i >= (size_t)kPipeDepth) CU(cudaStreamWaitEvent(pp.s_in, bf.run_done, 0));     // staging input consumed
         CU(cudaMemcpyAsync(bf.d_llr, (const char*)llr + (size_t)chunks[i].first * n * d->rsz,
                            (size_t)chunks[i].second * n * d->rsz, cudaMemcpyHostToDevice, pp.s_in));
         CU(cudaEventRecord(bf.in_ready, pp.s_in));
+        if (trace) {
+            cudaEventCreate(&tin[i]);
+            cudaEventRecord(tin[i], pp.s_in);
+        }
         return LDPC_OK;
     };
-    const bool trace = getenv("LDPC_PIPE_TRACE") != nullptr;   // debug: per-chunk timeline on stderr
     std::vector<cudaEvent_t> tev(trace ? 1 + 3 * chunks.size() : 0, nullptr);
     auto mark = [&](size_t idx, cudaStream_t st) {
         if (!trace) return;
@@ -1349,11 +1354,15 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
             cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]);
             cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * i]);
             cudaEventElapsedTime(&c, tev[0], tev[3 + 3 * i]);
-            fprintf(stderr, "chunk %2zu frames %6lld: decode start %7.2f ms  end %7.2f ms (%.2f)  outputs copied %7.2f ms\n", i,
-                    (long long)chunks[i].second, a, b, b - a, c);
+            float in = 0;
+            cudaEventElapsedTime(&in, tev[0], tin[i]);
+            fprintf(stderr, "chunk %2zu frames %6lld: input landed %7.2f ms  decode start %7.2f ms  end %7.2f ms (%.2f)  outputs copied %7.2f ms\n",
+                    i, (long long)chunks[i].second, in, a, b, b - a, c);
         }
     }
     for (cudaEvent_t e : tev)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : tin)
         if (e) cudaEventDestroy(e);
     return rc;
 }
