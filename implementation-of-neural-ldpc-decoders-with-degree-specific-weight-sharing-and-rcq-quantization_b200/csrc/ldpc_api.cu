@@ -361,9 +361,9 @@ struct Workspace {
 constexpr int kPipeDepth = 4;   // staging buffers: two chunks decoding, one arriving, one leaving
 constexpr size_t kMaxLevels = 32;   // compaction levels (each at most 60 % of its parent)
 
-// Host-buffer pipeline: three streams (H2D copies, kernels, D2H copies) over kPipeDepth staging buffers
-// and ONE message workspace, so that the copy of chunk i+1, the decode of chunk i and the copy-out of
-// chunk i-1 overlap while kernels of different chunks never compete for the SMs.
+// Host-buffer pipeline: four streams (H2D copies, two kernel streams, D2H copies) over kPipeDepth staging
+// buffers; the copy of chunk i+2, the decodes of chunks i and i+1 (two contexts of the decoder) and the
+// copy-out of chunk i-1 overlap.
 struct HostPipe {
     cudaStream_t s_in = nullptr, s_run = nullptr, s_run2 = nullptr, s_out = nullptr;
     struct Buf {
@@ -1186,7 +1186,7 @@ extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, u
     return decode_on_device(d, d->cx[0], llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
 }
 
-// Host-buffer entry point: chunked three-stage pipeline (see HostPipe).
+// Host-buffer entry point: chunked pipeline with two decode jobs in flight (see HostPipe, DecodeJob).
 extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
                                 int32_t* iterations, uint8_t* success) {
     if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
