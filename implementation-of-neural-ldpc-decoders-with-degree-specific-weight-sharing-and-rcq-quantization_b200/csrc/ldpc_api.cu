@@ -970,6 +970,35 @@ int job_start_on_device(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, co
     return job_start(j, d, cx, B, Bp, o, stream);
 }
 
+// Chunk plan of the host pipeline: (offset, frames) pairs covering [0, B), each at most `chunk` frames.
+// The link delivers a chunk's LLRs a little faster than the kernels consume them, so the first chunks grow
+// geometrically (x1.5 from 1/8 of a chunk: the kernels start ~1 ms into the call); the rest of the batch is
+// split into equal parts so that no small remainder is left for the un-overlapped tail.  Sizes are multiples of
+// one CTA's frame block (256 lanes x V frames) where the batch allows it: a partly filled last block costs a
+// whole CTA slot.
+std::vector<std::pair<int64_t, int64_t>> plan_chunks(int64_t B, int64_t chunk, int V) {
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    if (chunk < 1 || chunk > B) chunk = B;
+    const int64_t blk = (int64_t)256 * V;
+    const int64_t align = (chunk % blk == 0 && B >= 4 * blk) ? blk : kFrameAlign;
+    auto round_up = [&](int64_t x) { return (x + align - 1) / align * align; };
+    int64_t off = 0;
+    if (B > 2 * chunk) {
+        for (int64_t c = std::max<int64_t>(align, chunk / 8); c < chunk && B - off > 2 * chunk; c = round_up(c * 3 / 2)) {
+            chunks.emplace_back(off, c);
+            off += c;
+        }
+    }
+    while (off < B) {   // equal parts of at most `chunk` frames
+        const int64_t left = B - off;
+        const int64_t parts = (left + chunk - 1) / chunk;
+        const int64_t b = std::min<int64_t>(std::min<int64_t>(round_up((left + parts - 1) / parts), chunk), left);
+        chunks.emplace_back(off, b);
+        off += b;
+    }
+    return chunks;
+}
+
 int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits, void* post,
                      int32_t* iters, uint8_t* success, cudaStream_t stream) {
     DecodeJob j;
@@ -1223,32 +1252,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         pp.post_cap = posterior != nullptr;
     }
     int rc = LDPC_OK;
-    // chunk boundaries.  The link delivers a chunk's LLRs a little faster than the kernels consume them, so
-    // the first chunks grow geometrically (x1.5 from 1/8 of a chunk: each input copy then lands before the
-    // previous chunk's decode ends and the kernels start ~1 ms into the call); the rest of the batch is split
-    // into equal chunks so that no small remainder is left for the un-overlapped tail.
-    std::vector<std::pair<int64_t, int64_t>> chunks;   // (offset, frames)
-    {
-        // sizes are multiples of one CTA's frame block (256 lanes x V frames) where the batch allows it: a
-        // partly filled last block costs a whole CTA slot (7424-frame chunks ran 9 % slower per frame than 8192)
-        const int64_t blk = (int64_t)256 * d->V;
-        const int64_t align = (chunk % blk == 0 && B >= 4 * blk) ? blk : kFrameAlign;
-        auto round_up = [&](int64_t x) { return (x + align - 1) / align * align; };
-        int64_t off = 0;
-        if (B > 2 * chunk) {
-            for (int64_t c = std::max<int64_t>(align, chunk / 8); c < chunk && B - off > 2 * chunk; c = round_up(c * 3 / 2)) {
-                chunks.emplace_back(off, c);
-                off += c;
-            }
-        }
-        while (off < B) {   // equal parts of at most `chunk` frames
-            const int64_t left = B - off;
-            const int64_t parts = (left + chunk - 1) / chunk;
-            const int64_t b = std::min<int64_t>(std::min<int64_t>(round_up((left + parts - 1) / parts), chunk), left);
-            chunks.emplace_back(off, b);
-            off += b;
-        }
-    }
+    const std::vector<std::pair<int64_t, int64_t>> chunks = plan_chunks(B, chunk, d->V);   // (offset, frames)
     // Two chunks decode at a time (two contexts, two kernel streams): each is a resumable job, the host enqueues
     // one span per job in turn and blocks on the older of the two outstanding checkpoints, so that while one job
     // waits for its host round trip -- and while its kernels drain -- the other one keeps the SMs busy.  The
@@ -1365,6 +1369,15 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
     for (cudaEvent_t e : tin)
         if (e) cudaEventDestroy(e);
     return rc;
+}
+
+extern "C" int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t* frames_out, int32_t max_chunks,
+                                    int32_t* n_chunks) {
+    if (B < 1 || !n_chunks || frames_per_lane < 1) return fail(LDPC_ERR_INVALID, "bad arguments");
+    const auto plan = plan_chunks(B, chunk > 0 ? chunk : 8192, frames_per_lane);
+    *n_chunks = (int32_t)plan.size();
+    for (int32_t i = 0; i < (int32_t)plan.size() && i < max_chunks && frames_out; ++i) frames_out[i] = plan[(size_t)i].second;
+    return LDPC_OK;
 }
 
 // =================================================================================================

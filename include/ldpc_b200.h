@@ -144,6 +144,11 @@ int ldpc_decode_device(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bit
 int ldpc_decode_host(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bits, void *posterior,
                      int32_t *iterations, uint8_t *success);
 
+/* Test hook: the chunk plan ldpc_decode_host uses for a batch of B frames (frames per chunk, in order).
+ * chunk <= 0 selects the default (8192); frames_per_lane is 4 for F32 decoders, 2 for F64. */
+int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t *frames_out,
+                         int32_t max_chunks, int32_t *n_chunks);
+
 /* ---------------------------------------------------------------------------------------------
  * Monte-Carlo leg.  Replaces simulate_awgn_channel (ldpc_decoder.py:286-302) and the per-frame
  * body of LDPSimulator.simulate_single_snr (simulation_framework.py:110-131).

@@ -179,3 +179,31 @@ def test_simulation_bookkeeping(built_lib, tmp_path):
     blob = json.load(open(tmp_path / "r" / "a.json"))
     assert set(blob["x"]) == {"decoder_name", "snr_values", "frame_error_rates", "bit_error_rates",
                               "average_iterations", "simulation_times", "total_frames", "total_errors"}
+
+
+def test_host_pipeline_chunk_plan(built_lib):
+    """The chunk plan of ldpc_decode_host (test hook, no device needed): covers the batch exactly, no chunk above
+    the limit, geometric ramp at the head, equal block-aligned parts after it, no small trailing chunk."""
+    from ldpc_b200 import _lib
+    lib = _lib.load()
+
+    def plan(B, chunk, V=4):
+        out = np.zeros(4096, dtype=np.int64)
+        nc = ctypes.c_int32(0)
+        _lib.check(lib.ldpc_host_chunk_plan(B, chunk, V, out.ctypes.data, out.size, ctypes.byref(nc)))
+        return out[:nc.value].tolist()
+
+    assert plan(65536, 8192) == [1024, 2048, 3072, 5120, 8192, 8192, 8192, 8192, 7168, 7168, 7168]
+    assert plan(1, 8192) == [1] and plan(100, 8192) == [100] and plan(8192, 8192) == [8192]
+    assert plan(65536, 0) == plan(65536, 8192)                       # default chunk
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        B = int(rng.integers(1, 300000))
+        chunk = int(rng.choice([0, 100, 512, 1000, 4096, 8192, 16384]))
+        V = int(rng.choice([2, 4]))
+        p = plan(B, chunk, V)
+        lim = min(B, chunk if chunk > 0 else 8192)
+        assert sum(p) == B and all(0 < c <= lim for c in p), (B, chunk, p)
+        if B > 4 * lim and lim >= 1024:
+            assert p[-1] >= lim // 2, (B, chunk, p)                   # no small un-overlapped tail
+            assert p[0] <= max(lim // 8, 128 * 8), (B, chunk, p)        # the kernels start early
