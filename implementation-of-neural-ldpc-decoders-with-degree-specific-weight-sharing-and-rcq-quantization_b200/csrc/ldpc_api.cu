@@ -90,6 +90,9 @@ struct ldpc_graph {
     std::vector<int64_t> chk_ptr;        // original CSR (layered schedule walks checks in index order)
     std::vector<int32_t> chk_var;
     int nonempty_checks = 0;
+    // dependency levels of the layered schedule (checks in index order; see layered_level_kernel)
+    std::vector<int32_t> level_ptr, level_chk;
+    int32_t* d_level_chk = nullptr;
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
@@ -248,6 +251,27 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             pos = end;
         }
     }
+    // ---- dependency levels of the checks in index order (layered schedule) ----
+    {
+        std::vector<int32_t> last(n, 0), lvl(m, 0);
+        int32_t nlev = 0;
+        for (int32_t i = 0; i < m; ++i) {
+            if (check_ptr[i + 1] == check_ptr[i]) continue;
+            int32_t l = 0;
+            for (int64_t e = check_ptr[i]; e < check_ptr[i + 1]; ++e) l = std::max(l, last[check_var[e]]);
+            lvl[i] = ++l;
+            for (int64_t e = check_ptr[i]; e < check_ptr[i + 1]; ++e) last[check_var[e]] = l;
+            nlev = std::max(nlev, l);
+        }
+        g->level_ptr.assign((size_t)nlev + 1, 0);
+        for (int32_t i = 0; i < m; ++i)
+            if (lvl[i]) g->level_ptr[(size_t)lvl[i]]++;
+        for (int32_t l = 0; l < nlev; ++l) g->level_ptr[(size_t)l + 1] += g->level_ptr[(size_t)l];
+        g->level_chk.assign((size_t)g->nonempty_checks, 0);
+        std::vector<int32_t> fill(g->level_ptr.begin(), g->level_ptr.end());
+        for (int32_t i = 0; i < m; ++i)   // ascending check index inside a level
+            if (lvl[i]) g->level_chk[(size_t)fill[(size_t)lvl[i] - 1]++] = i;
+    }
     // fine lists (one node per item) and the degree ranges of both
     for (ldpc_graph::ItemList* pair : {g->cn, g->vn}) {
         for (const WorkItem& it : pair[0].items)
@@ -286,6 +310,7 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     }
     if (!rc) rc = upload(&g->d_chk_ptr, g->chk_ptr);
     if (!rc) rc = upload(&g->d_chk_var, g->chk_var);
+    if (!rc) rc = upload(&g->d_level_chk, g->level_chk);
     if (rc) {
         ldpc_graph_destroy(g);
         return rc;
@@ -306,6 +331,7 @@ extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
     }
     cudaFree(g->d_chk_ptr);
     cudaFree(g->d_chk_var);
+    cudaFree(g->d_level_chk);
     delete g;
     return LDPC_OK;
 }
@@ -418,6 +444,7 @@ struct ldpc_decoder {
     float* d_lut = nullptr;                // [Q][2^bc]
     HostPipe pipe;
     int64_t host_chunk = 0;
+    int layered_levels = 1;       // LDPC_LAYERED_LEVELS=0: always the sequential layered kernel
     int host_dual = 1;            // LDPC_HOST_DUAL=0: one chunk decodes at a time in the host pipeline
     // frame compaction (early stop at scale): child workspaces, one per level, plus bookkeeping buffers
     struct Level {
@@ -565,8 +592,18 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
     LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
     for (int t = 0; t < d->T; ++t) {
         const int q = d->q_of_iter[t];
-        LAUNCH(K_CN, launch_layered_iter(static_cast<float*>(ws.llrT), g->d_chk_ptr, g->d_chk_var, g->m,
-                                         d->d_thr + (size_t)q * d->nth, d->nth, d->bc, d->mono[q], ws.done, Bp, stream));
+        const int nlev = (int)g->level_ptr.size() - 1;
+        if (d->layered_levels && nlev > 0 && (int64_t)nlev * 16 <= g->nonempty_checks) {
+            // few dependency levels (e.g. one per block row of a quasi-cyclic code): a level's checks run concurrently
+            for (int l = 0; l < nlev; ++l)
+                LAUNCH(K_CN, launch_layered_level(static_cast<float*>(ws.llrT), g->d_chk_ptr, g->d_chk_var,
+                                                  g->d_level_chk + g->level_ptr[(size_t)l],
+                                                  g->level_ptr[(size_t)l + 1] - g->level_ptr[(size_t)l],
+                                                  d->d_thr + (size_t)q * d->nth, d->nth, d->mono[q], ws.done, Bp, stream));
+        } else {
+            LAUNCH(K_CN, launch_layered_iter(static_cast<float*>(ws.llrT), g->d_chk_ptr, g->d_chk_var, g->m,
+                                             d->d_thr + (size_t)q * d->nth, d->nth, d->bc, d->mono[q], ws.done, Bp, stream));
+        }
         LAUNCH(K_VN, launch_hard(d->dtype, ws.llrT, ws.hardw, Wn, g->n, Bp, stream));
         if (d->early_stop || t == d->T - 1) {
             uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
@@ -1073,7 +1110,8 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     d->schedule = cfg->schedule;
     for (auto& cx : d->cx) cx.levels.reserve(kMaxLevels);   // jobs keep pointers into these vectors
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);
-    if (const char* hd = getenv("LDPC_HOST_DUAL")) d->host_dual = atoi(hd) != 0;  // tuning knob: frames per pipeline chunk
+    if (const char* hd = getenv("LDPC_HOST_DUAL")) d->host_dual = atoi(hd) != 0;
+    if (const char* ll = getenv("LDPC_LAYERED_LEVELS")) d->layered_levels = atoi(ll) != 0;  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
     if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);

@@ -905,6 +905,69 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
     }
 }
 
+// The same schedule, level-parallel.  Checks are grouped into dependency LEVELS on the host (a check's level is one
+// above the highest level among the earlier checks it shares a variable with), so checks of one level touch
+// disjoint variables and every posterior still receives its updates in check-index order: running a level's
+// checks concurrently gives exactly the sequential result.  Quasi-cyclic codes have a handful of levels (one
+// per block row), chain-structured codes (dual-diagonal parity) have as many levels as checks and keep the
+// sequential kernel.  A lane owns four frames; one CTA handles kLayerChunk checks of the level.
+constexpr int kLayerChunk = 4;
+__global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restrict__ P, const int64_t* __restrict__ chk_ptr,
+                                                                  const int32_t* __restrict__ chk_var,
+                                                                  const int32_t* __restrict__ level_chk, int n_checks,
+                                                                  const float* __restrict__ thr, int nth, int mono,
+                                                                  const uint8_t* __restrict__ done, int64_t Bp, int nfb) {
+    constexpr int V = 4;
+    __shared__ float s_thr[kMaxQuantLevels];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
+    __syncthreads();
+    const int fb = blockIdx.x % nfb;
+    const int group = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= Bp) return;
+    const uint32_t dmask = load_done_mask<V>(done, f0);
+    if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
+    Quantizer<0> qz;
+    qz.load(s_thr, nth, mono != 0);
+    const uint32_t stride = (uint32_t)Bp * (uint32_t)sizeof(float);
+    float* __restrict__ P0 = P + f0;
+    for (int c = group * kLayerChunk; c < min(n_checks, (group + 1) * kLayerChunk); ++c) {
+        const int32_t i = __ldg(level_chk + c);
+        const int64_t e0 = __ldg(chk_ptr + i), e1 = __ldg(chk_ptr + i + 1);
+        const int dc = (int)(e1 - e0);
+        MinState<float, false> st[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].init();
+        for (int k = 0; k < dc; ++k) {
+            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride));
+#pragma unroll
+            for (int v = 0; v < V; ++v) st[v].push(x.v[v], k);
+        }
+        float va[V], vb[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (dc == 1) st[v].m2 = st[v].m1;
+            va[v] = s_thr[qz.index(st[v].m1)];
+            vb[v] = s_thr[qz.index(st[v].m2)];
+        }
+        for (int k = 0; k < dc; ++k) {
+            float* ptr = row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride);
+            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(ptr);
+            Pack<float, V> out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const bool is_min = fabsf(x.v[v]) == st[v].m1;
+                const float raw = is_min ? st[v].m2 : st[v].m1;
+                const float mag = is_min ? vb[v] : va[v];
+                // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude
+                const bool neg = (((st[v].par ^ __float_as_uint(x.v[v])) >> 31) != 0u) && (raw != 0.f);
+                out.v[v] = __fadd_rn(x.v[v], neg ? -mag : mag);
+            }
+            store_masked<float, V>(ptr, out, dmask);   // stopped frames keep their posteriors
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -999,6 +1062,19 @@ cudaError_t launch_cn_offset_all(const CnLaunch& p, cudaStream_t stream) {
 cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) {
     if (p.n_items == 0) return cudaSuccess;
     return dtype == 0 ? launch_cn_offset_all<float>(p, stream) : launch_cn_offset_all<double>(p, stream);
+}
+
+cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t* chk_var, const int32_t* level_chk,
+                                 int n_checks, const float* thr, int nth, int mono, const uint8_t* done, int64_t Bp,
+                                 cudaStream_t stream) {
+    if (n_checks <= 0) return cudaSuccess;
+    const int threads = threads_for(Bp, 4);
+    const int64_t nfb = (Bp / 4 + threads - 1) / threads;
+    const int64_t grid = nfb * ((n_checks + kLayerChunk - 1) / kLayerChunk);
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    layered_level_kernel<<<(unsigned)grid, threads, 0, stream>>>(P, chk_ptr, chk_var, level_chk, n_checks, thr, nth, mono, done,
+                                                                  Bp, (int)nfb);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,

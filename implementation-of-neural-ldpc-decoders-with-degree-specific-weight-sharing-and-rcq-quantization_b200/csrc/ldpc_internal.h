@@ -85,6 +85,10 @@ cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream);
 // one layered-RCQ iteration over all checks in index order, in place on the posteriors P [n][Bp]
 cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,
                                 int nth, int bc, int mono, const uint8_t* done, int64_t Bp, cudaStream_t stream);
+// the checks level_chk[0..n_checks) of ONE dependency level of that schedule, concurrently (they share no variable)
+cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t* chk_var, const int32_t* level_chk,
+                                 int n_checks, const float* thr, int nth, int mono, const uint8_t* done, int64_t Bp,
+                                 cudaStream_t stream);
 // hard decisions (P < 0) of every frame, bit-packed
 cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, int32_t n, int64_t Bp, cudaStream_t stream);
 cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream);

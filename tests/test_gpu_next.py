@@ -124,3 +124,27 @@ def test_create_test_decoders_builds_all_ten(built_lib):
     for name, d in decs.items():
         out = d.decode(llr.double().numpy()) if name == 'Basic MinSum' else (d.decode(llr) if name == 'RCQ MinSum' else d(llr))
         assert len(out) == 3 and len(out[0]) == 7 and isinstance(out[2], int)
+
+
+def test_layered_level_parallel_equals_sequential(built_lib, monkeypatch):
+    """Quasi-cyclic codes have few dependency levels (one per block row): the level-parallel layered kernel must
+    give exactly the sequential kernel's result (full (9472,8192)-shaped code, frames stopping at different
+    iterations), and a chain-structured code must keep using the sequential kernel."""
+    L = built_lib
+    T = 10
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    code = L.codes.qc_shaped(max_iterations=T)
+    llr = torch.cat([L.awgn_llr(code.n, 700, snr, seed=60 + k, llr_sign=1) for k, snr in enumerate((5.0, 6.5, 8.0))])
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LDPC_LAYERED_LEVELS", flag)
+        dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
+        b, s, i = dec.decode(llr)
+        outs.append((b, s, i, dec._engine(0).profile_read()["cn_launches"]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert len(set(outs[1][2].tolist())) > 2
+    assert outs[1][3] > outs[0][3] >= 1          # one launch per level instead of one per iteration
+    chain = L.codes.dvbs2_shaped(max_iterations=4, scale=20)      # dual-diagonal parity: as many levels as checks
+    dec = L.RCQMinSumDecoder(chain, 3, 8, qp, max_iterations=4, layered=True)
+    dec.decode(L.awgn_llr(chain.n, 64, 0.0, seed=1, llr_sign=-1))
+    assert dec._engine(0).profile_read()["cn_launches"] == 4

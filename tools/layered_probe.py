@@ -2,13 +2,13 @@
 import sys, time, torch, numpy as np
 sys.path.insert(0, ".")
 import ldpc_b200 as L
-code = L.codes.dvbs2_shaped(max_iterations=10)
 qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-for layered, B in ((False, 32768), (True, 32768), (True, 131072), (True, 262144)):
+for cname, layered, B in (("dvbs2", False, 32768), ("dvbs2", True, 32768), ("dvbs2", True, 131072), ("qc", False, 32768), ("qc", True, 32768)):
+    code = L.codes.dvbs2_shaped(max_iterations=10) if cname == "dvbs2" else L.codes.qc_shaped(max_iterations=10)
     dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=10, layered=layered)
     llr = L.awgn_llr(code.n, B, 2.0, seed=1, llr_sign=-1)
     for _ in range(2): dec.decode(llr)
     torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(3): out = dec.decode(llr)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 3
-    print("layered" if layered else "flooding", B, f"{dt*1e3:.1f} ms  {B/dt/1e3:.0f} K frames/s  avg it {out[2].float().mean().item():.2f}")
+    print(cname, "layered" if layered else "flooding", B, f"{dt*1e3:.1f} ms  {B/dt/1e3:.0f} K frames/s  avg it {out[2].float().mean().item():.2f}")
