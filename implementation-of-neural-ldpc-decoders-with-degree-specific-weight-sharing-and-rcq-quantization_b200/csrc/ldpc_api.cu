@@ -93,6 +93,10 @@ struct ldpc_graph {
     // dependency levels of the layered schedule (checks in index order; see layered_level_kernel)
     std::vector<int32_t> level_ptr, level_chk;
     int32_t* d_level_chk = nullptr;
+    // software-pipelined sequential walk (layered_pipe_kernel): one record per non-empty check; empty when a
+    // check has more than kLayerMaxDeg edges
+    std::vector<LayerRec> lay_recs;
+    LayerRec* d_lay_recs = nullptr;
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
@@ -272,6 +276,33 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
         for (int32_t i = 0; i < m; ++i)   // ascending check index inside a level
             if (lvl[i]) g->level_chk[(size_t)fill[(size_t)lvl[i] - 1]++] = i;
     }
+    // ---- records of the software-pipelined sequential walk (layered_pipe_kernel) ----
+    if (max_dc <= kLayerMaxDeg) {
+        const int depth = layered_pipe_depth();
+        std::vector<LayerRec> recs;
+        recs.reserve((size_t)g->nonempty_checks);
+        std::vector<int32_t> last_s(n, -1), last_k(n, 0);   // latest check of the walk that touched a variable, and where
+        for (int32_t i = 0; i < m; ++i) {
+            const int64_t e0 = check_ptr[i], e1 = check_ptr[i + 1];
+            if (e1 == e0) continue;
+            const int32_t s = (int32_t)recs.size();
+            LayerRec r{};
+            r.dc = (uint8_t)(e1 - e0);
+            for (int64_t e = e0; e < e1; ++e) {
+                const int k = (int)(e - e0);
+                const int32_t v = check_var[e];
+                r.var[k] = v;
+                if (last_s[v] >= 0 && s - last_s[v] < depth)
+                    recs[(size_t)last_s[v]].desc[last_k[v]] |= (uint8_t)(((s - last_s[v]) << 3) | k);   // forwarded by its last writer
+                else
+                    r.ahead_mask |= (uint8_t)(1u << k);                                                 // copied ahead
+                last_s[v] = s;
+                last_k[v] = k;
+            }
+            recs.push_back(r);
+        }
+        g->lay_recs = std::move(recs);
+    }
     // fine lists (one node per item) and the degree ranges of both
     for (ldpc_graph::ItemList* pair : {g->cn, g->vn}) {
         for (const WorkItem& it : pair[0].items)
@@ -311,6 +342,7 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     if (!rc) rc = upload(&g->d_chk_ptr, g->chk_ptr);
     if (!rc) rc = upload(&g->d_chk_var, g->chk_var);
     if (!rc) rc = upload(&g->d_level_chk, g->level_chk);
+    if (!rc) rc = upload(&g->d_lay_recs, g->lay_recs);
     if (rc) {
         ldpc_graph_destroy(g);
         return rc;
@@ -332,6 +364,7 @@ extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
     cudaFree(g->d_chk_ptr);
     cudaFree(g->d_chk_var);
     cudaFree(g->d_level_chk);
+    cudaFree(g->d_lay_recs);
     delete g;
     return LDPC_OK;
 }
@@ -347,6 +380,8 @@ extern "C" int ldpc_graph_query(const ldpc_graph* g, int what, int64_t* value) {
         case LDPC_GRAPH_MAX_DC: *value = g->max_dc; break;
         case LDPC_GRAPH_MAX_DV: *value = g->max_dv; break;
         case LDPC_GRAPH_DEVICE: *value = g->device; break;
+        case LDPC_GRAPH_LAYER_LEVELS: *value = (int64_t)g->level_ptr.size() - 1; break;
+        case LDPC_GRAPH_LAYER_PIPED: *value = g->lay_recs.empty() ? 0 : 1; break;
         default: return fail(LDPC_ERR_INVALID, "unknown query %d", what);
     }
     return LDPC_OK;
@@ -445,6 +480,7 @@ struct ldpc_decoder {
     HostPipe pipe;
     int64_t host_chunk = 0;
     int layered_levels = 1;       // LDPC_LAYERED_LEVELS=0: always the sequential layered kernel
+    int layered_pipe = 1;         // LDPC_LAYERED_PIPE=0: the plain sequential kernel instead of the software-pipelined one
     int host_dual = 1;            // LDPC_HOST_DUAL=0: one chunk decodes at a time in the host pipeline
     // frame compaction (early stop at scale): child workspaces, one per level, plus bookkeeping buffers
     struct Level {
@@ -600,6 +636,10 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
                                                   g->d_level_chk + g->level_ptr[(size_t)l],
                                                   g->level_ptr[(size_t)l + 1] - g->level_ptr[(size_t)l],
                                                   d->d_thr + (size_t)q * d->nth, d->nth, d->mono[q], ws.done, Bp, stream));
+        } else if (d->layered_pipe && !g->lay_recs.empty()) {
+            // chain-structured codes: one thread per frame walks the checks, inputs prefetched / forwarded on chip
+            LAUNCH(K_CN, launch_layered_pipe(static_cast<float*>(ws.llrT), g->d_lay_recs, (int)g->lay_recs.size(),
+                                             d->d_thr + (size_t)q * d->nth, d->nth, d->mono[q], ws.done, Bp, stream));
         } else {
             LAUNCH(K_CN, launch_layered_iter(static_cast<float*>(ws.llrT), g->d_chk_ptr, g->d_chk_var, g->m,
                                              d->d_thr + (size_t)q * d->nth, d->nth, d->bc, d->mono[q], ws.done, Bp, stream));
@@ -1111,6 +1151,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     for (auto& cx : d->cx) cx.levels.reserve(kMaxLevels);   // jobs keep pointers into these vectors
     if (const char* hc = getenv("LDPC_HOST_CHUNK")) d->host_chunk = atoll(hc);
     if (const char* hd = getenv("LDPC_HOST_DUAL")) d->host_dual = atoi(hd) != 0;
+    if (const char* lp = getenv("LDPC_LAYERED_PIPE")) d->layered_pipe = atoi(lp) != 0;
     if (const char* ll = getenv("LDPC_LAYERED_LEVELS")) d->layered_levels = atoi(ll) != 0;  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction

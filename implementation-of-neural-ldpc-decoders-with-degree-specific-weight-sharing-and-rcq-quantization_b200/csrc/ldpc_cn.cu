@@ -905,6 +905,194 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
     }
 }
 
+// The same sequential walk, software-pipelined.  A thread still owns one frame and visits the checks in index
+// order, but the walk no longer waits for DRAM once per check: every input of check s comes out of the thread's
+// own column of a shared-memory ring of kLayerDepth check slots.  The host classifies every edge (s, k) of the
+// walk (ldpc_graph_create, `lay_desc`):
+//   * no check in (s - kLayerDepth, s) touches its variable  -> the posterior is copied global -> ring by a
+//     per-thread cp.async issued kLayerDepth checks ahead (nothing writes the value in between);
+//   * otherwise the latest such check j FORWARDS the value it writes to the posterior row into ring slot s as well
+//     (descriptor of its own edge: distance s - j and position k).
+// So a dual-diagonal parity chain (every check shares a variable with its predecessor) runs off registers and
+// shared memory, and the frame's other posteriors arrive kLayerDepth checks early.  The arithmetic per check is
+// the plain kernel's, on the same values in the same order.  Needs check degrees <= kLayerMaxDeg.
+#ifndef LDPC_LAYER_DEPTH
+#define LDPC_LAYER_DEPTH 8
+#endif
+constexpr int kLayerDepth = LDPC_LAYER_DEPTH;
+constexpr int kLayerThreads = 128;
+static_assert(kLayerDepth >= 2 && kLayerDepth <= 16, "descriptor holds a 4-bit distance");
+static_assert(kLayerMaxDeg == 8, "descriptor holds a 3-bit position");
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// One check of the walk as the kernel reads it: three broadcast 16-byte loads from the warp's record ring in
+// shared memory (fixed, short latency -- a record read from global memory sits on every step's critical path
+// and an L1 sector miss costs more than the whole step).
+struct LayerRecRegs {
+    uint4 a, b, c;   // var[0..3] | var[4..7] | desc[0..3], desc[4..7], dc + (copy-ahead mask << 8), pad
+    __device__ __forceinline__ void load(const LayerRec* rec) {
+        const uint4* r = reinterpret_cast<const uint4*>(rec);
+        a = r[0];
+        b = r[1];
+        c = r[2];
+    }
+    __device__ __forceinline__ uint32_t var(int k) const {
+        return k == 0 ? a.x : k == 1 ? a.y : k == 2 ? a.z : k == 3 ? a.w : k == 4 ? b.x : k == 5 ? b.y : k == 6 ? b.z : b.w;
+    }
+    __device__ __forceinline__ uint32_t fwd(int k) const { return ((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0x7fu; }
+    __device__ __forceinline__ int dc() const { return (int)(c.z & 0xffu); }
+    __device__ __forceinline__ uint32_t ahead_mask() const { return c.z >> 8; }
+};
+
+// reconstruction value of a magnitude: thr[last j >= 1 with mag >= thr[j]], thr[0] if none (rcq_decoder.py:76-84,
+// 100-121).  NTH > 0: the table sits in registers and "the last one that passes" is a chain of selects.
+template <int NTH>
+struct LayerQuant {
+    float t[NTH > 0 ? NTH : 1];
+    const float* s_thr;
+    int nth;
+    bool mono;
+    __device__ __forceinline__ void load(const float* s_thr_, int nth_, bool mono_) {
+        s_thr = s_thr_;
+        nth = nth_;
+        mono = mono_;
+        if constexpr (NTH > 0) {
+#pragma unroll
+            for (int j = 0; j < NTH; ++j) t[j] = (j < nth_) ? s_thr_[j] : __int_as_float(0x7fc00000);   // NaN never passes
+        }
+    }
+    __device__ __forceinline__ float value(float mag) const {
+        if constexpr (NTH > 0) {
+            float v = t[0];
+#pragma unroll
+            for (int j = 1; j < NTH; ++j) v = (mag >= t[j]) ? t[j] : v;
+            return v;
+        } else {
+            return s_thr[quant_index(mag, s_thr, nth, mono)];
+        }
+    }
+};
+
+constexpr uint32_t kLayerPosBytes = kLayerThreads * sizeof(float);          // one ring position, all threads
+constexpr uint32_t kLayerSlotBytes = kLayerMaxDeg * kLayerPosBytes;         // one check
+constexpr uint32_t kLayerRingBytes = kLayerDepth * kLayerSlotBytes;
+static_assert((kLayerDepth & (kLayerDepth - 1)) == 0, "ring offsets wrap with a mask");
+static_assert(kLayerSlotBytes == (8u << 9) && kLayerPosBytes == (1u << 9), "descriptor (distance << 3 | position) << 9 is a ring offset");
+
+// One check of degree DC: `col` is the thread's column of the ring, `sbase` the byte offset of the check's slot.
+template <int DC, int NTH>
+__device__ __forceinline__ void layer_step(const LayerRecRegs& r, float* __restrict__ Pf, bool live, uint32_t stride, char* col,
+                                           uint32_t sbase, const LayerQuant<NTH>& qz) {
+    float x[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) x[k] = *reinterpret_cast<const float*>(col + sbase + k * kLayerPosBytes);
+    MinState<float, false> st;
+    st.init();
+#pragma unroll
+    for (int k = 0; k < DC; ++k) st.push(x[k], k);
+    if (DC == 1) st.m2 = st.m1;
+    const float va = qz.value(st.m1), vb = qz.value(st.m2);
+    // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude; the
+    // reconstruction is then -value, i.e. the value with its sign bit flipped
+    const uint32_t a1 = __float_as_uint(va), a2 = __float_as_uint(vb);
+    const uint32_t g1 = st.m1 != 0.f ? 0x80000000u : 0u, g2 = st.m2 != 0.f ? 0x80000000u : 0u;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+        const bool is_min = fabsf(x[k]) == st.m1;
+        const uint32_t rec = (is_min ? a2 : a1) ^ ((st.par ^ __float_as_uint(x[k])) & (is_min ? g2 : g1));
+        const float out = __fadd_rn(x[k], __uint_as_float(rec));
+        if (live) *row_at(Pf, r.var(k), stride) = out;   // stopped frames keep their posteriors
+        const uint32_t fwd = r.fwd(k);   // next reader within the ring: (distance << 3) | position
+        if (fwd) *reinterpret_cast<float*>(col + ((sbase + (fwd << 9)) & (kLayerRingBytes - 1))) = out;
+    }
+}
+
+constexpr int kLayerRecAhead = 3 * kLayerDepth;   // a record is staged this many steps before its check is visited
+constexpr int kLayerRecRing = 4 * kLayerDepth;    // records per warp ring
+static_assert(kLayerRecAhead >= 2 * kLayerDepth + 1, "a staged record must have landed kLayerDepth steps before its check");
+static_assert(kLayerRecRing > kLayerRecAhead && (kLayerRecRing & (kLayerRecRing - 1)) == 0, "record ring");
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int NTH>
+__global__ void __launch_bounds__(kLayerThreads) layered_pipe_kernel(float* __restrict__ P, const LayerRec* __restrict__ recs,
+                                                                      int n_checks, const float* __restrict__ thr, int nth,
+                                                                      int mono, const uint8_t* __restrict__ done, int64_t Bp) {
+    __shared__ float s_thr[kMaxQuantLevels];
+    __shared__ __align__(16) float s_ring[kLayerDepth][kLayerMaxDeg][kLayerThreads];
+    __shared__ __align__(16) LayerRec s_recs[kLayerThreads / 32][kLayerRecRing];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
+    __syncthreads();
+    // A warp walks as long as one of its frames runs; lanes of stopped frames walk along (the warp stages its
+    // records cooperatively) but never write a posterior.
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = f < Bp && !done[f < Bp ? f : 0];
+    if (!__any_sync(0xffffffffu, live)) return;
+    if (f >= Bp) f = Bp - 1;
+    const int lane = threadIdx.x & 31;
+    LayerRec* const wrecs = s_recs[threadIdx.x >> 5];
+    LayerQuant<NTH> qz;
+    qz.load(s_thr, nth, mono != 0);
+    float* const Pf = P + f;
+    const uint32_t stride = (uint32_t)Bp * (uint32_t)sizeof(float);
+    char* const col = reinterpret_cast<char*>(&s_ring[0][0][threadIdx.x]);
+    // the copies of a check that may be issued ahead of time, into the slot at byte offset sbase
+    auto fetch = [&](const LayerRecRegs& r, uint32_t sbase) {
+        const uint32_t mask = r.ahead_mask();
+#pragma unroll
+        for (int k = 0; k < kLayerMaxDeg; ++k)
+            if (mask & (1u << k))
+                cp_async_f32(reinterpret_cast<float*>(col + sbase + k * kLayerPosBytes), row_at(Pf, r.var(k), stride));
+    };
+    // records 0 .. kLayerRecAhead-1 synchronously, 16 bytes per lane and turn
+    {
+        const int chunks = min(kLayerRecAhead, n_checks) * 3;
+        const uint4* src = reinterpret_cast<const uint4*>(recs);
+        uint4* dst = reinterpret_cast<uint4*>(wrecs);
+        for (int c = lane; c < chunks; c += 32) dst[c] = __ldg(src + c);
+        __syncwarp();
+    }
+    for (int s = 0; s < kLayerDepth; ++s) {
+        if (s < n_checks) {
+            LayerRecRegs r;
+            r.load(wrecs + s);
+            fetch(r, (uint32_t)s * kLayerSlotBytes);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int s = 0; s < n_checks; ++s) {
+        // lanes 0..2 stage the record of check s + kLayerRecAhead; it belongs to this step's copy group, which has
+        // landed (wait_group below) 2 * kLayerDepth steps before anybody reads it, and the per-step __syncwarp
+        // publishes it to the other lanes
+        if (lane < 3 && s + kLayerRecAhead < n_checks)
+            cp_async_16(reinterpret_cast<uint4*>(wrecs + ((s + kLayerRecAhead) % kLayerRecRing)) + lane,
+                        reinterpret_cast<const uint4*>(recs + s + kLayerRecAhead) + lane);
+        LayerRecRegs cur, ahead;
+        cur.load(wrecs + (s % kLayerRecRing));
+        ahead.load(wrecs + ((s + kLayerDepth) % kLayerRecRing));   // used at the end of this step (if that check exists)
+        asm volatile("cp.async.wait_group %0;" ::"n"(kLayerDepth - 1) : "memory");   // the copies of check s have landed
+        __syncwarp();
+        const uint32_t sbase = ((uint32_t)s % kLayerDepth) * kLayerSlotBytes;
+        switch (cur.dc()) {   // warp-uniform
+            case 1: layer_step<1, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 2: layer_step<2, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 3: layer_step<3, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 4: layer_step<4, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 5: layer_step<5, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 6: layer_step<6, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 7: layer_step<7, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            default: layer_step<8, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+        }
+        if (s + kLayerDepth < n_checks) fetch(ahead, sbase);   // slot s is free again: check s + kLayerDepth moves in
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+}
+
 // The same schedule, level-parallel.  Checks are grouped into dependency LEVELS on the host (a check's level is one
 // above the highest level among the earlier checks it shares a variable with), so checks of one level touch
 // disjoint variables and every posterior still receives its updates in check-index order: running a level's
@@ -1076,6 +1264,19 @@ cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t
                                                                   Bp, (int)nfb);
     return cudaGetLastError();
 }
+
+cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
+                                const uint8_t* done, int64_t Bp, cudaStream_t stream) {
+    if (n_checks <= 0) return cudaSuccess;
+    const int threads = (int)(Bp < kLayerThreads ? Bp : kLayerThreads);
+    const unsigned grid = (unsigned)((Bp + threads - 1) / threads);
+    if (nth <= 4) layered_pipe_kernel<4><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+    else if (nth <= 8) layered_pipe_kernel<8><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+    else layered_pipe_kernel<0><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+    return cudaGetLastError();
+}
+
+int layered_pipe_depth() { return kLayerDepth; }
 
 cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t* chk_var, int32_t m, const float* thr,
                                 int nth, int bc, int mono, const uint8_t* done, int64_t Bp, cudaStream_t stream) {

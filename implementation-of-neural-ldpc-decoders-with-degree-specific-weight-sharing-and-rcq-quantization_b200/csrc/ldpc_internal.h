@@ -89,6 +89,21 @@ cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t*
 cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t* chk_var, const int32_t* level_chk,
                                  int n_checks, const float* thr, int nth, int mono, const uint8_t* done, int64_t Bp,
                                  cudaStream_t stream);
+// the whole iteration in index order, software-pipelined (see layered_pipe_kernel): one record per NON-EMPTY check.
+// desc[k] bits 6..0: (distance << 3 | position) of the next reader this edge's new value is forwarded to, 0 = none;
+// ahead_mask bit k: input k is copied ahead from its posterior row (nobody forwards it).  Positions >= dc hold 0.
+constexpr int kLayerMaxDeg = 8;
+struct alignas(16) LayerRec {
+    int32_t var[kLayerMaxDeg];
+    uint8_t desc[kLayerMaxDeg];
+    uint8_t dc;
+    uint8_t ahead_mask;
+    uint8_t pad[6];
+};
+static_assert(sizeof(LayerRec) == 48, "three 16-byte loads per check");
+cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
+                                const uint8_t* done, int64_t Bp, cudaStream_t stream);
+int layered_pipe_depth();   // ring depth the descriptors must be built for
 // hard decisions (P < 0) of every frame, bit-packed
 cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, int32_t n, int64_t Bp, cudaStream_t stream);
 cudaError_t launch_syndrome(const SynLaunch& p, cudaStream_t stream);

@@ -70,7 +70,9 @@ enum {
     LDPC_GRAPH_VAR_CLASSES = 4,   /* number of distinct variable degrees (incl. 0) */
     LDPC_GRAPH_MAX_DC = 5,
     LDPC_GRAPH_MAX_DV = 6,
-    LDPC_GRAPH_DEVICE = 7
+    LDPC_GRAPH_DEVICE = 7,
+    LDPC_GRAPH_LAYER_LEVELS = 8,  /* dependency levels of the checks in index order (layered schedule)        */
+    LDPC_GRAPH_LAYER_PIPED = 9    /* 1: the sequential layered walk runs software-pipelined (check degree <= 8) */
 };
 int ldpc_graph_query(const ldpc_graph *g, int what, int64_t *value);
 /* Test hook: message-slot id of every edge (check-major edge order in, slot out). */

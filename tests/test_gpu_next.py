@@ -148,3 +148,52 @@ def test_layered_level_parallel_equals_sequential(built_lib, monkeypatch):
     dec = L.RCQMinSumDecoder(chain, 3, 8, qp, max_iterations=4, layered=True)
     dec.decode(L.awgn_llr(chain.n, 64, 0.0, seed=1, llr_sign=-1))
     assert dec._engine(0).profile_read()["cn_launches"] == 4
+
+
+def test_layered_pipelined_walk_equals_plain_walk(built_lib, monkeypatch):
+    """Chain-structured code at full size ((16200,7200) shape, dual-diagonal parity: 9000 dependency levels): the
+    software-pipelined sequential walk (inputs copied ahead / forwarded through shared memory) must give exactly
+    the plain sequential kernel's decisions, flags, iteration counts -- frames stopping at different iterations,
+    a batch that is not a multiple of the CTA size."""
+    L = built_lib
+    T = 10
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    code = L.codes.dvbs2_shaped(max_iterations=T)
+    assert code.graph.query(0, 9) == 1 and code.graph.query(0, 8) > 8000
+    llr = torch.cat([L.awgn_llr(code.n, 333, snr, seed=80 + k, llr_sign=1) for k, snr in enumerate((2.0, 3.5, 5.0))])
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LDPC_LAYERED_PIPE", flag)
+        dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
+        outs.append(dec.decode(llr))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert len(set(outs[1][2].tolist())) > 2
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
+    """Small dense graphs: most variables are shared by checks fewer than a ring depth apart (forwarding at every
+    distance 1..7, several readers in a row, variables first read late in the walk), degree-1 and empty checks."""
+    from oracle import capi as O
+    from oracle.restatement import SparseGraph, quantizer_schedule
+    L = built_lib
+    rng = np.random.default_rng(500 + seed)
+    m, n = int(rng.integers(12, 60)), int(rng.integers(9, 40))
+    H = np.zeros((m, n), dtype=np.int64)
+    for i in range(m):
+        H[i, rng.choice(n, int(rng.integers(1, 9)), replace=False)] = 1
+    H[rng.integers(1, m - 1), :] = 0
+    T = int(rng.integers(2, 9))
+    code = L.LDPCCode(n, max(1, n - m), H, max_iterations=T)
+    assert code.graph.query(0, 9) == 1
+    llr = (3.0 * (1.0 + 1.1 * rng.standard_normal((257, n)))).astype(np.float32)
+    llr[rng.random(llr.shape) < 0.02] = 0.0
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
+    b, s, i = dec.decode(torch.from_numpy(llr).cuda())
+    thr = np.array([q.thresholds for q in dec.quantizers]).astype(np.float32)
+    ref = O.decode_layered_rcq(SparseGraph.from_dense(H), llr, T=T, bc=3, thresholds=thr,
+                               quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+    assert np.array_equal(s.cpu().numpy(), ref.success)

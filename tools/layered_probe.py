@@ -3,7 +3,7 @@ import sys, time, torch, numpy as np
 sys.path.insert(0, ".")
 import ldpc_b200 as L
 qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-for cname, layered, B in (("dvbs2", False, 32768), ("dvbs2", True, 32768), ("dvbs2", True, 131072), ("qc", False, 32768), ("qc", True, 32768)):
+for cname, layered, B in (("dvbs2", False, 32768), ("dvbs2", True, 8192), ("dvbs2", True, 32768), ("dvbs2", True, 65536), ("dvbs2", True, 131072), ("qc", False, 32768), ("qc", True, 32768)):
     code = L.codes.dvbs2_shaped(max_iterations=10) if cname == "dvbs2" else L.codes.qc_shaped(max_iterations=10)
     dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=10, layered=layered)
     llr = L.awgn_llr(code.n, B, 2.0, seed=1, llr_sign=-1)
