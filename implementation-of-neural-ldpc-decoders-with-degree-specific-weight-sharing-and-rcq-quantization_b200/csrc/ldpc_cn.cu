@@ -919,6 +919,9 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
 #ifndef LDPC_LAYER_DEPTH
 #define LDPC_LAYER_DEPTH 8
 #endif
+#ifndef LDPC_LAYER_CTA_SYNC
+#define LDPC_LAYER_CTA_SYNC 0
+#endif
 constexpr int kLayerDepth = LDPC_LAYER_DEPTH;
 constexpr int kLayerThreads = 128;
 static_assert(kLayerDepth >= 2 && kLayerDepth <= 16, "descriptor holds a 4-bit distance");
@@ -1032,7 +1035,11 @@ __global__ void __launch_bounds__(kLayerThreads) layered_pipe_kernel(float* __re
     // records cooperatively) but never write a posterior.
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = f < Bp && !done[f < Bp ? f : 0];
+#if LDPC_LAYER_CTA_SYNC
+    if (!__syncthreads_or(live)) return;
+#else
     if (!__any_sync(0xffffffffu, live)) return;
+#endif
     if (f >= Bp) f = Bp - 1;
     const int lane = threadIdx.x & 31;
     LayerRec* const wrecs = s_recs[threadIdx.x >> 5];
@@ -1076,7 +1083,11 @@ __global__ void __launch_bounds__(kLayerThreads) layered_pipe_kernel(float* __re
         cur.load(wrecs + (s % kLayerRecRing));
         ahead.load(wrecs + ((s + kLayerDepth) % kLayerRecRing));   // used at the end of this step (if that check exists)
         asm volatile("cp.async.wait_group %0;" ::"n"(kLayerDepth - 1) : "memory");   // the copies of check s have landed
+#if LDPC_LAYER_CTA_SYNC
+        __syncthreads();   // tuning build: the warps of a CTA visit a check together (their row segments are adjacent)
+#else
         __syncwarp();
+#endif
         const uint32_t sbase = ((uint32_t)s % kLayerDepth) * kLayerSlotBytes;
         switch (cur.dc()) {   // warp-uniform
             case 1: layer_step<1, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
