@@ -197,3 +197,9 @@ def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
                                quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
     assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
     assert np.array_equal(s.cpu().numpy(), ref.success)
+    # ragged batches (partly filled warps / CTAs, stopped lanes walking along) and repeated calls (the rings are
+    # filled asynchronously: a race would show as a run-to-run difference)
+    for B in (1, 31, 129):
+        for _ in range(3):
+            b2, s2, i2 = dec.decode(torch.from_numpy(llr[:B]).cuda())
+            assert np.array_equal(b2.cpu().numpy(), ref.bits[:B]) and np.array_equal(i2.cpu().numpy(), ref.iterations[:B])

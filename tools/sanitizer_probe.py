@@ -31,6 +31,8 @@ with torch.no_grad():
     d2._beta_table.fill_(0.8); d2._alpha_table.fill_(1.0)
 x = torch.cat([L.awgn_llr(c2.n, 500, s, seed=k, llr_sign=1) for k, s in enumerate((1.0, 2.5, 4.0))])
 d2(x); d2._engine(0).decode_device(x)
+# layered RCQ on a chain-structured code: software-pipelined walk (shared-memory rings, cp.async), frames that stop early
+L.RCQMinSumDecoder(c2, 3, 8, qp + [(7.0, 1.3)], max_iterations=9, layered=True).decode(x)
 cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
 fbe = torch.zeros(1500, dtype=torch.int32, device="cuda"); fit = torch.zeros_like(fbe)
 d2._engine(0).mc_round(2.5, 1500, seed=1, frame0=7, llr_sign=1, counters=cnt, frame_bit_errors=fbe, frame_iterations=fit)
