@@ -1137,10 +1137,19 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
         MinState<float, false> st[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) st[v].init();
-        for (int k = 0; k < dc; ++k) {
-            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride));
+        // eight rows in flight at a time (a row at a time leaves the check latency-bound: dc is 29/30 on the QC shape)
+        for (int k0 = 0; k0 < dc; k0 += 8) {
+            Pack<float, V> x[8];
 #pragma unroll
-            for (int v = 0; v < V; ++v) st[v].push(x.v[v], k);
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < dc)
+                    x[u] = *reinterpret_cast<const Pack<float, V>*>(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k0 + u), stride));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < dc) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) st[v].push(x[u].v[v], k0 + u);
+                }
         }
         float va[V], vb[V];
 #pragma unroll
@@ -1149,20 +1158,30 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
             va[v] = s_thr[qz.index(st[v].m1)];
             vb[v] = s_thr[qz.index(st[v].m2)];
         }
-        for (int k = 0; k < dc; ++k) {
-            float* ptr = row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride);
-            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(ptr);
-            Pack<float, V> out;
+        for (int k0 = 0; k0 < dc; k0 += 4) {
+            float* ptr[4];
+            Pack<float, V> x[4];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const bool is_min = fabsf(x.v[v]) == st[v].m1;
-                const float raw = is_min ? st[v].m2 : st[v].m1;
-                const float mag = is_min ? vb[v] : va[v];
-                // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude
-                const bool neg = (((st[v].par ^ __float_as_uint(x.v[v])) >> 31) != 0u) && (raw != 0.f);
-                out.v[v] = __fadd_rn(x.v[v], neg ? -mag : mag);
-            }
-            store_masked<float, V>(ptr, out, dmask);   // stopped frames keep their posteriors
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u < dc) {
+                    ptr[u] = row_at(P0, (uint32_t)__ldg(chk_var + e0 + k0 + u), stride);
+                    x[u] = *reinterpret_cast<const Pack<float, V>*>(ptr[u]);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u < dc) {
+                    Pack<float, V> out;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const bool is_min = fabsf(x[u].v[v]) == st[v].m1;
+                        const float raw = is_min ? st[v].m2 : st[v].m1;
+                        const float mag = is_min ? vb[v] : va[v];
+                        // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude
+                        const bool neg = (((st[v].par ^ __float_as_uint(x[u].v[v])) >> 31) != 0u) && (raw != 0.f);
+                        out.v[v] = __fadd_rn(x[u].v[v], neg ? -mag : mag);
+                    }
+                    store_masked<float, V>(ptr[u], out, dmask);   // stopped frames keep their posteriors
+                }
         }
     }
 }

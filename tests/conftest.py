@@ -56,7 +56,7 @@ def built_lib():
     return ldpc_b200
 
 
-FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc"]
+FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2"]
 
 
 def load_fullsize(case):

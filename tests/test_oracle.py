@@ -197,7 +197,7 @@ def test_next_rows_match_live_reference(stem, case, impl):
         assert np.array_equal(res.success, g["success"])
 
 
-@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc"])
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2"])
 def test_oracle_reproduces_fullsize_reference_vectors(case):
     """BASELINE's full code sizes: frames decoded by the LIVE reference (minutes per frame,
     tests/golden/make_golden_fullsize.py) against the C port -- bits, iterations, success, posteriors bit for bit."""
@@ -217,7 +217,9 @@ def test_oracle_reproduces_fullsize_reference_vectors(case):
     else:
         thr = z["thresholds"].astype(np.float32)
         kw = dict(T=T, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
-        if case.startswith("rcq"):
+        if case.startswith("rcq_layered"):
+            ref = O.decode_layered_rcq(og, x, **kw)
+        elif case.startswith("rcq"):
             ref = O.decode(og, x, mode=MODE_RCQ, **kw)
         else:
             dec = L.WeightedRCQDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], weight_sharing_type=1, max_iterations=T)
