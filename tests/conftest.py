@@ -56,7 +56,7 @@ def built_lib():
     return ldpc_b200
 
 
-FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2"]
+FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4"]
 
 
 def load_fullsize(case):
@@ -69,7 +69,10 @@ def load_fullsize(case):
     import ldpc_b200 as L
     z = np.load(path)
     T = int(z["T"])
-    code = L.codes.dvbs2_shaped(max_iterations=T) if case.endswith("dvbs2") else L.codes.qc_shaped(max_iterations=T)
+    if case.endswith("dvbs2_s4"):
+        code = L.codes.dvbs2_shaped(max_iterations=T, scale=4)
+    else:
+        code = L.codes.dvbs2_shaped(max_iterations=T) if case.endswith("dvbs2") else L.codes.qc_shaped(max_iterations=T)
     g = code.graph
     h = hashlib.sha256()
     h.update(np.ascontiguousarray(g.check_ptr).tobytes())

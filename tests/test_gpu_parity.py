@@ -221,7 +221,7 @@ def test_batch_equals_single_frames_and_host_equals_device(built_lib):
         assert torch.equal(b, B[f]) and torch.equal(p, P[f]) and i == int(I[f])
 
 
-@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2"])
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4"])
 def test_fullsize_reference_vectors(built_lib, case):
     """The CUDA path against frames decoded by the LIVE reference at BASELINE's full code sizes."""
     from conftest import fullsize_tables, load_fullsize
