@@ -922,6 +922,9 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
 #ifndef LDPC_LAYER_CTA_SYNC
 #define LDPC_LAYER_CTA_SYNC 0
 #endif
+#ifndef LDPC_LAYER_MIN_CTAS
+#define LDPC_LAYER_MIN_CTAS 1
+#endif
 constexpr int kLayerDepth = LDPC_LAYER_DEPTH;
 constexpr int kLayerThreads = 128;
 static_assert(kLayerDepth >= 2 && kLayerDepth <= 16, "descriptor holds a 4-bit distance");
@@ -1023,7 +1026,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 }
 
 template <int NTH>
-__global__ void __launch_bounds__(kLayerThreads) layered_pipe_kernel(float* __restrict__ P, const LayerRec* __restrict__ recs,
+__global__ void __launch_bounds__(kLayerThreads, LDPC_LAYER_MIN_CTAS) layered_pipe_kernel(float* __restrict__ P, const LayerRec* __restrict__ recs,
                                                                       int n_checks, const float* __restrict__ thr, int nth,
                                                                       int mono, const uint8_t* __restrict__ done, int64_t Bp) {
     __shared__ float s_thr[kMaxQuantLevels];
