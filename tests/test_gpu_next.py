@@ -203,3 +203,33 @@ def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
         for _ in range(3):
             b2, s2, i2 = dec.decode(torch.from_numpy(llr[:B]).cuda())
             assert np.array_equal(b2.cpu().numpy(), ref.bits[:B]) and np.array_equal(i2.cpu().numpy(), ref.iterations[:B])
+
+
+@pytest.mark.parametrize("m", [2, 3, 7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 32, 33, 57, 100])
+def test_layered_pipelined_walk_ring_boundaries(built_lib, m):
+    """Chains of m checks around the sizes of the kernel's rings (8 check slots, records staged 24 checks ahead into
+    a 32-record ring): dual-diagonal parity part plus random information columns, against the oracle."""
+    from oracle import capi as O
+    from oracle.restatement import SparseGraph, quantizer_schedule
+    L = built_lib
+    rng = np.random.default_rng(700 + m)
+    k = max(3, m)                                   # information variables
+    n = k + m
+    H = np.zeros((m, n), dtype=np.int64)
+    for i in range(m):
+        H[i, k + i] = 1                             # parity chain: check i touches p_i and p_{i-1}
+        if i:
+            H[i, k + i - 1] = 1
+        H[i, rng.choice(k, int(rng.integers(1, min(k, 6) + 1)), replace=False)] = 1
+    T = 6
+    code = L.LDPCCode(n, k, H, max_iterations=T)
+    assert code.graph.query(0, 9) == 1
+    llr = (4.0 * (1.0 + 0.9 * rng.standard_normal((200, n)))).astype(np.float32)
+    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
+    b, s, i = dec.decode(torch.from_numpy(llr).cuda())
+    thr = np.array([q.thresholds for q in dec.quantizers]).astype(np.float32)
+    ref = O.decode_layered_rcq(SparseGraph.from_dense(H), llr, T=T, bc=3, thresholds=thr,
+                               quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
+    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
+    assert np.array_equal(s.cpu().numpy(), ref.success)
