@@ -1,3 +1,6 @@
+"""One layered RCQ decode of B frames of the (16200,7200)-shaped chain code (ncu target for layered_pipe_kernel):
+    ncu --set full -k regex:layered_pipe -s 3 -c 1 python tools/layered_one.py 32768
+"""
 import sys, torch
 sys.path.insert(0, ".")
 import ldpc_b200 as L
