@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
 // shared memory, and the frame's other posteriors arrive kLayerDepth checks early.  The arithmetic per check is
 // the plain kernel's, on the same values in the same order.  Needs check degrees <= kLayerMaxDeg.
 #ifndef LDPC_LAYER_DEPTH
-#define LDPC_LAYER_DEPTH 8
+#define LDPC_LAYER_DEPTH 4
 #endif
 #ifndef LDPC_LAYER_CTA_SYNC
 #define LDPC_LAYER_CTA_SYNC 0
@@ -988,31 +988,49 @@ constexpr uint32_t kLayerRingBytes = kLayerDepth * kLayerSlotBytes;
 static_assert((kLayerDepth & (kLayerDepth - 1)) == 0, "ring offsets wrap with a mask");
 static_assert(kLayerSlotBytes == (8u << 9) && kLayerPosBytes == (1u << 9), "descriptor (distance << 3 | position) << 9 is a ring offset");
 
-// One check of degree DC: `col` is the thread's column of the ring, `sbase` the byte offset of the check's slot.
-template <int DC, int NTH>
-__device__ __forceinline__ void layer_step(const LayerRecRegs& r, float* __restrict__ Pf, bool live, uint32_t stride, char* col,
+// One check of degree DC for the V frames of a thread: `col` is the thread's column of the ring (V adjacent
+// floats per position), `sbase` the byte offset of the check's slot, bit v of `live` says frame v still runs.
+template <int DC, int NTH, int V>
+__device__ __forceinline__ void layer_step(const LayerRecRegs& r, float* __restrict__ Pf, uint32_t live, uint32_t stride, char* col,
                                            uint32_t sbase, const LayerQuant<NTH>& qz) {
-    float x[DC];
+    Pack<float, V> x[DC];
 #pragma unroll
-    for (int k = 0; k < DC; ++k) x[k] = *reinterpret_cast<const float*>(col + sbase + k * kLayerPosBytes);
-    MinState<float, false> st;
-    st.init();
+    for (int k = 0; k < DC; ++k) x[k] = *reinterpret_cast<const Pack<float, V>*>(col + sbase + k * kLayerPosBytes);
+    MinState<float, false> st[V];
+    uint32_t a1[V], a2[V], g1[V], g2[V];
 #pragma unroll
-    for (int k = 0; k < DC; ++k) st.push(x[k], k);
-    if (DC == 1) st.m2 = st.m1;
-    const float va = qz.value(st.m1), vb = qz.value(st.m2);
-    // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude; the
-    // reconstruction is then -value, i.e. the value with its sign bit flipped
-    const uint32_t a1 = __float_as_uint(va), a2 = __float_as_uint(vb);
-    const uint32_t g1 = st.m1 != 0.f ? 0x80000000u : 0u, g2 = st.m2 != 0.f ? 0x80000000u : 0u;
+    for (int v = 0; v < V; ++v) {
+        st[v].init();
+#pragma unroll
+        for (int k = 0; k < DC; ++k) st[v].push(x[k].v[v], k);
+        if (DC == 1) st[v].m2 = st[v].m1;
+        // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude; the
+        // reconstruction is then -value, i.e. the value with its sign bit flipped
+        a1[v] = __float_as_uint(qz.value(st[v].m1));
+        a2[v] = __float_as_uint(qz.value(st[v].m2));
+        g1[v] = st[v].m1 != 0.f ? 0x80000000u : 0u;
+        g2[v] = st[v].m2 != 0.f ? 0x80000000u : 0u;
+    }
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
-        const bool is_min = fabsf(x[k]) == st.m1;
-        const uint32_t rec = (is_min ? a2 : a1) ^ ((st.par ^ __float_as_uint(x[k])) & (is_min ? g2 : g1));
-        const float out = __fadd_rn(x[k], __uint_as_float(rec));
-        if (live) *row_at(Pf, r.var(k), stride) = out;   // stopped frames keep their posteriors
+        Pack<float, V> out;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const bool is_min = fabsf(x[k].v[v]) == st[v].m1;
+            const uint32_t rec = (is_min ? a2[v] : a1[v]) ^ ((st[v].par ^ __float_as_uint(x[k].v[v])) & (is_min ? g2[v] : g1[v]));
+            out.v[v] = __fadd_rn(x[k].v[v], __uint_as_float(rec));
+        }
+        // stopped frames keep their posteriors
+        float* row = row_at(Pf, r.var(k), stride);
+        if (V == 1 || live == (1u << V) - 1u) {
+            if (live) *reinterpret_cast<Pack<float, V>*>(row) = out;
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if ((live >> v) & 1u) row[v] = out.v[v];
+        }
         const uint32_t fwd = r.fwd(k);   // next reader within the ring: (distance << 3) | position
-        if (fwd) *reinterpret_cast<float*>(col + ((sbase + (fwd << 9)) & (kLayerRingBytes - 1))) = out;
+        if (fwd) *reinterpret_cast<Pack<float, V>*>(col + ((sbase + (fwd << 9)) & (kLayerRingBytes - 1))) = out;
     }
 }
 
@@ -1025,39 +1043,52 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-template <int NTH>
-__global__ void __launch_bounds__(kLayerThreads, LDPC_LAYER_MIN_CTAS) layered_pipe_kernel(float* __restrict__ P, const LayerRec* __restrict__ recs,
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8, "cp.async.ca size");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+
+// V frames per thread (kLayerThreads / V threads per CTA: a CTA always owns kLayerThreads frames, so the ring
+// geometry does not depend on V).  V = 2 amortises the warp-uniform work of a step (records, addresses, predicates)
+// over two frames and gives every thread two independent dependency chains; it pays once the batch is large
+// enough to fill the machine with half the warps.
+template <int NTH, int V>
+__global__ void __launch_bounds__(kLayerThreads / V, LDPC_LAYER_MIN_CTAS) layered_pipe_kernel(float* __restrict__ P, const LayerRec* __restrict__ recs,
                                                                       int n_checks, const float* __restrict__ thr, int nth,
                                                                       int mono, const uint8_t* __restrict__ done, int64_t Bp) {
     __shared__ float s_thr[kMaxQuantLevels];
     __shared__ __align__(16) float s_ring[kLayerDepth][kLayerMaxDeg][kLayerThreads];
-    __shared__ __align__(16) LayerRec s_recs[kLayerThreads / 32][kLayerRecRing];
+    __shared__ __align__(16) LayerRec s_recs[kLayerThreads / V / 32][kLayerRecRing];
     for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
     __syncthreads();
     // A warp walks as long as one of its frames runs; lanes of stopped frames walk along (the warp stages its
     // records cooperatively) but never write a posterior.
-    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = f < Bp && !done[f < Bp ? f : 0];
+    int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    uint32_t live = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (f + v < Bp && !done[f + v]) live |= 1u << v;
 #if LDPC_LAYER_CTA_SYNC
-    if (!__syncthreads_or(live)) return;
+    if (!__syncthreads_or(live != 0)) return;
 #else
-    if (!__any_sync(0xffffffffu, live)) return;
+    if (!__any_sync(0xffffffffu, live != 0)) return;
 #endif
-    if (f >= Bp) f = Bp - 1;
+    if (f + V > Bp) f = Bp - V;   // (Bp is a multiple of the CTA's frame count; such a lane has live == 0)
     const int lane = threadIdx.x & 31;
     LayerRec* const wrecs = s_recs[threadIdx.x >> 5];
     LayerQuant<NTH> qz;
     qz.load(s_thr, nth, mono != 0);
     float* const Pf = P + f;
     const uint32_t stride = (uint32_t)Bp * (uint32_t)sizeof(float);
-    char* const col = reinterpret_cast<char*>(&s_ring[0][0][threadIdx.x]);
+    char* const col = reinterpret_cast<char*>(&s_ring[0][0][threadIdx.x * V]);
     // the copies of a check that may be issued ahead of time, into the slot at byte offset sbase
     auto fetch = [&](const LayerRecRegs& r, uint32_t sbase) {
         const uint32_t mask = r.ahead_mask();
 #pragma unroll
         for (int k = 0; k < kLayerMaxDeg; ++k)
             if (mask & (1u << k))
-                cp_async_f32(reinterpret_cast<float*>(col + sbase + k * kLayerPosBytes), row_at(Pf, r.var(k), stride));
+                cp_async_small<4 * V>(col + sbase + k * kLayerPosBytes, row_at(Pf, r.var(k), stride));
     };
     // records 0 .. kLayerRecAhead-1 synchronously, 16 bytes per lane and turn
     {
@@ -1093,14 +1124,14 @@ __global__ void __launch_bounds__(kLayerThreads, LDPC_LAYER_MIN_CTAS) layered_pi
 #endif
         const uint32_t sbase = ((uint32_t)s % kLayerDepth) * kLayerSlotBytes;
         switch (cur.dc()) {   // warp-uniform
-            case 1: layer_step<1, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 2: layer_step<2, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 3: layer_step<3, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 4: layer_step<4, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 5: layer_step<5, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 6: layer_step<6, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            case 7: layer_step<7, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
-            default: layer_step<8, NTH>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 1: layer_step<1, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 2: layer_step<2, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 3: layer_step<3, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 4: layer_step<4, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 5: layer_step<5, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 6: layer_step<6, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            case 7: layer_step<7, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
+            default: layer_step<8, NTH, V>(cur, Pf, live, stride, col, sbase, qz); break;
         }
         if (s + kLayerDepth < n_checks) fetch(ahead, sbase);   // slot s is free again: check s + kLayerDepth moves in
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1298,15 +1329,26 @@ cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
-                                const uint8_t* done, int64_t Bp, cudaStream_t stream) {
-    if (n_checks <= 0) return cudaSuccess;
-    const int threads = (int)(Bp < kLayerThreads ? Bp : kLayerThreads);
-    const unsigned grid = (unsigned)((Bp + threads - 1) / threads);
-    if (nth <= 4) layered_pipe_kernel<4><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
-    else if (nth <= 8) layered_pipe_kernel<8><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
-    else layered_pipe_kernel<0><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+namespace {
+template <int V>
+cudaError_t launch_layered_pipe_v(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
+                                  const uint8_t* done, int64_t Bp, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((Bp + kLayerThreads - 1) / kLayerThreads);
+    const int threads = kLayerThreads / V;
+    if (nth <= 4) layered_pipe_kernel<4, V><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+    else if (nth <= 8) layered_pipe_kernel<8, V><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
+    else layered_pipe_kernel<0, V><<<grid, threads, 0, stream>>>(P, recs, n_checks, thr, nth, mono, done, Bp);
     return cudaGetLastError();
+}
+}  // namespace
+
+// frames_per_thread: 1 or 2 (Bp must be a multiple of kLayerThreads, which the workspace padding guarantees)
+cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
+                                const uint8_t* done, int64_t Bp, int frames_per_thread, cudaStream_t stream) {
+    if (n_checks <= 0) return cudaSuccess;
+    if (Bp % kLayerThreads != 0) return cudaErrorInvalidValue;
+    return frames_per_thread == 2 ? launch_layered_pipe_v<2>(P, recs, n_checks, thr, nth, mono, done, Bp, stream)
+                                  : launch_layered_pipe_v<1>(P, recs, n_checks, thr, nth, mono, done, Bp, stream);
 }
 
 int layered_pipe_depth() { return kLayerDepth; }

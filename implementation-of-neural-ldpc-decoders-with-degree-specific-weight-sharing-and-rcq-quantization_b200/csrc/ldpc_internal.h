@@ -102,7 +102,7 @@ struct alignas(16) LayerRec {
 };
 static_assert(sizeof(LayerRec) == 48, "three 16-byte loads per check");
 cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
-                                const uint8_t* done, int64_t Bp, cudaStream_t stream);
+                                const uint8_t* done, int64_t Bp, int frames_per_thread, cudaStream_t stream);
 int layered_pipe_depth();   // ring depth the descriptors must be built for
 // hard decisions (P < 0) of every frame, bit-packed
 cudaError_t launch_hard(int dtype, const void* P, uint32_t* hardw, int64_t Wn, int32_t n, int64_t Bp, cudaStream_t stream);

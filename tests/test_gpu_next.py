@@ -162,17 +162,19 @@ def test_layered_pipelined_walk_equals_plain_walk(built_lib, monkeypatch):
     assert code.graph.query(0, 9) == 1 and code.graph.query(0, 8) > 8000
     llr = torch.cat([L.awgn_llr(code.n, 333, snr, seed=80 + k, llr_sign=1) for k, snr in enumerate((2.0, 3.5, 5.0))])
     outs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("LDPC_LAYERED_PIPE", flag)
+    for pipe, v2_from in (("0", "0"), ("1", "0"), ("1", "128")):   # plain walk | pipelined | pipelined, two frames per thread
+        monkeypatch.setenv("LDPC_LAYERED_PIPE", pipe)
+        monkeypatch.setenv("LDPC_LAYERED_V2_FRAMES", v2_from)
         dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
         outs.append(dec.decode(llr))
-    for a, b in zip(outs[0], outs[1]):
-        assert torch.equal(a, b)
+    for k in (1, 2):
+        for a, b in zip(outs[0], outs[k]):
+            assert torch.equal(a, b)
     assert len(set(outs[1][2].tolist())) > 2
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
+def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, monkeypatch, seed):
     """Small dense graphs: most variables are shared by checks fewer than a ring depth apart (forwarding at every
     distance 1..7, several readers in a row, variables first read late in the walk), degree-1 and empty checks."""
     from oracle import capi as O
@@ -190,6 +192,7 @@ def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
     llr = (3.0 * (1.0 + 1.1 * rng.standard_normal((257, n)))).astype(np.float32)
     llr[rng.random(llr.shape) < 0.02] = 0.0
     qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
+    monkeypatch.setenv("LDPC_LAYERED_V2_FRAMES", "128" if seed % 2 else "0")    # odd seeds: two frames per thread
     dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
     b, s, i = dec.decode(torch.from_numpy(llr).cuda())
     thr = np.array([q.thresholds for q in dec.quantizers]).astype(np.float32)
@@ -206,7 +209,7 @@ def test_layered_pipelined_walk_dense_overlaps_vs_oracle(built_lib, seed):
 
 
 @pytest.mark.parametrize("m", [2, 3, 7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 32, 33, 57, 100])
-def test_layered_pipelined_walk_ring_boundaries(built_lib, m):
+def test_layered_pipelined_walk_ring_boundaries(built_lib, monkeypatch, m):
     """Chains of m checks around the sizes of the kernel's rings (8 check slots, records staged 24 checks ahead into
     a 32-record ring): dual-diagonal parity part plus random information columns, against the oracle."""
     from oracle import capi as O
@@ -226,10 +229,14 @@ def test_layered_pipelined_walk_ring_boundaries(built_lib, m):
     assert code.graph.query(0, 9) == 1
     llr = (4.0 * (1.0 + 0.9 * rng.standard_normal((200, n)))).astype(np.float32)
     qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-    dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
-    b, s, i = dec.decode(torch.from_numpy(llr).cuda())
-    thr = np.array([q.thresholds for q in dec.quantizers]).astype(np.float32)
-    ref = O.decode_layered_rcq(SparseGraph.from_dense(H), llr, T=T, bc=3, thresholds=thr,
-                               quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
-    assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations)
-    assert np.array_equal(s.cpu().numpy(), ref.success)
+    ref = None
+    for v2_from in ("0", "128"):          # one frame per thread | two frames per thread (normally from 65 536 frames on)
+        monkeypatch.setenv("LDPC_LAYERED_V2_FRAMES", v2_from)
+        dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=T, layered=True)
+        b, s, i = dec.decode(torch.from_numpy(llr).cuda())
+        if ref is None:
+            thr = np.array([q.thresholds for q in dec.quantizers]).astype(np.float32)
+            ref = O.decode_layered_rcq(SparseGraph.from_dense(H), llr, T=T, bc=3, thresholds=thr,
+                                       quantizer_of_iter=quantizer_schedule(T, 3), nthreads=4)
+        assert np.array_equal(b.cpu().numpy(), ref.bits) and np.array_equal(i.cpu().numpy(), ref.iterations), v2_from
+        assert np.array_equal(s.cpu().numpy(), ref.success), v2_from
