@@ -905,10 +905,10 @@ __global__ void __launch_bounds__(kThreads) layered_iter_kernel(float* __restric
     }
 }
 
-// The same sequential walk, software-pipelined.  A thread still owns one frame and visits the checks in index
+// The same sequential walk, software-pipelined.  A thread still owns its frame(s) and visits the checks in index
 // order, but the walk no longer waits for DRAM once per check: every input of check s comes out of the thread's
 // own column of a shared-memory ring of kLayerDepth check slots.  The host classifies every edge (s, k) of the
-// walk (ldpc_graph_create, `lay_desc`):
+// walk (ldpc_graph_create, `LayerRec`):
 //   * no check in (s - kLayerDepth, s) touches its variable  -> the posterior is copied global -> ring by a
 //     per-thread cp.async issued kLayerDepth checks ahead (nothing writes the value in between);
 //   * otherwise the latest such check j FORWARDS the value it writes to the posterior row into ring slot s as well
@@ -929,10 +929,6 @@ constexpr int kLayerDepth = LDPC_LAYER_DEPTH;
 constexpr int kLayerThreads = 128;
 static_assert(kLayerDepth >= 2 && kLayerDepth <= 16, "descriptor holds a 4-bit distance");
 static_assert(kLayerMaxDeg == 8, "descriptor holds a 3-bit position");
-
-__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
-}
 
 // One check of the walk as the kernel reads it: three broadcast 16-byte loads from the warp's record ring in
 // shared memory (fixed, short latency -- a record read from global memory sits on every step's critical path
