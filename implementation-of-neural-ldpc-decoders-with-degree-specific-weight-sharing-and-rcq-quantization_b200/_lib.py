@@ -10,7 +10,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # LDPC_B200_LIB selects a tuning build of the same library (csrc/build.py variant ...); default: the in-tree build
-LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(PKG_DIR, "libldpc_b200.so")
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(os.path.dirname(PKG_DIR), "ldpc_b200", "libldpc_b200.so")
 
 LDPC_OK, LDPC_ERR_INVALID, LDPC_ERR_CUDA, LDPC_ERR_NOMEM, LDPC_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 LDPC_F32, LDPC_F64 = 0, 1

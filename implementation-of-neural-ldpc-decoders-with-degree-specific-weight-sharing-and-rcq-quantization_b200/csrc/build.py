@@ -1,4 +1,7 @@
-"""In-tree build of the CUDA library: nvcc -> ../libldpc_b200.so (sm_100a only, no torch headers)."""
+"""In-tree build of the CUDA library: nvcc -> <repo>/ldpc_b200/libldpc_b200.so (sm_100a only, no torch headers).
+
+The library lives next to the short import alias (``ldpc_b200/``) rather than inside the package directory:
+its path then stays short enough for every tool that lists the shared objects a process has mapped."""
 from __future__ import annotations
 
 import os
@@ -11,14 +14,17 @@ SOURCES = [os.path.join(HERE, f) for f in ("ldpc_cn.cu", "ldpc_vn.cu", "ldpc_mis
 HEADERS = [os.path.join(HERE, "ldpc_device.cuh"), os.path.join(HERE, "ldpc_kernel_common.cuh"),
            os.path.join(HERE, "ldpc_internal.h"), os.path.join(os.path.dirname(PKG), "include", "ldpc_b200.h")]
 OBJDIR = os.path.join(HERE, "build")
-OUT = os.path.join(PKG, "libldpc_b200.so")
+OUT = os.path.join(os.path.dirname(PKG), "ldpc_b200", "libldpc_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",               # parity: llr + alpha*s and beta*raw round the product first
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
 ]
-LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+# the CUDA runtime is linked dynamically (the image's libcudart.so.12; a process that imported torch first shares
+# torch's copy): the shipped artefact then carries no runtime symbol table of its own
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared",
+              "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
 
 
 def nvcc_path() -> str:

@@ -49,7 +49,7 @@ class Golden:
 def built_lib():
     """The in-tree CUDA library (built on demand where nvcc exists; on the GPU box it is prebuilt)."""
     import __graft_entry__ as ge
-    pkg_lib = os.path.join(ROOT, ge.PKG, "libldpc_b200.so")
+    pkg_lib = os.path.join(ROOT, "ldpc_b200", "libldpc_b200.so")
     if not os.path.exists(pkg_lib):
         ge.build()
     import ldpc_b200

@@ -1,6 +1,8 @@
-"""Small end-to-end exercise of every kernel family, meant to run under compute-sanitizer:
-    compute-sanitizer --tool memcheck python tools/sanitizer_probe.py
-"""
+"""Small end-to-end exercise of every kernel family on ragged sizes (wide checks / variables, tiny batches,
+compaction, the Monte-Carlo round), each result compared with the oracle:
+    python tools/sanitizer_probe.py
+compute-sanitizer is closed on this GPU pool (gpurun refuses it), so out-of-bounds accesses are hunted with
+small ragged cases like these plus the oracle comparison, not with the sanitizer."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
