@@ -17,7 +17,7 @@ LDPC_F32, LDPC_F64 = 0, 1
 RULE_NORMALIZED, RULE_OFFSET = 0, 1
 SCHEDULE_FLOODING, SCHEDULE_LAYERED = 0, 1
 (GRAPH_N, GRAPH_M, GRAPH_E, GRAPH_CHECK_CLASSES, GRAPH_VAR_CLASSES, GRAPH_MAX_DC, GRAPH_MAX_DV,
- GRAPH_DEVICE) = range(8)
+ GRAPH_DEVICE, GRAPH_LAYER_LEVELS, GRAPH_LAYER_PIPED) = range(10)
 
 # every symbol include/ldpc_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .engine import Engine, default_device
+from .engine import Engine, EngineCache, default_device
 
 
 class WeightView(Mapping):
@@ -36,6 +36,14 @@ class WeightView(Mapping):
     def __contains__(self, key) -> bool:
         return key in self._index
 
+    def position(self, key: str) -> Optional[Tuple[int, int]]:
+        """(row, column) of ``key`` in the table, or None."""
+        return self._index.get(key)
+
+    def items_index(self):
+        """(key, (row, column)) in the reference's creation order."""
+        return ((k, self._index[k]) for k in self._keys)
+
 
 def seeded_normal(count: int, scale: float, shift: float) -> torch.Tensor:
     """``count`` draws of ``torch.randn(1) * scale + shift`` in call order.  Up to 2^17 draws are
@@ -51,7 +59,7 @@ def seeded_normal(count: int, scale: float, shift: float) -> torch.Tensor:
     return out * scale + shift
 
 
-class DecoderModule(nn.Module):
+class DecoderModule(EngineCache, nn.Module):
     """Base of the nn.Module decoders.  Subclasses fill:
          self._beta_table / self._alpha_table : nn.Parameter [T, W] or None
          self._beta_index [E] / self._alpha_index [n] : int32 column maps (numpy) or None
@@ -63,46 +71,71 @@ class DecoderModule(nn.Module):
         self.max_iterations = max_iterations
         self._engines = {}
         self._pushed = {}
+        # state_dict() / load_state_dict() speak the reference's ParameterDict layout (see the hooks below)
+        self._register_state_dict_hook(_export_reference_keys)
+        self._register_load_state_dict_pre_hook(_import_reference_keys, with_module=True)
 
     # ---- quantiser hooks (overridden by the RCQ classes) ----
     def _quant_config(self):
         return 0, None, None
 
     def _tables(self):
+        """float32 host copies of the weight tables, cut to the current ``max_iterations`` rows.  The reference
+        reads ``max_iterations`` at call time and looks its weights up by key: fewer iterations than the tables
+        hold simply use the first rows, more fail with the missing key."""
         T = self.max_iterations
+
+        def rows(table):
+            if table.shape[0] < T:
+                raise KeyError(f"iter_{table.shape[0]}_...: the decoder was built with {table.shape[0]} iterations of "
+                               f"weights, max_iterations is now {T}")
+            return np.ascontiguousarray(table.detach().cpu().numpy()[:T], dtype=np.float32)
+
         beta = self._beta_table
         if beta is not None:
-            b = beta.detach().cpu().numpy().astype(np.float32)
+            b = rows(beta)
         elif getattr(self, "_beta_const", None) is not None:
             b = np.full((T, 1), np.float32(self._beta_const), dtype=np.float32)
         else:
             b = None
         alpha = self._alpha_table
-        a = alpha.detach().cpu().numpy().astype(np.float32) if alpha is not None else None
+        a = rows(alpha) if alpha is not None else None
         return b, a
 
-    def _versions(self):
-        return tuple((p._version, p.data_ptr()) if p is not None else None
-                     for p in (self._beta_table, self._alpha_table))
+    def _engine_key(self, device: int):
+        bc, thr, _ = self._quant_config()
+        return (device, int(self.max_iterations), int(bc), thr.tobytes() if thr is not None else None)
 
     def _engine(self, device: int) -> Engine:
+        """The device engine for the module's CURRENT configuration.  Everything the reference reads at call time is
+        re-read here: ``max_iterations``, ``bc`` and the quantiser thresholds select the engine, and the weight
+        tables are compared BY CONTENT with what the device holds (in-place edits through ``param.data`` or a numpy
+        alias do not bump a tensor's version counter), and pushed again when they differ."""
         if self.max_iterations < 1:
             raise ValueError("max_iterations must be >= 1")
-        eng = self._engines.get(device)
+        key = self._engine_key(device)
+        b, a = self._tables()
+        eng = self._engines.get(key)
         if eng is None:
-            b, a = self._tables()
             bc, thr, qoi = self._quant_config()
             eng = Engine(self.code.graph, dtype=np.float32, max_iterations=self.max_iterations,
                          beta=b, beta_index=self._beta_index if self._beta_table is not None else None,
                          alpha=a, alpha_index=self._alpha_index if a is not None else None,
                          bc=bc, thresholds=thr, quantizer_of_iter=qoi,
                          check_rule=getattr(self, "_check_rule", 0), device=device)
-            self._engines[device] = eng
-            self._pushed[device] = self._versions()
-        elif self._pushed[device] != self._versions():
-            b, a = self._tables()
-            eng.set_weights(b if self._beta_table is not None else None, a)
-            self._pushed[device] = self._versions()
+            # one engine per device: a changed configuration replaces it (its workspace goes with it)
+            for old in [k for k in self._engines if k[0] == device]:
+                self._engines.pop(old).close()
+                self._pushed.pop(old, None)
+            self._engines[key] = eng
+            self._pushed[key] = (b, a)
+        else:
+            pb, pa = self._pushed[key]
+            new_b = b is not None and self._beta_table is not None and not np.array_equal(b, pb)
+            new_a = a is not None and not np.array_equal(a, pa)
+            if new_b or new_a:
+                eng.set_weights(b if new_b else None, a if new_a else None)
+                self._pushed[key] = (b, a)
         return eng
 
     def _run(self, llr, want_posterior: bool):
@@ -159,6 +192,55 @@ class DecoderModule(nn.Module):
             missing = [k for k in self.reference_state_dict() if k not in seen]
             if missing:
                 raise KeyError(f"missing keys: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+
+
+def _weight_views(module):
+    for name, table_name in (("beta_weights", "_beta_table"), ("alpha_weights", "_alpha_table")):
+        view = getattr(module, name, None)
+        if isinstance(view, WeightView) and getattr(module, table_name, None) is not None:
+            yield name, table_name, view
+
+
+def _export_reference_keys(module, state_dict, prefix, local_metadata):
+    """state_dict() hook: replace the dense tables by the reference's ``ParameterDict`` entries
+    (``beta_weights.iter_0_dc3`` ... each a shape-[1] tensor sharing storage with the table, in the reference's
+    creation order), so that ``reference_module.load_state_dict(ours.state_dict())`` works
+    (neural_2d_decoder.py:46-82, neural_minsum_decoder.py:47-53, rcq_decoder.py:398-431)."""
+    for name, table_name, view in _weight_views(module):
+        table = state_dict.pop(prefix + table_name, None)
+        if table is None:
+            continue
+        for key, (t, c) in view.items_index():
+            state_dict[f"{prefix}{name}.{key}"] = table[t, c:c + 1]
+    return state_dict
+
+
+def _import_reference_keys(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """load_state_dict() pre-hook: fold ``beta_weights.<key>`` / ``alpha_weights.<key>`` entries (a reference
+    module's state_dict, or our own) into the dense tables.  Unknown keys stay in ``state_dict`` and are reported
+    as unexpected; absent ones are reported as missing (both only matter under ``strict``).  The native
+    ``_beta_table`` / ``_alpha_table`` entries are accepted as well."""
+    for name, table_name, view in _weight_views(module):
+        head = f"{prefix}{name}."
+        keys = [k for k in state_dict if k.startswith(head)]
+        if not keys:
+            continue
+        table = getattr(module, table_name).detach().clone()
+        seen = 0
+        for full in keys:
+            pos = view.position(full[len(head):])
+            if pos is None:
+                continue                      # unexpected: left for load_state_dict to report
+            value = torch.as_tensor(state_dict.pop(full))
+            if value.numel() != 1:
+                error_msgs.append(f"size mismatch for {full}: expected one element, got {tuple(value.shape)}")
+                continue
+            table[pos[0], pos[1]] = value.reshape(()).to(table.dtype)
+            seen += 1
+        if seen != len(view):
+            have = {full[len(head):] for full in keys}
+            missing_keys.extend(f"{head}{k}" for k in view if k not in have)
+        state_dict[prefix + table_name] = table
 
 
 def degree_lists(code):

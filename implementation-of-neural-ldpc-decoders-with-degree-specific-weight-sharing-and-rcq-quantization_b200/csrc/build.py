@@ -8,7 +8,7 @@ import os
 import shutil
 import subprocess
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.dirname(os.path.realpath(__file__))
 PKG = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, f) for f in ("ldpc_cn.cu", "ldpc_vn.cu", "ldpc_misc.cu", "ldpc_api.cu")]
 HEADERS = [os.path.join(HERE, "ldpc_device.cuh"), os.path.join(HERE, "ldpc_kernel_common.cuh"),

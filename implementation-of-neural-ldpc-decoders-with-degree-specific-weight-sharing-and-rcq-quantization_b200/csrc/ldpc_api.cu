@@ -498,8 +498,14 @@ struct ldpc_decoder {
         int32_t* d_scan = nullptr;    // [scan_cap] per-block counts / offsets
         int64_t scan_cap = 0;
         int32_t* d_total = nullptr;   // device int32
-        int32_t* h_total = nullptr;   // pinned host int32
-        cudaEvent_t ev = nullptr;     // recorded after a checkpoint's count has been copied to h_total
+        // two checkpoints may be outstanding (the host decides one span late): slot = checkpoint number & 1
+        int32_t* h_total = nullptr;            // pinned host int32[2]
+        cudaEvent_t ev[2] = {nullptr, nullptr};   // recorded after a checkpoint's count has been copied to h_total[slot]
+        // end of the last call that used this context, and the stream it ran on: a call on ANOTHER stream first
+        // waits for it (the workspace is shared), and so does a weight update
+        cudaEvent_t tail = nullptr;
+        cudaStream_t tail_stream = nullptr;
+        bool tail_valid = false;
     };
     Ctx cx[3];
     // launch-bound decodes (tiny codes / tiny batches): the whole T-iteration launch sequence is captured once
@@ -523,6 +529,8 @@ struct ldpc_decoder {
     int64_t compact_min_frames = 512;
     int compact_percent = 60;     // compact when at most this share of the level's lanes still runs
     int checkpoint_step = 1;      // iterations between checkpoints for batches of >= 16384 frames
+    int speculate = 0;            // LDPC_SPECULATE=1: keep a second span in flight while the host waits for a checkpoint (see DecodeJob)
+    int post_mode = 0;            // LDPC_POST_MODE: 0 adaptive, 1 posterior rows refreshed every iteration, 2 written on stop
     int64_t stat_compactions = 0, stat_early_exits = 0;
     // instrumentation
     int prof_mode = 0;
@@ -707,6 +715,8 @@ void fill_cn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, CnLaunch& cn) {
 
 void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass, bool want_post, VnLaunch& vn) {
     const ldpc_graph* g = d->g;
+    vn.iters = ws.iters;
+    vn.post_iter = 0;
     vn.c2v = ws.c2v;
     vn.v2c = ws.v2c;
     vn.llrT = ws.llrT;
@@ -734,11 +744,22 @@ void fill_vn(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t, bool final_pass,
     vn.wide_stage = d->wide_ring;
 }
 
+// How forward()'s posterior rows ws.post are kept.  Invariant after every iteration of either mode: a frame that
+// has stopped holds the posterior of the iteration it stopped at.
+//   POST_EACH:    every running frame refreshes its entries in every variable-node pass (+4n bytes written per
+//                 frame-iteration, and as many read where a lane mixes stopped and running frames).
+//   POST_ON_STOP: nothing is written until a frame stops; right after the commit of iteration t a posterior-only
+//                 pass recomputes the posterior of the frames that stopped AT t from the check->variable messages
+//                 of t (still in place: the next check-node pass has not run).  Iteration T-1 writes the rest.
+//                 Costs nothing while no frame stops, but a lane (4 frames) / DRAM sector (8 frames) with one newly
+//                 stopped frame reads all its message rows again, so it loses once a few percent of the frames stop
+//                 per iteration.
+enum { POST_NONE = 0, POST_EACH = 1, POST_ON_STOP = 2 };
+
 // Flooding iterations [t0, t1) on the frames of `ws`.  Iteration T-1 runs the FINAL variable-node variant (its
 // dead v2c update is not written).  Stopped frames are never touched again: their packed decisions stay in
-// place from the iteration they stopped at, and so does their posterior row entry when posteriors are wanted
-// (running frames refresh theirs every iteration).
-int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool want_post, cudaStream_t stream) {
+// place from the iteration they stopped at, and so does their posterior row entry when posteriors are wanted.
+int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, int post_mode, cudaStream_t stream) {
     const ldpc_graph* g = d->g;
     const int64_t Wn = Bp / 32;
     for (int t = t0; t < t1; ++t) {
@@ -748,7 +769,7 @@ int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool wa
         else LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
         const bool last = (t == d->T - 1);
         VnLaunch vn{};
-        fill_vn(d, ws, Bp, t, last, want_post, vn);
+        fill_vn(d, ws, Bp, t, last, post_mode == POST_EACH || (post_mode == POST_ON_STOP && last), vn);
         LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
         if (d->early_stop || last) {
             uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
@@ -762,6 +783,12 @@ int run_span(ldpc_decoder* d, Workspace& ws, int64_t Bp, int t0, int t1, bool wa
             sy.unsat = cur;
             LAUNCH(K_OTHER, launch_syndrome(sy, stream));
             LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
+            if (post_mode == POST_ON_STOP && !last) {
+                VnLaunch pv{};
+                fill_vn(d, ws, Bp, t, true, true, pv);
+                pv.post_iter = t + 1;
+                LAUNCH(K_OTHER, launch_vn(d->dtype, pv, stream));
+            }
         }
     }
     return LDPC_OK;
@@ -816,8 +843,9 @@ int scan_ensure(ldpc_decoder::Ctx& cx, int64_t Bp) {
         cx.scan_cap = nb;
     }
     if (!cx.d_total) CU(cudaMalloc((void**)&cx.d_total, sizeof(int32_t)));
-    if (!cx.h_total) CU(cudaHostAlloc((void**)&cx.h_total, sizeof(int32_t), cudaHostAllocDefault));
-    if (!cx.ev) CU(cudaEventCreateWithFlags(&cx.ev, cudaEventDisableTiming));
+    if (!cx.h_total) CU(cudaHostAlloc((void**)&cx.h_total, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    for (auto& e : cx.ev)
+        if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return LDPC_OK;
 }
 
@@ -857,7 +885,7 @@ int replay_graph(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool wan
             cudaError_t le = launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream);
             d->prof.launches++;
             if (le != cudaSuccess) rc = fail(LDPC_ERR_CUDA, "reset (capture): %s", cudaGetErrorString(le));
-            if (!rc) rc = run_span(d, ws, Bp, 0, d->T, want_post, stream);
+            if (!rc) rc = run_span(d, ws, Bp, 0, d->T, want_post ? POST_EACH : POST_NONE, stream);
         }
         cudaGraph_t graph = nullptr;
         cudaError_t ee = cudaStreamEndCapture(cs, &graph);
@@ -891,42 +919,70 @@ int replay_graph(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool wan
 }
 
 // The whole decode of the frames resident as llrT [n][Bp] in the context's root workspace, results delivered per
-// OutSpec, as a RESUMABLE job: start() enqueues up to the first checkpoint, resume() is called once that
-// checkpoint's count has arrived (cx.ev) and enqueues up to the next one.  The plain entry points drive one job
-// to completion; the host pipeline alternates between two.
+// OutSpec, as a RESUMABLE job: start() enqueues the first spans, resume() is called once the OLDEST outstanding
+// checkpoint's count has arrived (wait_event()) and enqueues more.  The plain entry points drive one job to
+// completion; the host pipeline alternates between two.
 //
 // Flooding with early stop runs in spans between checkpoints.  At a checkpoint the number of running frames
 // comes back to the host: zero ends the decode (no empty launches up to T); if at most 60 % of the level's
 // lanes still run, those frames' LLR and V2C columns are gathered into a dense child level that carries on
 // from the same iteration, and the parent level delivers the results of its finished frames.  Every frame
 // sees exactly the arithmetic of the uncompacted schedule (columns are independent), so results are identical.
+//
+// The host decides ONE SPAN LATE: while it waits for the count of checkpoint k, span k+1 (and its checkpoint) is
+// already enqueued, so the GPU never idles for a host round trip.  A span that runs after every frame has
+// stopped does nothing (all warps leave at once), so the late "all stopped" decision costs one empty span; a
+// compaction first drains the one outstanding checkpoint, so the gather works on exact counts as before.
 struct DecodeJob {
     ldpc_decoder* d = nullptr;
     ldpc_decoder::Ctx* cx = nullptr;
     cudaStream_t stream = nullptr;
     OutSpec o;
     bool want_post = false, checkpoints = false;
+    int post_mode = POST_NONE;        // of the spans enqueued from now on
     Workspace* ws = nullptr;          // current level
     const int32_t* map = nullptr;     // its frames -> frames of the caller's batch
     int64_t curB = 0, curBp = 0;
     size_t level = 0;
     int t = 0, quiet = 0;
-    bool waiting = false;             // a checkpoint count is in flight (cx->ev)
+    uint32_t cp_issued = 0, cp_done = 0;   // checkpoints enqueued / consumed (slot = number & 1)
+    int cp_t[2] = {0, 0};             // iteration count at each outstanding checkpoint
+    int64_t last_pending = 0;         // running frames at the last consumed checkpoint (or at the start of the level)
+    int last_t = 0;
+    bool finished = false;            // everything up to the delivery of the results is enqueued
+    bool waiting = false;             // the job needs resume() once wait_event() has completed
+    cudaEvent_t wait_event() const { return cx->ev[cp_done & 1u]; }
 };
 
-// enqueue the next span; either the decode ends with it or a checkpoint is recorded
+// enqueue the next span; either the decode ends with it (results delivered, `finished`) or a checkpoint is recorded
 int job_enqueue(DecodeJob& j) {
     ldpc_decoder* d = j.d;
     cudaStream_t stream = j.stream;
     const int t1 = j.checkpoints ? next_checkpoint(j.t, d->T, j.curBp, j.quiet, d->checkpoint_step) : d->T;
-    int rc = run_span(d, *j.ws, j.curBp, j.t, t1, j.want_post, stream);
+    int rc = run_span(d, *j.ws, j.curBp, j.t, t1, j.post_mode, stream);
     if (rc) return rc;
     j.t = t1;
-    if (j.t >= d->T) return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
+    if (j.t >= d->T) {
+        j.finished = true;
+        return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
+    }
+    const uint32_t slot = j.cp_issued & 1u;
     LAUNCH(K_OTHER, launch_pending_scan(j.ws->done, j.curBp, j.cx->d_scan, j.cx->d_total, stream));
-    CU(cudaMemcpyAsync(j.cx->h_total, j.cx->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    CU(cudaEventRecord(j.cx->ev, stream));
-    j.waiting = true;
+    CU(cudaMemcpyAsync(j.cx->h_total + slot, j.cx->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(j.cx->ev[slot], stream));
+    j.cp_t[slot] = j.t;
+    j.cp_issued++;
+    return LDPC_OK;
+}
+
+// keep up to two spans (one when speculation is off) in flight
+int job_top_up(DecodeJob& j) {
+    const uint32_t depth = j.d->speculate ? 2u : 1u;
+    while (!j.finished && j.cp_issued - j.cp_done < depth) {
+        int rc = job_enqueue(j);
+        if (rc) return rc;
+    }
+    j.waiting = !j.finished;
     return LDPC_OK;
 }
 
@@ -957,28 +1013,58 @@ int job_start(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, i
     j.ws = &root;
     j.curB = B;
     j.curBp = Bp;
+    j.last_pending = B;
+    if (j.want_post) {
+        // with checkpoints the stop rate is known one span late and the mode follows it (job_resume); the first
+        // iterations rarely stop a frame.  Without them: on-stop when nothing can stop early, else every iteration.
+        if (d->post_mode) j.post_mode = d->post_mode;
+        else j.post_mode = (j.checkpoints || !d->early_stop) ? POST_ON_STOP : POST_EACH;
+    }
     if (j.checkpoints) {
         int rc = scan_ensure(cx, Bp);
         if (rc) return rc;
     }
-    return job_enqueue(j);
+    return job_top_up(j);
 }
 
-// precondition: j.waiting and cx->ev has completed
+// precondition: j.waiting and wait_event() has completed
 int job_resume(DecodeJob& j) {
     ldpc_decoder* d = j.d;
     ldpc_decoder::Ctx& cx = *j.cx;
     cudaStream_t stream = j.stream;
     const ldpc_graph* g = d->g;
     j.waiting = false;
-    const int64_t pending = *cx.h_total;
-    j.quiet = (pending >= j.curB) ? j.quiet + 1 : 0;
+    auto consume = [&]() -> int64_t {
+        const uint32_t slot = j.cp_done & 1u;
+        const int64_t pending = cx.h_total[slot];
+        const int t_cp = j.cp_t[slot];
+        j.cp_done++;
+        j.quiet = (pending >= j.curB) ? j.quiet + 1 : 0;
+        if (j.want_post && d->post_mode == 0 && t_cp > j.last_t && j.last_pending > 0) {
+            // frames stopped per iteration, as a share of the running ones: the on-stop pass re-reads a whole lane /
+            // sector for one newly stopped frame, so it only pays while stops are rare
+            const double rate = (double)(j.last_pending - pending) / (double)j.last_pending / (double)(t_cp - j.last_t);
+            j.post_mode = rate < 0.02 ? POST_ON_STOP : POST_EACH;
+        }
+        j.last_pending = pending;
+        j.last_t = t_cp;
+        return pending;
+    };
+    int64_t pending = consume();
     if (pending == 0) {
         d->stat_early_exits++;   // decisions (and posteriors) of stopped frames are already in place
         return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
     }
     if (j.curBp >= d->compact_min_frames && pending * 100 <= j.curBp * d->compact_percent && j.level < kMaxLevels) {
         // ---- move the running frames to a dense child level ----
+        if (j.cp_done != j.cp_issued) {   // the span in flight ends with a checkpoint of its own: gather on ITS count
+            CU(cudaEventSynchronize(j.wait_event()));
+            pending = consume();
+            if (pending == 0) {
+                d->stat_early_exits++;
+                return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
+            }
+        }
         if (cx.levels.size() <= j.level) cx.levels.emplace_back();   // capacity reserved at creation: no reallocation
         ldpc_decoder::Level& lv = cx.levels[j.level];
         const int64_t childBp = pad_frames(pending);
@@ -997,7 +1083,7 @@ int job_resume(DecodeJob& j) {
         if (rc == LDPC_ERR_NOMEM) {   // no room for a child level: carry on uncompacted
             cudaGetLastError();
             lv.ws.release();
-            return job_enqueue(j);
+            return job_top_up(j);
         }
         if (rc) return rc;
         if (j.want_post) {
@@ -1019,17 +1105,35 @@ int job_resume(DecodeJob& j) {
         j.curBp = childBp;
         ++j.level;
     }
-    return job_enqueue(j);
+    return job_top_up(j);
+}
+
+int job_drive(DecodeJob& j) {
+    int rc = LDPC_OK;
+    while (!rc && j.waiting) {
+        CU(cudaEventSynchronize(j.wait_event()));
+        rc = job_resume(j);
+    }
+    return rc;
+}
+
+int ctx_enter(ldpc_decoder::Ctx& cx, cudaStream_t stream) {
+    if (!cx.tail) CU(cudaEventCreateWithFlags(&cx.tail, cudaEventDisableTiming));
+    if (cx.tail_valid && cx.tail_stream != stream) CU(cudaStreamWaitEvent(stream, cx.tail, 0));
+    return LDPC_OK;
+}
+
+int ctx_leave(ldpc_decoder::Ctx& cx, cudaStream_t stream) {
+    CU(cudaEventRecord(cx.tail, stream));
+    cx.tail_stream = stream;
+    cx.tail_valid = true;
+    return LDPC_OK;
 }
 
 int decode_resident(ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, int64_t Bp, const OutSpec& o, cudaStream_t stream) {
     DecodeJob j;
     int rc = job_start(j, d, cx, B, Bp, o, stream);
-    while (!rc && j.waiting) {
-        CU(cudaEventSynchronize(cx.ev));
-        rc = job_resume(j);
-    }
-    return rc;
+    return rc ? rc : job_drive(j);
 }
 
 // pack + job_start on the context's root workspace
@@ -1082,11 +1186,7 @@ int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, in
                      int32_t* iters, uint8_t* success, cudaStream_t stream) {
     DecodeJob j;
     int rc = job_start_on_device(j, d, cx, llr, B, bits, post, iters, success, stream);
-    while (!rc && j.waiting) {
-        CU(cudaEventSynchronize(cx.ev));
-        rc = job_resume(j);
-    }
-    return rc;
+    return rc ? rc : job_drive(j);
 }
 
 }  // namespace
@@ -1162,6 +1262,8 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* gr = getenv("LDPC_GRAPHS")) d->use_graphs = atoi(gr) != 0;
     if (const char* cf = getenv("LDPC_COMPACT_PERCENT")) d->compact_percent = std::min(95, std::max(5, atoi(cf)));
     if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
+    if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp) != 0;
+    if (const char* pm = getenv("LDPC_POST_MODE")) d->post_mode = std::min(2, std::max(0, atoi(pm)));
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
     DeviceGuard guard(g->device);
@@ -1236,6 +1338,9 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
 extern "C" int ldpc_decoder_set_weights(ldpc_decoder* d, const void* beta, const void* alpha) {
     if (!d) return fail(LDPC_ERR_INVALID, "NULL decoder");
     DeviceGuard guard(d->g->device);
+    // decodes return with kernels still in flight on the caller's stream: the tables must not change under them
+    for (auto& cx : d->cx)
+        if (cx.tail_valid) CU(cudaEventSynchronize(cx.tail));
     if (beta) {
         if (!d->d_beta) return fail(LDPC_ERR_INVALID, "decoder was created without beta");
         CU(cudaMemcpy(d->d_beta, beta, (size_t)d->T * d->n_beta * d->rsz, cudaMemcpyHostToDevice));
@@ -1265,7 +1370,9 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
         cudaFree(cx.d_scan);
         cudaFree(cx.d_total);
         if (cx.h_total) cudaFreeHost(cx.h_total);
-        if (cx.ev) cudaEventDestroy(cx.ev);
+        for (auto& e : cx.ev)
+            if (e) cudaEventDestroy(e);
+        if (cx.tail) cudaEventDestroy(cx.tail);
     }
     for (auto& ev : d->ev_pool) {
         cudaEventDestroy(ev.first);
@@ -1294,7 +1401,10 @@ extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, u
     if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
     DeviceGuard guard(d->g->device);
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
-    return decode_on_device(d, d->cx[0], llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
+    int rc = ctx_enter(d->cx[0], (cudaStream_t)stream);
+    if (!rc) rc = decode_on_device(d, d->cx[0], llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
+    if (!rc) rc = ctx_leave(d->cx[0], (cudaStream_t)stream);
+    return rc;
 }
 
 // Host-buffer entry point: chunked pipeline with two decode jobs in flight (see HostPipe, DecodeJob).
@@ -1397,7 +1507,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
             for (int k = 0; k < 2; ++k)
                 if (slot[k].busy && (pick < 0 || slot[k].cp_seq < slot[pick].cp_seq)) pick = k;
             Slot& sl = slot[pick];
-            CU(cudaEventSynchronize(sl.job.cx->ev));
+            CU(cudaEventSynchronize(sl.job.wait_event()));
             int r = job_resume(sl.job);
             if (r) return r;
             if (sl.job.waiting) sl.cp_seq = ++seq;
@@ -1484,7 +1594,8 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t Bp = pad_frames(B);
-    int rc = ws_ensure(d, d->cx[0].root, Bp);
+    int rc = ctx_enter(d->cx[0], stream);
+    if (!rc) rc = ws_ensure(d, d->cx[0].root, Bp);
     if (rc) return rc;
     d->prof.frames_padded = Bp;
     Workspace& ws = d->cx[0].root;
@@ -1495,7 +1606,9 @@ extern "C" int ldpc_mc_round(ldpc_decoder* d, float snr_db, int32_t llr_sign, ui
     o.counters = counters;
     o.frame_bit_errors = frame_bit_errors;
     o.frame_iters = frame_iterations;
-    return decode_resident(d, d->cx[0], B, Bp, o, stream);
+    rc = decode_resident(d, d->cx[0], B, Bp, o, stream);
+    if (!rc) rc = ctx_leave(d->cx[0], stream);
+    return rc;
 }
 
 extern "C" int ldpc_count_errors(int device, int32_t n, int64_t B, const uint8_t* bits, const uint8_t* codeword,

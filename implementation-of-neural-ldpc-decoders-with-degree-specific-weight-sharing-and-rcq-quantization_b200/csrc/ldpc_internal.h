@@ -66,6 +66,11 @@ struct VnLaunch {
     int items_wide_end;
     int wide_max_deg;           // largest degree among them (rows of the shared-memory stage)
     int wide_stage;             // 1: those items run in vn_wide_kernel
+    // Posterior-on-stop pass (final_pass && postT only): post_iter > 0 restricts the pass to the frames that
+    // stopped exactly at iteration post_iter (done && iters == post_iter); it writes their posterior row entries
+    // from the check->variable messages of that iteration and nothing else.
+    const int32_t* iters;       // [Bp]
+    int post_iter;
 };
 
 struct SynLaunch {

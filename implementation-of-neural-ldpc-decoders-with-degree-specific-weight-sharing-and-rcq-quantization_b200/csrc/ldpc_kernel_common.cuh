@@ -60,6 +60,7 @@ __device__ __forceinline__ T* row_at(T* base, uint32_t row, uint32_t stride_byte
 // segment is read, merged and written back whole, so the access stays one vector transaction per lane.
 template <typename T, int V>
 __device__ __forceinline__ void store_masked(T* __restrict__ rowptr, Pack<T, V> val, uint32_t keep) {
+    if (keep == (1u << V) - 1u) return;   // nothing of this lane changes
     if (keep != 0) {
         const Pack<T, V> old = *reinterpret_cast<const Pack<T, V>*>(rowptr);
 #pragma unroll
@@ -67,6 +68,22 @@ __device__ __forceinline__ void store_masked(T* __restrict__ rowptr, Pack<T, V> 
             if ((keep >> v) & 1u) val.v[v] = old.v[v];
     }
     st_stream<Pack<T, V>>(rowptr, val);
+}
+
+// Frames of this lane a variable-node pass works on, as a "leave alone" mask.  Normal passes: the stopped frames.
+// Posterior-on-stop pass (post_iter > 0): everything except the frames that stopped exactly at iteration post_iter.
+template <int V>
+__device__ __forceinline__ uint32_t vn_frame_mask(const uint8_t* __restrict__ done, const int32_t* __restrict__ iters,
+                                                  int post_iter, int64_t f0) {
+    uint32_t dmask = load_done_mask<V>(done, f0);
+    if (post_iter > 0) {
+        uint32_t sel = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (((dmask >> v) & 1u) && __ldg(iters + f0 + v) == post_iter) sel |= 1u << v;
+        dmask = ~sel & ((1u << V) - 1u);
+    }
+    return dmask;
 }
 
 // message type of the check->variable array

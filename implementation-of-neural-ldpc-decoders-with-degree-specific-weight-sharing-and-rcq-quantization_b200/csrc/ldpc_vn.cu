@@ -1,5 +1,7 @@
 // Variable-node half iteration + posterior + hard decision: vn_kernel (degree <= 8 unrolled, > 64 generic),
 // vn_wide_kernel (degree 9..64, inputs staged once in shared memory) and hard_kernel (layered schedule).
+#include <algorithm>
+
 #include "ldpc_kernel_common.cuh"
 
 namespace ldpc {
@@ -69,11 +71,19 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
 #pragma unroll
         for (int d = 0; d < DV; ++d) slot[u][d] = (uint32_t)__ldg(p.vslots + lbase + u * DV + d);
     }
+    // a lane whose frames are all left alone (stopped, or not selected by the posterior-on-stop pass) moves no data
+    const bool lane_idle = FINAL && POST && dmask == ((1u << V) - 1u);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+        if (!lane_idle) {
 #pragma unroll
-        for (int d = 0; d < DV; ++d) cin[u][d] = ld_stream<Pack<InT, V>>(row_at(c2v, slot[u][d], in_stride));
-        L[u] = ld_stream<Pack<Real, V>>(row_at(llr0, j[u], real_stride));
+            for (int d = 0; d < DV; ++d) cin[u][d] = ld_stream<Pack<InT, V>>(row_at(c2v, slot[u][d], in_stride));
+            L[u] = ld_stream<Pack<Real, V>>(row_at(llr0, j[u], real_stride));
+        } else {
+#pragma unroll
+            for (int d = 0; d < DV; ++d) cin[u][d] = Pack<InT, V>{};
+            L[u] = Pack<Real, V>{};
+        }
     }
     const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
 #pragma unroll
@@ -114,7 +124,8 @@ __device__ __forceinline__ void vn_node_small(const VnLaunch& p, int32_t vpos, i
         // forward(): the posterior of a frame is the one of the iteration it stops at -- running frames refresh
         // their entry every iteration, stopped frames keep theirs
         if constexpr (POST) store_masked<Real, V>(row_at(static_cast<Real*>(p.postT) + f0, j[u], real_stride), post, dmask);
-        write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit, keepw);
+        // (the posterior-on-stop pass leaves the decisions alone: they are in place since the frame's last iteration)
+        if (!(FINAL && POST) || p.post_iter == 0) write_hard<Real, V>(p.hardw, p.Wn, j[u], wbase, bit, keepw);
     }
 }
 
@@ -183,7 +194,7 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
         }
     }
     if constexpr (POST) store_masked<Real, V>(static_cast<Real*>(p.postT) + j * p.Bp + f0, post, dmask);
-    write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
+    if (!(FINAL && POST) || p.post_iter == 0) write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
 }
 
 // FINAL: iteration T-1 (the dead v2c update is not written).  POST: forward()'s posterior output -- running
@@ -191,7 +202,8 @@ __device__ void vn_node_generic(const VnLaunch& p, int32_t vpos, int64_t lbase, 
 // iteration it stopped at; messages and decisions of stopped frames are never touched again either way.
 template <typename Real, bool QUANT, bool FINAL, bool POST>
 __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINCTAS : 3) vn_kernel(const VnLaunch p, const int nfb,
-                                                                                                   const int item0) {
+                                                                                                   const int item0, const int item1,
+                                                                                                   const int item_stride) {
     constexpr int V = FramesPerLane<Real>::value;
     extern __shared__ float s_lut[];
     if (QUANT) {
@@ -200,10 +212,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
         __syncthreads();
     }
     const int fb = blockIdx.x % nfb;
-    const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
     if (f0 >= p.Bp) return;
-    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    const uint32_t dmask = vn_frame_mask<V>(p.done, p.iters, (FINAL && POST) ? p.post_iter : 0, f0);
     if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
     const uint32_t keepw = keep_word<V>(dmask);
     int lutbase[V];
@@ -211,6 +222,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
     for (int v = 0; v < V; ++v) lutbase[v] = QUANT ? (p.q_now << p.bc) : 0;
     const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
     const int64_t wbase = (warp_f0 / (32 * V)) * V;
+    // one work item per CTA (item_stride == number of items of the launch), except in the posterior-on-stop pass,
+    // whose few CTAs per frame block walk the items (most of its warps have left above)
+    for (int item_id = item0 + blockIdx.x / nfb; item_id < item1; item_id += item_stride) {
     const WorkItem it = p.items[item_id];
     int64_t lbase = it.first_slot;
     int32_t vpos = it.first_node;
@@ -233,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
                 vn_node_generic<Real, QUANT, FINAL, POST>(p, vpos, lbase, it.deg, f0, dmask, keepw, wbase, s_lut, lutbase);
     }
 #undef LDPC_VN_CASE
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(Real) == 4 ? LDPC_VN_F32_MINC
 // column (LDS.128 per element for the four frames).  A column belongs to one thread: no barriers.
 // ---------------------------------------------------------------------------------------------
 constexpr int kVnWideThreads = 128;
+constexpr int kPostOnlyGroups = 32;   // CTAs per frame block in the posterior-on-stop pass
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_own(void* smem_dst, const void* gmem_src) {
@@ -310,7 +326,7 @@ __device__ __forceinline__ void vn_wide_sums(const VnLaunch& p, const Pack<Real,
 #endif
 template <typename Real, bool QUANT, bool FINAL, bool POST>
 __global__ void __launch_bounds__(kVnWideThreads, QUANT ? LDPC_VNW_Q_MINCTAS : LDPC_VNW_F_MINCTAS) vn_wide_kernel(const VnLaunch p, const int nfb, const int item0,
-                                                                  const int stage_rows) {
+                                                                  const int item1, const int item_stride, const int stage_rows) {
     constexpr int V = FramesPerLane<Real>::value;
     using InT = typename CnOut<Real, QUANT>::type;
     using PackR = Pack<Real, V>;
@@ -326,10 +342,9 @@ __global__ void __launch_bounds__(kVnWideThreads, QUANT ? LDPC_VNW_Q_MINCTAS : L
         __syncthreads();
     }
     const int fb = blockIdx.x % nfb;
-    const int item_id = item0 + blockIdx.x / nfb;
     const int64_t f0 = ((int64_t)fb * kVnWideThreads + threadIdx.x) * V;
     if (f0 >= p.Bp) return;   // whole warps
-    const uint32_t dmask = load_done_mask<V>(p.done, f0);
+    const uint32_t dmask = vn_frame_mask<V>(p.done, p.iters, (FINAL && POST) ? p.post_iter : 0, f0);
     if (__all_sync(0xffffffffu, dmask == ((1u << V) - 1u))) return;
     const uint32_t keepw = keep_word<V>(dmask);
     int lutbase[V];
@@ -338,18 +353,20 @@ __global__ void __launch_bounds__(kVnWideThreads, QUANT ? LDPC_VNW_Q_MINCTAS : L
     const uint32_t lutmask = (1u << p.bc) - 1u;
     const int64_t warp_f0 = f0 - (int64_t)(threadIdx.x & 31) * V;
     const int64_t wbase = (warp_f0 / (32 * V)) * V;
-    const WorkItem it = p.items[item_id];
-    const int dv = it.deg;
     const uint32_t in_stride = (uint32_t)p.Bp * (uint32_t)sizeof(InT), real_stride = (uint32_t)p.Bp * (uint32_t)sizeof(Real);
     const InT* __restrict__ c2v = static_cast<const InT*>(p.c2v) + f0;
     Real* __restrict__ v2c = static_cast<Real*>(p.v2c) + f0;
     const Real* __restrict__ llr0 = static_cast<const Real*>(p.llrT) + f0;
     const bool has_alpha = (p.alpha_t != nullptr) && !FINAL;
+    for (int item_id = item0 + blockIdx.x / nfb; item_id < item1; item_id += item_stride) {
+    const WorkItem it = p.items[item_id];
+    const int dv = it.deg;
     int64_t lbase = it.first_slot;
     int32_t vpos = it.first_node;
     for (int c = 0; c < it.count; ++c, lbase += dv, ++vpos) {
         const uint32_t j = (uint32_t)__ldg(p.vpos_var + vpos);
         for (int i = 0; i < dv; ++i) {
+            if (FINAL && POST && dmask == ((1u << V) - 1u)) break;   // idle lane: nothing it computes is stored
             const uint32_t slot = (uint32_t)__ldg(p.vslots + lbase + i);
             if constexpr (QUANT) cp_async_own<sizeof(PackIn)>(s_code + (size_t)i * kVnWideThreads, row_at(c2v, slot, in_stride));
             else cp_async_own<sizeof(PackR)>(s_val + (size_t)i * kVnWideThreads, row_at(c2v, slot, in_stride));
@@ -389,7 +406,8 @@ __global__ void __launch_bounds__(kVnWideThreads, QUANT ? LDPC_VNW_Q_MINCTAS : L
 #undef LDPC_VNW_CASE
         if (!handled) vn_wide_sums<Real, FINAL, 0>(p, s_val, dv, L, alpha, has_alpha, lbase, v2c, real_stride, dmask, post, bit);
         if constexpr (POST) store_masked<Real, V>(row_at(static_cast<Real*>(p.postT) + f0, j, real_stride), post, dmask);
-        write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
+        if (!(FINAL && POST) || p.post_iter == 0) write_hard<Real, V>(p.hardw, p.Wn, j, wbase, bit, keepw);
+    }
     }
 }
 
@@ -414,20 +432,23 @@ template <typename Real, bool QUANT>
 cudaError_t launch_vn_range(const VnLaunch& p, int item0, int item1, bool wide, cudaStream_t stream) {
     if (item1 <= item0) return cudaSuccess;
     constexpr int V = FramesPerLane<Real>::value;
+    // posterior-on-stop pass: nearly all of its warps leave at once, so a few CTAs per frame block walk the items
+    const bool post_only = p.final_pass && p.postT && p.post_iter > 0;
     if (wide) {
         using InT = typename CnOut<Real, QUANT>::type;
         const int rows = p.wide_max_deg;
         const size_t smem = (size_t)rows * kVnWideThreads * (sizeof(Pack<Real, V>) + (QUANT ? sizeof(Pack<InT, V>) : 0)) +
                             (QUANT ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0);
         const int64_t nfb = (p.Bp + (int64_t)kVnWideThreads * V - 1) / ((int64_t)kVnWideThreads * V);
-        const int64_t grid = nfb * (item1 - item0);
+        const int groups = post_only ? std::min(item1 - item0, kPostOnlyGroups) : item1 - item0;
+        const int64_t grid = nfb * groups;
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 #define LDPC_VNW(FINAL, POST)                                                                                          \
     do {                                                                                                               \
         cudaError_t e_ = cudaFuncSetAttribute(vn_wide_kernel<Real, QUANT, FINAL, POST>,                                \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
         if (e_ != cudaSuccess) return e_;                                                                              \
-        vn_wide_kernel<Real, QUANT, FINAL, POST><<<(unsigned)grid, kVnWideThreads, smem, stream>>>(p, (int)nfb, item0, rows);   \
+        vn_wide_kernel<Real, QUANT, FINAL, POST><<<(unsigned)grid, kVnWideThreads, smem, stream>>>(p, (int)nfb, item0, item1, groups, rows);   \
     } while (0)
         if (p.final_pass) { if (p.postT) LDPC_VNW(true, true); else LDPC_VNW(true, false); }
         else { if (p.postT) LDPC_VNW(false, true); else LDPC_VNW(false, false); }
@@ -435,17 +456,18 @@ cudaError_t launch_vn_range(const VnLaunch& p, int item0, int item1, bool wide, 
     } else {
         const int threads = threads_for(p.Bp, V);
         const int64_t nfb = (p.Bp / V + threads - 1) / threads;
-        const int64_t grid = nfb * (item1 - item0);
+        const int groups = post_only ? std::min(item1 - item0, kPostOnlyGroups) : item1 - item0;
+        const int64_t grid = nfb * groups;
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         const size_t smem = p.bc ? sizeof(float) * ((size_t)p.n_quant << p.bc) : 0;
         const unsigned g = (unsigned)grid;
         const int nf = (int)nfb;
         if (p.final_pass) {
-            if (p.postT) vn_kernel<Real, QUANT, true, true><<<g, threads, smem, stream>>>(p, nf, item0);
-            else vn_kernel<Real, QUANT, true, false><<<g, threads, smem, stream>>>(p, nf, item0);
+            if (p.postT) vn_kernel<Real, QUANT, true, true><<<g, threads, smem, stream>>>(p, nf, item0, item1, groups);
+            else vn_kernel<Real, QUANT, true, false><<<g, threads, smem, stream>>>(p, nf, item0, item1, groups);
         } else {
-            if (p.postT) vn_kernel<Real, QUANT, false, true><<<g, threads, smem, stream>>>(p, nf, item0);
-            else vn_kernel<Real, QUANT, false, false><<<g, threads, smem, stream>>>(p, nf, item0);
+            if (p.postT) vn_kernel<Real, QUANT, false, true><<<g, threads, smem, stream>>>(p, nf, item0, item1, groups);
+            else vn_kernel<Real, QUANT, false, false><<<g, threads, smem, stream>>>(p, nf, item0, item1, groups);
         }
     }
     return cudaGetLastError();

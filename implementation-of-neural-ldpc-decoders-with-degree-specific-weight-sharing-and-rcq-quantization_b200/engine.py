@@ -84,6 +84,20 @@ class TannerGraph:
         np.add.at(ptr, rows + 1, 1)
         return TannerGraph(n, m, np.cumsum(ptr), cols.astype(np.int32))
 
+    # the graph is immutable: copies of a decoder share it; a pickled one re-creates its device handles on demand
+    def __deepcopy__(self, memo):
+        return self
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}
+        state.pop("_lock", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._lock = threading.Lock()
+
     def handle(self, device: int) -> int:
         """Device-side graph (degree-sorted slot layout), created once per device."""
         with self._lock:
@@ -124,6 +138,18 @@ class TannerGraph:
                 lib.ldpc_graph_destroy(h)
         except Exception:
             pass
+
+
+class EngineCache:
+    """Mixin of the decoder classes: ``self._engines`` (device engines by configuration) is per object -- a copy or
+    an unpickled decoder starts without engines and builds its own on first use."""
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engines"] = {}
+        if "_pushed" in state:
+            state["_pushed"] = {}
+        return state
 
 
 class Engine:
@@ -232,18 +258,21 @@ class Engine:
             raise IndexError(f"llr must have shape [B, {self.graph.n}], got {llr.shape}")
         B = llr.shape[0]
         out = out or {}
-        bits = out.get("bits")
-        if bits is None:
-            bits = np.empty((B, self.graph.n), dtype=np.uint8)
-        post = out.get("posterior")
-        if post is None and want_posterior:
-            post = np.empty((B, self.graph.n), dtype=self.dtype)
-        iters = out.get("iterations")
-        if iters is None:
-            iters = np.empty(B, dtype=np.int32)
-        succ = out.get("success")
-        if succ is None:
-            succ = np.empty(B, dtype=np.uint8)
+
+        def buffer(name, shape, dtype, wanted=True):
+            a = out.get(name)
+            if a is None:
+                return np.empty(shape, dtype=dtype) if wanted else None
+            # the C side writes through the raw pointer: the array must be exactly what it expects
+            if not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != np.dtype(dtype) or \
+                    not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"out[{name!r}] must be a writable C-contiguous {np.dtype(dtype).name} array of shape {shape}")
+            return a
+
+        bits = buffer("bits", (B, self.graph.n), np.uint8)
+        post = buffer("posterior", (B, self.graph.n), self.dtype, wanted=want_posterior)
+        iters = buffer("iterations", (B,), np.int32)
+        succ = buffer("success", (B,), np.uint8)
         with self._lock:
             _lib.check(_lib.load().ldpc_decode_host(self._h, _ptr(llr), B, _ptr(bits), _ptr(post), _ptr(iters), _ptr(succ)))
         return bits, post, iters, succ

@@ -18,7 +18,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-from .engine import Engine, TannerGraph, awgn_llr, default_device
+from .engine import Engine, EngineCache, TannerGraph, awgn_llr, default_device
 
 
 @dataclass
@@ -37,7 +37,19 @@ class LDPCCode:
     def rate(self) -> float:
         return self.k / self.n
 
+    def invalidate(self):
+        """Forget the cached degree maps and graph (call after editing ``H`` IN PLACE; assigning a new ``H`` object is
+        noticed by itself).  The reference recomputes both from ``H`` on every access."""
+        self._graph = None
+        self._deg = None
+        self._h_id = id(self.H)
+
+    def _check_h(self):
+        if getattr(self, "_h_id", None) != id(self.H):
+            self.invalidate()
+
     def _degree_maps(self):
+        self._check_h()
         if self._deg is None:
             try:
                 import scipy.sparse as sp
@@ -65,6 +77,7 @@ class LDPCCode:
 
     @property
     def graph(self) -> TannerGraph:
+        self._check_h()
         if self._graph is None:
             self._graph = TannerGraph.from_H(self.H)
             if self._graph.n != self.n:
@@ -84,7 +97,7 @@ def _as_batch(llr):
     return (a[None] if a.ndim == 1 else a), a.ndim == 1, False
 
 
-class BasicMinSumDecoder:
+class BasicMinSumDecoder(EngineCache):
     """Normalised min-sum, flooding schedule, float64 (ldpc_decoder.py:56-153).
 
     ``c2v = (factor * raw) * prod(other signs)``, iterations = ``code.max_iterations`` (read at call
@@ -147,3 +160,12 @@ def simulate_awgn_channel(codeword: np.ndarray, snr_db: float) -> np.ndarray:
     cw_dev = torch.from_numpy(cw).to(f"cuda:{dev}")
     llr = awgn_llr(cw.shape[0], 1, snr_db, seed=seed, frame0=0, llr_sign=-1, codeword=cw_dev, device=dev)
     return llr[0].double().cpu().numpy()
+
+
+def __getattr__(name):
+    # ``from ldpc_decoder import NeuralMinSumDecoder`` gives the reference's legacy class of that name
+    # (ldpc_decoder.py:155-272); resolved lazily because it is built on the nn.Module base of the neural decoders
+    if name == "NeuralMinSumDecoder":
+        from .neural_minsum_decoder import LegacyNeuralMinSumDecoder
+        return LegacyNeuralMinSumDecoder
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from ._neural_base import DecoderModule, build_2d_tables
-from .engine import Engine, default_device
+from .engine import Engine, EngineCache, default_device
 from .ldpc_decoder import LDPCCode
 
 
@@ -71,7 +71,7 @@ def _threshold_table(quantizers) -> np.ndarray:
     return np.array([q.thresholds for q in quantizers], dtype=np.float64).astype(np.float32)
 
 
-class RCQMinSumDecoder:
+class RCQMinSumDecoder(EngineCache):
     """Min-sum whose C2V messages pass through quantise -> reconstruct (rcq_decoder.py:123-279)."""
 
     def __init__(self, code: LDPCCode, bc: int, bv: int, quantizer_params: List[Tuple[float, float]],
@@ -88,13 +88,18 @@ class RCQMinSumDecoder:
         return self.quantizers[int(_schedule(self.max_iterations, len(self.quantizers))[iteration])]
 
     def _engine(self, device: int) -> Engine:
-        key = (device, bool(self.layered))
+        # the reference reads max_iterations, bc, layered and the quantisers at call time (rcq_decoder.py:169-208)
+        thr = _threshold_table(self.quantizers)
+        key = (device, bool(self.layered), int(self.max_iterations), int(self.bc), thr.tobytes())
         eng = self._engines.get(key)
         if eng is None:
+            if self.max_iterations < 1:
+                raise ValueError("max_iterations must be >= 1")
             eng = Engine(self.code.graph, dtype=np.float32, max_iterations=self.max_iterations, bc=self.bc,
-                         thresholds=_threshold_table(self.quantizers),
-                         quantizer_of_iter=_schedule(self.max_iterations, len(self.quantizers)),
+                         thresholds=thr, quantizer_of_iter=_schedule(self.max_iterations, len(self.quantizers)),
                          schedule=1 if self.layered else 0, device=device)
+            for old in [k for k in self._engines if k[:2] == key[:2]]:   # one engine per (device, schedule)
+                self._engines.pop(old).close()
             self._engines[key] = eng
         return eng
 
