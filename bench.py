@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """Headline benchmark: info Gb/s (frames/s) of batched flooding min-sum decoding at 10 iterations.
 
-Workload (BASELINE.json configs[1] on the largest named code shape): Neural2DMinSumDecoder,
-weight_sharing_type=2, 10 iterations, 65 536 frames per GPU, synthetic (16200,7200)-shaped code
-(E = 48 599), AWGN LLRs at 2 dB in the reference's own sign convention (ldpc_decoder.py:289), under which
-no frame satisfies the parity checks, so every frame executes exactly 10 full iterations with the
-per-iteration posterior / hard decision / syndrome / early-stop test of the reference still running.
+Workload of `value` (BASELINE.json configs[1] on the largest named code shape): Neural2DMinSumDecoder.forward,
+weight_sharing_type=2, 10 iterations, 65 536 frames per GPU, synthetic (16200,7200)-shaped code (E = 48 599),
+AWGN LLRs at 2 dB in the reference's own sign convention (ldpc_decoder.py:289), under which no frame satisfies
+the parity checks, so every frame executes exactly 10 full iterations with the per-iteration posterior / hard
+decision / syndrome / early-stop test of the reference still running.  forward() returns (decoded, posterior,
+iterations) (neural_2d_decoder.py:206-225): the timed call delivers all three.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 our arm
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] CPU arm (oracle port, all host threads)
 
-A step = one decode of the whole batch.  `value` times ldpc_decode_device with the LLRs resident in HBM
-(CUDA events on the launching stream); `e2e` times ldpc_decode_host (pinned host LLRs in, hard decisions
-+ iteration counts + success flags out, copies inside the timed region).  One JSON line on stdout.
+A step = one decode of the whole batch.  `value` times ldpc_decode_device with the LLRs resident in HBM (CUDA events
+on the launching stream); `e2e` times ldpc_decode_host (pinned host LLRs in; hard decisions + posteriors + iteration
+counts + success flags out; every copy inside the timed region).  `decode_only` / `e2e_decode_only` are the same two
+calls without the posterior (the reference's decode() surface).  `configs` holds one short leg for each of the other
+BASELINE.json configurations (C1 (7,4) Basic f64, C3 RCQ bc=3, C4 W-RCQ type 1 on the QC shape, C5 the Monte-Carlo
+SNR sweep through LDPSimulator at T = 50); at N > 1 `mc_parity` says whether the all-reduced Monte-Carlo counters of a
+sharded round equal those of the same global frame range decoded by rank 0 alone.  One JSON line on stdout.
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
+import importlib
 import json
 import os
 import statistics
@@ -24,29 +32,19 @@ import subprocess
 import sys
 import tempfile
 import time
+import types
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+PKG = "implementation-of-neural-ldpc-decoders-with-degree-specific-weight-sharing-and-rcq-quantization_b200"
 
 METRIC = "info_gbps_at_10_iters"
 UNIT = "info Gb/s"
 T_ITERS = 10
 SNR_DB = 2.0
-# dram__bytes_read.sum + dram__bytes_write.sum per FRAME of one launch, from the committed `ncu --set full`
-# captures (profiles/r01b_ncu_full_*_8192frames_raw.csv: bytes of one launch / 8192 frames); scaled by the
-# frames of the benchmarked launch.  Only the captured (decoder, code, kernel) pairs have an entry.
-NCU_TRAFFIC_BYTES_PER_FRAME = {
-    ("n2d2", "dvbs2", "vn_kernel"): (2.123882e9 + 1.558320e9) / 8192,
-    ("n2d2", "dvbs2", "cn_kernel"): (1.592799e9 + 1.542210e9) / 8192,
-    ("rcq", "dvbs2", "vn_kernel"): (0.929480e9 + 1.551163e9) / 8192,
-    ("rcq", "dvbs2", "cn_kernel"): (1.592856e9 + 0.371589e9) / 8192,
-    ("n2d2", "qc", "vn_kernel"): (1.552332e9 + 1.204139e9) / 8192,
-    ("n2d2", "qc", "cn_kernel"): (1.242029e9 + 1.192600e9) / 8192,       # cn_wide_kernel (row ring)
-    ("wrcq1", "qc", "vn_kernel"): (0.621112e9 + 1.193412e9) / 8192,
-    ("wrcq1", "qc", "cn_kernel"): (1.241724e9 + 0.280145e9) / 8192,      # cn_wide_kernel (row ring)
-}
+QP = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
 
 
 def parse_args():
@@ -56,27 +54,51 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=65536, help="frames per GPU per step")
-    ap.add_argument("--code", default="dvbs2", choices=["dvbs2", "qc", "dv12"])
+    ap.add_argument("--code", default="dvbs2", choices=["dvbs2", "qc", "dv12", "h74", "r504"])
     ap.add_argument("--decoder", default="n2d2", choices=["n2d2", "n2d1", "nnms", "oms2", "rcq", "wrcq1", "basic"])
+    ap.add_argument("--decode-only", action="store_true", help="time decode() (no posterior) as `value` instead of forward()")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-mc", action="store_true", help="skip the early-stop Monte-Carlo leg (T=50, frames converge)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs for BASELINE configs 1, 3, 4, 5")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
 
-def make_code(L, name):
+def host_only_package():
+    """The package's host-side modules (code generators, graph construction) WITHOUT importing the package itself:
+    its __init__ loads the CUDA library, which the CPU reference arm must not map."""
+    name = "_ldpc_b200_hostonly"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(ROOT, PKG)]
+        sys.modules[name] = pkg
+    ns = types.SimpleNamespace()
+    ns.codes = importlib.import_module(name + ".codes")
+    ns.create_test_ldpc_code = importlib.import_module(name + ".ldpc_decoder").create_test_ldpc_code
+    return ns
+
+
+def make_code(L, name, T=T_ITERS):
     if name == "dv12":   # not a BASELINE shape: exercises the variable-node path for degrees above 8
-        return L.codes.ira_code({12: 1620, 3: 4860}, {5: 4861, 6: 4859}, max_iterations=T_ITERS)
-    return L.codes.dvbs2_shaped(max_iterations=T_ITERS) if name == "dvbs2" else L.codes.qc_shaped(max_iterations=T_ITERS)
+        return L.codes.ira_code({12: 1620, 3: 4860}, {5: 4861, 6: 4859}, max_iterations=T)
+    if name == "h74":
+        code = L.create_test_ldpc_code()
+        code.max_iterations = T
+        return code
+    if name == "r504":
+        return L.codes.regular_code(504, 3, 6, max_iterations=T)
+    return L.codes.dvbs2_shaped(max_iterations=T) if name == "dvbs2" else L.codes.qc_shaped(max_iterations=T)
 
 
-def workload_name(args):
-    shape = {"dvbs2": "(16200,7200)-shaped E=48599", "qc": "(9472,8192)-shaped QC E=37888",
-             "dv12": "(16200,6480) IRA dv 12/3/2 E=53459"}[args.code]
-    dec = {"n2d2": "Neural2DMinSumDecoder type 2", "n2d1": "Neural2DMinSumDecoder type 1", "nnms": "NeuralMinSumDecoder (per-edge weights)", "oms2": "Neural2DOffsetMinSumDecoder type 2", "rcq": "RCQMinSumDecoder bc=3", "wrcq1": "WeightedRCQ type 1 bc=3",
-           "basic": "BasicMinSumDecoder f64 factor 0.7"}[args.decoder]
-    return f"{dec}, {T_ITERS} iters, {shape}, AWGN {SNR_DB} dB reference sign convention"
+SHAPES = {"dvbs2": "(16200,7200)-shaped E=48599", "qc": "(9472,8192)-shaped QC E=37888",
+          "dv12": "(16200,6480) IRA dv 12/3/2 E=53459", "h74": "(7,4) test code E=13", "r504": "(3,6)-regular n=504 E=1512"}
+DECODERS = {"n2d2": "Neural2DMinSumDecoder type 2", "n2d1": "Neural2DMinSumDecoder type 1",
+            "nnms": "NeuralMinSumDecoder (per-edge weights)", "oms2": "Neural2DOffsetMinSumDecoder type 2",
+            "rcq": "RCQMinSumDecoder bc=3", "wrcq1": "WeightedRCQ type 1 bc=3", "basic": "BasicMinSumDecoder f64 factor 0.7"}
+
+
+def workload_name(decoder, code, T=T_ITERS, snr=SNR_DB):
+    return f"{DECODERS[decoder]}, {T} iters, {SHAPES[code]}, AWGN {snr} dB reference sign convention"
 
 
 def det_weights(T):
@@ -84,71 +106,74 @@ def det_weights(T):
     return (0.75 + t / 64).astype(np.float32), (1 - t / 32).astype(np.float32)
 
 
-def build_decoder(L, code, kind):
+def build_decoder(L, code, kind, T=None):
     import torch
-    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-    b, a = det_weights(T_ITERS)
+    T = T_ITERS if T is None else T
+    b, a = det_weights(T)
+
+    def fill(table, column):
+        with torch.no_grad():
+            table.copy_(torch.from_numpy(column)[:, None].expand_as(table))
+
     if kind == "n2d2":
-        dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T_ITERS)
-        with torch.no_grad():
-            dec._beta_table.copy_(torch.from_numpy(b)[:, None].expand_as(dec._beta_table))
-            dec._alpha_table.copy_(torch.from_numpy(a)[:, None].expand_as(dec._alpha_table))
+        dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
+        fill(dec._beta_table, b)
+        fill(dec._alpha_table, a)
     elif kind == "n2d1":
-        dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=1, max_iterations=T_ITERS)
-        with torch.no_grad():
-            dec._beta_table.copy_(torch.from_numpy(b)[:, None].expand_as(dec._beta_table))
+        dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=1, max_iterations=T)
+        fill(dec._beta_table, b)
     elif kind == "oms2":
-        dec = L.Neural2DOffsetMinSumDecoder(code, weight_sharing_type=2, max_iterations=T_ITERS)
+        dec = L.Neural2DOffsetMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
         with torch.no_grad():
             dec._beta_table.fill_(0.15)
             dec._alpha_table.fill_(0.02)
     elif kind == "nnms":
-        dec = L.NeuralMinSumDecoder(code, max_iterations=T_ITERS)
-        with torch.no_grad():
-            dec._beta_table.copy_(torch.from_numpy(b)[:, None].expand_as(dec._beta_table))
+        dec = L.NeuralMinSumDecoder(code, max_iterations=T)
+        fill(dec._beta_table, b)
     elif kind == "rcq":
-        dec = L.RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=qp, max_iterations=T_ITERS)
+        dec = L.RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=QP, max_iterations=T)
     elif kind == "wrcq1":
-        dec = L.WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=qp, weight_sharing_type=1, max_iterations=T_ITERS)
-        with torch.no_grad():
-            dec._beta_table.copy_(torch.from_numpy(b)[:, None].expand_as(dec._beta_table))
+        dec = L.WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=QP, weight_sharing_type=1, max_iterations=T)
+        fill(dec._beta_table, b)
     else:
         dec = L.BasicMinSumDecoder(code, factor=0.7)
     return dec
 
 
-def algorithmic_bytes(code, kind):
-    """bytes per frame-iteration at storage width, and per kernel launch per frame."""
+def algorithmic_bytes(code, kind, posterior):
+    """bytes per frame-iteration at storage width, and per kernel launch per frame.  With `posterior`
+    the final variable-node pass also writes the frame's posterior row entries."""
     g = code.graph
     E, n = g.E, g.n
     if kind in ("rcq", "wrcq1"):
-        return dict(frame_iter=10 * E + 4 * n, cn=4 * E + 1 * E, vn=1 * E + 4 * n + 4 * E, vn_final=1 * E + 4 * n)
-    w = 8 if kind == "basic" else 4
-    return dict(frame_iter=4 * w * E + w * n, cn=2 * w * E, vn=2 * w * E + w * n, vn_final=w * E + w * n)
+        w, cw = 4, 1
+    else:
+        w = cw = 8 if kind == "basic" else 4
+    return dict(frame_iter=(2 * w + 2 * cw) * E + w * n, cn=(w + cw) * E, vn=(w + cw) * E + w * n,
+                vn_final=cw * E + w * n + (w * n if posterior else 0))
 
 
-def oracle_setup(L, code, kind):
-    from oracle.restatement import MODE_NMS, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule, quantizer_thresholds
+def oracle_setup(code, kind, T=T_ITERS):
+    from oracle.restatement import (MODE_NMS, MODE_OFFSET, MODE_RCQ, MODE_WRCQ, SparseGraph, quantizer_schedule,
+                                    quantizer_thresholds)
     g = code.graph
     og = SparseGraph.from_coo(g.n, g.m, g.edge_check, g.check_var)
-    b, a = det_weights(T_ITERS)
-    kw = dict(T=T_ITERS, want_posterior=False)
-    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-    thr = np.array([quantizer_thresholds(3, C, gm) for C, gm in qp]).astype(np.float32)
+    b, a = det_weights(T)
+    kw = dict(T=T, want_posterior=False)
+    thr = np.array([quantizer_thresholds(3, C, gm) for C, gm in QP]).astype(np.float32)
     if kind == "n2d2":
         kw.update(mode=MODE_NMS, beta=np.tile(b[:, None], (1, g.E)), alpha=np.tile(a[:, None], (1, g.n)))
     elif kind in ("n2d1", "nnms"):
         kw.update(mode=MODE_NMS, beta=np.tile(b[:, None], (1, g.E)))
     elif kind == "oms2":
-        from oracle.restatement import MODE_OFFSET
-        kw.update(mode=MODE_OFFSET, beta=np.full((T_ITERS, g.E), np.float32(0.15)), alpha=np.full((T_ITERS, g.n), np.float32(0.02)))
+        kw.update(mode=MODE_OFFSET, beta=np.full((T, g.E), np.float32(0.15)), alpha=np.full((T, g.n), np.float32(0.02)))
     elif kind == "rcq":
-        kw.update(mode=MODE_RCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T_ITERS, 3))
+        kw.update(mode=MODE_RCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 3))
     elif kind == "wrcq1":
-        kw.update(mode=MODE_WRCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T_ITERS, 3),
-                  beta=np.tile(b[:, None], (1, g.E)), alpha=np.ones((T_ITERS, g.n), np.float32))
+        kw.update(mode=MODE_WRCQ, bc=3, thresholds=thr, quantizer_of_iter=quantizer_schedule(T, 3),
+                  beta=np.tile(b[:, None], (1, g.E)), alpha=np.ones((T, g.n), np.float32))
     else:
-        kw.update(mode=MODE_NMS, dtype=np.float64, beta=np.full((T_ITERS, g.E), 0.7))
+        kw.update(mode=MODE_NMS, dtype=np.float64, beta=np.full((T, g.E), 0.7))
     return og, kw
 
 
@@ -158,10 +183,11 @@ def host_llrs(code, frames, seed, dtype=np.float32):
     return (2 * (-1.0 + np.sqrt(s2) * rng.standard_normal((frames, code.n), dtype=np.float32)) / s2).astype(dtype)
 
 
-def cpu_leg(L, code, kind, seconds, threads):
-    """Time the oracle port on a bounded sample of the same workload.  Returns dict for `cpu_baseline`."""
+def cpu_leg(code, kind, seconds, threads, posterior):
+    """Time the oracle port on a bounded sample of the same workload.  Returns the `cpu_baseline` dict."""
     from oracle import capi as O
-    og, kw = oracle_setup(L, code, kind)
+    og, kw = oracle_setup(code, kind)
+    kw["want_posterior"] = posterior
     dtype = kw.get("dtype", np.float32)
     probe = host_llrs(code, max(threads, 8), 99, dtype)
     t0 = time.perf_counter()
@@ -176,7 +202,7 @@ def cpu_leg(L, code, kind, seconds, threads):
     fps = frames / dt
     return dict(value=fps * code.k / 1e9, unit=UNIT, cores=threads, kind="port", frames_per_s=fps,
                 sample=f"{frames} frames of the same workload ({dt:.1f} s), oracle/minsum_oracle.c with {threads} OpenMP threads, "
-                       f"avg iterations {float(res.iterations.mean()):.2f}"), dt, frames
+                       f"avg iterations {float(res.iterations.mean()):.2f}")
 
 
 class ClockSampler:
@@ -236,6 +262,50 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic(kind, code_name, kernel, frames_padded):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full`
+    raw page of this round (profiles/r02_ncu_full_<decoder>_<code>_<frames>frames_raw.csv).  The capture taken at
+    the benchmarked frame count is used as is; otherwise the nearest one is scaled per frame.  (None, why) if absent."""
+    files = glob.glob(os.path.join(ROOT, "profiles", f"r02_ncu_full_{kind}_{code_name}_*frames_raw.csv"))
+    best = None
+    for f in files:
+        try:
+            frames = int(os.path.basename(f).split("_")[-2].replace("frames", ""))
+        except ValueError:
+            continue
+        if best is None or abs(frames - frames_padded) < abs(best[1] - frames_padded):
+            best = (f, frames)
+    if best is None:
+        return None, "no r02 ncu capture committed for this (decoder, code)"
+    f, frames = best
+    rows = list(csv.reader(open(f, newline="")))
+    head, units = rows[0], rows[1]
+    col = {name: i for i, name in enumerate(head)}
+    want = [kernel] if kernel != "cn_kernel" else ["cn_kernel", "cn_wide_kernel"]
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        hit = next((w for w in want if w + "<" in name), None)
+        if hit is None:
+            continue
+        targs = [a.strip() for a in name.split(hit + "<")[1].split(">")[0].split(",")]
+        if hit == "vn_kernel" and len(targs) >= 3 and targs[2] != "0":
+            continue    # the dominant variable-node launch is the non-final variant <Real, QUANT, FINAL=0, POST>
+        if True:
+            try:
+                rd = float(r[col["dram__bytes_read.sum"]]) * _UNIT_SCALE[units[col["dram__bytes_read.sum"]]]
+                wr = float(r[col["dram__bytes_write.sum"]]) * _UNIT_SCALE[units[col["dram__bytes_write.sum"]]]
+            except (KeyError, ValueError):
+                continue
+            scale = frames_padded / frames
+            note = os.path.relpath(f, ROOT) + (f" (launch `{name}`, {frames} frames" +
+                                              ("" if frames == frames_padded else f", scaled x{scale:g} per frame") + ")")
+            return (rd + wr) * scale, note
+    return None, f"{os.path.relpath(f, ROOT)} holds no launch of {kernel}"
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host
     buffer is allocated, so that the end-to-end leg's staging memory is local to the GPU's PCIe root.  With
@@ -255,15 +325,20 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+# =====================================================================================================
+# reference arm: the reference's algorithm on the host cores (C port in oracle/; the reference itself is pure
+# Python and cannot travel to the GPU box).  No part of the CUDA package is imported here.
+# =====================================================================================================
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import ldpc_b200 as L
     from oracle import capi as O
+    L = host_only_package()
     code = make_code(L, args.code)
     threads = os.cpu_count() or 1
-    og, kw = oracle_setup(L, code, args.decoder)
+    og, kw = oracle_setup(code, args.decoder)
+    kw["want_posterior"] = not args.decode_only
     dtype = kw.get("dtype", np.float32)
     # step = a bounded sample sized so the whole run stays within a few minutes
     budget = 150.0 / max(1, args.steps + args.warmup)
@@ -286,7 +361,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.decoder == "basic" else "f32", "data": "synthetic",
         "frames_per_s": fps,
-        "config": {"workload": workload_name(args), "frames_per_step": frames,
+        "config": {"workload": workload_name(args.decoder, args.code), "frames_per_step": frames,
+                   "call": "decode() (decisions only)" if args.decode_only else "forward() (decisions + posterior + iterations)",
                    "note": "reference algorithm timed as its C port (the reference is pure Python and cannot travel to the GPU box)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{frames} frames per step x {args.steps} steps, avg iterations {float(res.iterations.mean()):.2f}"},
@@ -295,214 +371,322 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def mc_leg(L, code, kind, B, local_rank, rank, world, barrier, dev, T=50, snrs=(2.0, 3.0), rounds=3):
-    import torch
-    import torch.distributed as dist
-    t = np.arange(T, dtype=np.float64)
-    beta = np.minimum(0.75 + t / 64, 1.0).astype(np.float32)
-    qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
-    out = []
-    for compact in (0, 1):
-        os.environ["LDPC_COMPACT"] = str(compact)      # read when the decoder handle is created
-        if kind == "n2d2":
-            dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
-            with torch.no_grad():
-                dec._beta_table.copy_(torch.from_numpy(beta)[:, None].expand_as(dec._beta_table))
-                dec._alpha_table.fill_(1.0)
-        elif kind == "rcq":
-            dec = L.RCQMinSumDecoder(code, bc=3, bv=8, quantizer_params=qp, max_iterations=T)
-        else:
-            dec = L.WeightedRCQDecoder(code, bc=3, bv=8, quantizer_params=qp, weight_sharing_type=1, max_iterations=T)
-            with torch.no_grad():
-                dec._beta_table.copy_(torch.from_numpy(beta)[:, None].expand_as(dec._beta_table))
-        eng = dec._engine(local_rank)
-        counters = torch.zeros(4, dtype=torch.int64, device=dev)
-        for snr in snrs:
-            eng.mc_round(snr, B, seed=7, frame0=rank * B, llr_sign=1, counters=counters)     # warm-up / allocation
-            barrier()
-            counters.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for r in range(rounds):
-                eng.mc_round(snr, B, seed=11, frame0=(r * world + rank) * B, llr_sign=1, counters=counters)
-            e1.record()
-            barrier()
-            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-                dist.all_reduce(counters)
-            fe, be, it, nf = (int(v) for v in counters.tolist())
-            fps = nf / (float(ms.item()) / 1e3)
-            out.append({"snr_db": snr, "max_iterations": T, "compaction": bool(compact), "frames": nf,
-                        "frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "avg_iterations": it / max(nf, 1),
-                        "fer": fe / max(nf, 1), "ber": be / max(nf * code.n, 1)})
-        del dec, eng
-    os.environ.pop("LDPC_COMPACT", None)
-    return out
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+class Rig:
+    """Per-process context of the GPU arm: rank / world, device, barrier and max-over-ranks reduction."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device(self, fn, steps, warmup):
+        """W warm-ups, then K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over
+        ranks.  Returns (ms per step, last result)."""
+        torch = self.torch
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, out
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    import ldpc_b200 as L
-    code = make_code(L, args.code)
-    g = code.graph
-    kind = args.decoder
-    dec = build_decoder(L, code, kind)
-    B = int(args.frames)
-    f64 = kind == "basic"
-    eng = dec._engine(local_rank)
-    eng.reserve(B)
-
-    # synthetic LLRs generated on the device (Philox), distinct frames per rank; resident before timing
-    llr = L.awgn_llr(g.n, B, SNR_DB, seed=1234, frame0=rank * B, llr_sign=-1, device=local_rank)
-    if f64:
-        llr = llr.double()
-    torch.cuda.synchronize()
-
-    def step_device():
-        return eng.decode_device(llr, want_posterior=False)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        bits, _, iters, succ = step_device()
-    barrier()
-    avg_iters = float(iters.float().mean().item())
-    eng.profile_read(reset=True)
-    eng.profile_mode(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        bits, _, iters, succ = step_device()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else {}
-    ms = e0.elapsed_time(e1)
-    prof = eng.profile_read(reset=True)
-    eng.profile_mode(0)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    fps = world * B * args.steps / (ms_max / 1e3)
-    value = fps * code.k / 1e9
-
-    # ---- roofline of the dominant kernel (live CUDA-event durations from inside the timed region) ----
-    ab = algorithmic_bytes(code, kind)
-    Bp = prof["frames_padded"]
+def kernel_roofline(prof, ab, Bp, steps, T, step_ms, kind, code_name):
+    """Roofline of the dominant kernel from the library's per-launch CUDA-event durations (profiling mode) inside the
+    timed region: algorithmic bytes per launch / average launch duration, against the measured HBM peak."""
     peak, peak_src = peak_hbm()
-    vn_per_step = prof["vn_launches"] / args.steps
+    vn_per_step = prof["vn_launches"] / steps
     vn_bytes = ((vn_per_step - 1) * ab["vn"] + ab["vn_final"]) / vn_per_step * Bp
     cn_bytes = ab["cn"] * Bp
     vn_ms = prof["vn_ms"] / max(prof["vn_launches"], 1)
     cn_ms = prof["cn_ms"] / max(prof["cn_launches"], 1)
-    vn_gbs = vn_bytes / (vn_ms * 1e-3) / 1e9
-    cn_gbs = cn_bytes / (cn_ms * 1e-3) / 1e9
+    vn_gbs = vn_bytes / (vn_ms * 1e-3) / 1e9 if vn_ms > 0 else 0.0
+    cn_gbs = cn_bytes / (cn_ms * 1e-3) / 1e9 if cn_ms > 0 else 0.0
     dominant = "vn_kernel" if prof["vn_ms"] >= prof["cn_ms"] else "cn_kernel"
     ach = vn_gbs if dominant == "vn_kernel" else cn_gbs
-    step_bytes = T_ITERS * ab["frame_iter"] * B
-    roofline = {
+    step_bytes = T * ab["frame_iter"] * Bp
+    traffic, traffic_src = ncu_traffic(kind, code_name, dominant, Bp)
+    return {
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": (NCU_TRAFFIC_BYTES_PER_FRAME[(kind, args.code, dominant)] * Bp
-                    if (kind, args.code, dominant) in NCU_TRAFFIC_BYTES_PER_FRAME else None),
-        "traffic_source": "ncu --set full at 8192 frames per launch, scaled per frame (profiles/README.md, r01b captures)",
+        "traffic": traffic, "traffic_source": traffic_src,
         "kernel": dominant, "peak_source": peak_src,
         "bytes_per_launch": vn_bytes if dominant == "vn_kernel" else cn_bytes,
         "avg_launch_ms": vn_ms if dominant == "vn_kernel" else cn_ms,
         "vn_kernel": {"gbs": vn_gbs, "frac": vn_gbs / peak, "ms_total": prof["vn_ms"], "launches": prof["vn_launches"]},
         "cn_kernel": {"gbs": cn_gbs, "frac": cn_gbs / peak, "ms_total": prof["cn_ms"], "launches": prof["cn_launches"]},
         "other_ms_total": prof["other_ms"],
-        "whole_step": {"gbs": step_bytes / (ms_max / args.steps * 1e-3) / 1e9,
-                       "frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak,
+        "whole_step": {"gbs": step_bytes / (step_ms * 1e-3) / 1e9, "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
                        "bytes_per_frame_iter": ab["frame_iter"]},
     }
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host buffers, copies inside) ----
-    e2e = None
-    if not args.no_e2e:
-        rdt = np.float64 if f64 else np.float32
-        pin_llr = L.PinnedBuffer((B, g.n), rdt)
-        pin_bits = L.PinnedBuffer((B, g.n), np.uint8)
-        pin_it = L.PinnedBuffer((B,), np.int32)
-        pin_su = L.PinnedBuffer((B,), np.uint8)
-        chunk = 8192
-        for s in range(0, B, chunk):   # fill the pinned input from the device-generated LLRs
-            pin_llr.array[s:s + chunk] = llr[s:s + chunk].cpu().numpy()
-        outs = dict(bits=pin_bits.array, iterations=pin_it.array, success=pin_su.array)
-        for _ in range(max(1, min(args.warmup, 2))):
-            eng.decode_host(pin_llr.array, out=outs)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.decode_host(pin_llr.array, out=outs)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e_fps = world * B * args.steps / dt
-        same = bool(np.array_equal(pin_bits.array[:256], bits[:256].cpu().numpy()))
-        e2e = {"value": e2e_fps * code.k / 1e9, "unit": UNIT, "frames_per_s": e2e_fps,
-               "h2d_bytes_per_step": int(B * g.n * np.dtype(rdt).itemsize),
-               "d2h_bytes_per_step": int(B * g.n + B * 4 + B), "ms_per_step": 1e3 * dt / args.steps,
-               "api": "ldpc_decode_host (pinned host LLR in; hard decisions + iterations + success out)",
-               "matches_device_path": same}
-        for p in (pin_llr, pin_bits, pin_it, pin_su):
-            p.free()
 
-    # ---- early-stop leg: BASELINE configs[4] shape -- T = 50, LLRs of the all-zero codeword in the
-    # converging sign convention, AWGN generated on the device (ldpc_mc_round), frames stop at different
-    # iterations; with and without frame compaction.  Reported next to the headline, not part of `value`.
-    early = None
-    if not args.no_mc and kind != "basic":
-        early = mc_leg(L, code, kind, B, local_rank, rank, world, barrier, dev)
+def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampler=None):
+    """One device-resident leg: LLRs generated on the device (Philox, distinct frames per rank, reference sign
+    convention at SNR_DB), resident before timing; returns the result record and the pieces the caller reuses."""
+    torch = rig.torch
+    g = code.graph
+    dec = build_decoder(L, code, kind)
+    eng = dec._engine(rig.local_rank)
+    eng.reserve(B)
+    llr = L.awgn_llr(g.n, B, SNR_DB, seed=1234, frame0=rig.rank * B, llr_sign=-1, device=rig.local_rank)
+    if kind == "basic":
+        llr = llr.double()
+    torch.cuda.synchronize()
+
+    def step():
+        return eng.decode_device(llr, want_posterior=posterior)
+
+    for _ in range(warmup):
+        out = step()
+    rig.barrier()
+    avg_iters = float(out[2].float().mean().item())
+    eng.profile_read(reset=True)
+    eng.profile_mode(1)
+    if sampler is not None:
+        sampler.start()
+    ms, out = rig.timed_device(step, steps, 0)
+    clocks = sampler.stop() if sampler is not None else None
+    prof = eng.profile_read(reset=True)
+    eng.profile_mode(0)
+    fps = rig.world * B * steps / (ms * steps / 1e3)
+    ab = algorithmic_bytes(code, kind, posterior)
+    roof = kernel_roofline(prof, ab, prof["frames_padded"], steps, T_ITERS, ms, kind, code_name)
+    rec = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "avg_iterations": avg_iters,
+           "edge_msgs_per_s": fps * T_ITERS * 2 * g.E, "launches": int(prof["launches"]), "roofline": roof}
+    return rec, dec, eng, llr, out, clocks
+
+
+def e2e_leg(rig, L, code, eng, llr, B, steps, warmup, posterior, check_bits):
+    """ldpc_decode_host on pinned host buffers: H2D of the LLRs, decode, D2H of every output, all inside the timed
+    region (host wall clock around the blocking call; max over ranks)."""
+    torch = rig.torch
+    g = code.graph
+    rdt = np.float64 if eng.dtype == np.float64 else np.float32
+    pins = {"llr": L.PinnedBuffer((B, g.n), rdt), "bits": L.PinnedBuffer((B, g.n), np.uint8),
+            "iterations": L.PinnedBuffer((B,), np.int32), "success": L.PinnedBuffer((B,), np.uint8)}
+    if posterior:
+        pins["posterior"] = L.PinnedBuffer((B, g.n), rdt)
+    chunk = 8192
+    for s in range(0, B, chunk):   # fill the pinned input from the device-generated LLRs
+        pins["llr"].array[s:s + chunk] = llr[s:s + chunk].cpu().numpy()
+    outs = {k: p.array for k, p in pins.items() if k != "llr"}
+    for _ in range(max(1, min(warmup, 2))):
+        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs)
+    rig.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs)
+    torch.cuda.synchronize()
+    dt = rig.max_over_ranks(time.perf_counter() - t0)
+    fps = rig.world * B * steps / dt
+    same = bool(np.array_equal(pins["bits"].array[:256], check_bits[:256].cpu().numpy()))
+    d2h = B * g.n + B * 4 + B + (B * g.n * np.dtype(rdt).itemsize if posterior else 0)
+    rec = {"value": fps * code.k / 1e9, "unit": UNIT, "frames_per_s": fps,
+           "h2d_bytes_per_step": int(B * g.n * np.dtype(rdt).itemsize), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": 1e3 * dt / steps,
+           "api": "ldpc_decode_host (pinned host LLR in; hard decisions" + (" + posteriors" if posterior else "") +
+                  " + iterations + success out)",
+           "matches_device_path": same}
+    for p in pins.values():
+        p.free()
+    return rec
+
+
+def release(*objs):
+    import gc
+    for o in objs:
+        close = getattr(o, "close", None)
+        if close:
+            close()
+    gc.collect()
+
+
+def config_legs(rig, L, args):
+    """One short leg per remaining BASELINE.json configuration (configs[0], [2], [3], [4])."""
+    torch = rig.torch
+    legs = []
+    steps, warmup = 5, 3
+
+    def kernel_leg(tag, code_name, kind, B, posterior):
+        code = make_code(L, code_name)
+        rec, dec, eng, llr, out, _ = device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior)
+        r = rec["roofline"]
+        leg = {"config": tag, "workload": workload_name(kind, code_name), "frames_per_gpu": B,
+               "call": "forward()" if posterior else "decode()", "steps": steps, "warmup": warmup,
+               "frames_per_s": rec["frames_per_s"], "info_gbps": rec["info_gbps"], "ms_per_step": rec["ms_per_step"],
+               "avg_iterations": rec["avg_iterations"],
+               "roofline": {"cn_frac": r["cn_kernel"]["frac"], "vn_frac": r["vn_kernel"]["frac"],
+                            "whole_step_frac": r["whole_step"]["frac"], "bytes_per_frame_iter": r["whole_step"]["bytes_per_frame_iter"],
+                            "peak_gbs": r["peak"]}}
+        del llr, out
+        release(eng)
+        del dec, eng
+        torch.cuda.empty_cache()
+        return leg
+
+    # C1: create_test_ldpc_code() + BasicMinSumDecoder factor 0.7, 10 iterations, float64 (configs[0])
+    legs.append(kernel_leg("C1", "h74", "basic", 1 << 22, False))
+    # C3: RCQMinSumDecoder bc=3 bv=8 on the (16200,7200) shape (configs[2]); decode() returns no posterior
+    legs.append(kernel_leg("C3", "dvbs2", "rcq", args.frames, False))
+    # C4: WeightedRCQ type-1 degree weights on the (9472,8192)-shaped QC code (configs[3]); forward() with posterior
+    legs.append(kernel_leg("C4", "qc", "wrcq1", args.frames, True))
+    # C5: FER/BER Monte-Carlo sweep through LDPSimulator.simulate_decoder (simulation_framework.py:141-176) over the
+    # SimulationConfig default grid 0..6 dB step 0.5, T = 50, frames sharded over the ranks (configs[4])
+    legs.append(mc_sweep_leg(rig, L, args))
+    return legs
+
+
+def mc_sweep_leg(rig, L, args):
+    torch, dist = rig.torch, rig.dist
+    T = 50
+    code = make_code(L, "dvbs2", T)
+    dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
+    t = np.arange(T, dtype=np.float64)
+    with torch.no_grad():
+        dec._beta_table.copy_(torch.from_numpy(np.minimum(0.75 + t / 64, 1.0).astype(np.float32))[:, None].expand_as(dec._beta_table))
+        dec._alpha_table.fill_(1.0)
+    per_gpu = min(args.frames, 32768)
+    cfg = L.SimulationConfig(snr_range=(0.0, 6.0), snr_step=0.5, max_frames=per_gpu * rig.world * 2, max_errors=200,
+                             batch_frames=per_gpu, seed=20, save_results=False)
+    sim = L.LDPSimulator(cfg)
+    sim.simulate_single_snr(dec, code, 3.0, per_gpu * rig.world, 10 ** 9)     # warm-up / workspace allocation
+    rig.barrier()
+    t0 = time.perf_counter()
+    res = sim.simulate_decoder(dec, code, "N-2D-NMS Type 2")
+    torch.cuda.synchronize()
+    dt = rig.max_over_ranks(time.perf_counter() - t0)
+    frames = int(sum(res.total_frames))
+    leg = {"config": "C5", "workload": f"LDPSimulator.simulate_decoder, {DECODERS['n2d2']}, T = {T}, {SHAPES['dvbs2']}, "
+                                       f"SNR 0..6 dB step 0.5 (13 points), all-zero codeword, converging sign convention, Philox AWGN on device",
+           "max_frames_per_point": cfg.max_frames, "max_errors": cfg.max_errors, "batch_frames_per_gpu": per_gpu,
+           "frames": frames, "seconds": dt, "frames_per_s": frames / dt, "info_gbps": frames / dt * code.k / 1e9,
+           "snr_db": [float(s) for s in res.snr_values], "fer": res.frame_error_rates, "ber": res.bit_error_rates,
+           "avg_iterations": res.average_iterations, "frames_per_point": res.total_frames,
+           "frame_errors_per_point": res.total_errors, "seconds_per_point": res.simulation_times}
+    # Monte-Carlo parity across GPU counts: one sharded round of `world * R` global frames (all-reduced counters)
+    # against the same global frame range decoded by rank 0 alone.  Noise is keyed by the global frame index.
+    parity = None
+    if rig.world > 1:
+        R = 4096
+        eng = dec._engine(rig.local_rank)
+        parity = True
+        for snr in (1.5, 2.5):
+            c = torch.zeros(4, dtype=torch.int64, device=rig.dev)
+            eng.mc_round(snr, R, seed=77, frame0=rig.rank * R, llr_sign=1, counters=c)
+            dist.all_reduce(c)
+            alone = torch.zeros(4, dtype=torch.int64, device=rig.dev)
+            if rig.rank == 0:
+                eng.mc_round(snr, R * rig.world, seed=77, frame0=0, llr_sign=1, counters=alone)
+            dist.broadcast(alone, src=0)
+            parity = parity and bool(torch.equal(c, alone))
+            leg.setdefault("mc_parity_counters", []).append({"snr_db": snr, "sharded": c.tolist(), "rank0_alone": alone.tolist()})
+    leg["mc_parity"] = parity
+    release(*dec._engines.values())
+    return leg
+
+
+def run_ours(args):
+    rig = Rig(args)
+    torch = rig.torch
+    if rig.world != args.gpus and rig.world > 1:
+        args.gpus = rig.world
+    import ldpc_b200 as L
+
+    code = make_code(L, args.code)
+    g = code.graph
+    kind = args.decoder
+    B = int(args.frames)
+    f64 = kind == "basic"
+    posterior = not args.decode_only and kind not in ("basic", "rcq")   # decode() of those two returns no posterior
+
+    # ---- headline: device-resident, the reference's forward() surface ----
+    sampler = ClockSampler(rig.local_rank) if rig.rank == 0 else None
+    head, dec, eng, llr, out, clocks = device_leg(rig, L, code, args.code, kind, B, args.steps, args.warmup, posterior, sampler)
+    bits = out[0]
+    # ---- the same step without the posterior (decode() surface) ----
+    decode_only = None
+    if posterior:
+        k = max(3, min(args.steps, 10))
+        eng.profile_read(reset=True)
+        eng.profile_mode(1)
+        ms, _ = rig.timed_device(lambda: eng.decode_device(llr, want_posterior=False), k, 2)
+        prof = eng.profile_read(reset=True)
+        eng.profile_mode(0)
+        fps = rig.world * B / (ms / 1e3)
+        r = kernel_roofline(prof, algorithmic_bytes(code, kind, False), prof["frames_padded"], k, T_ITERS, ms, kind, args.code)
+        decode_only = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "steps": k,
+                       "vn_frac": r["vn_kernel"]["frac"], "cn_frac": r["cn_kernel"]["frac"], "whole_step_frac": r["whole_step"]["frac"]}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host buffers, copies inside) ----
+    e2e = e2e_decode_only = None
+    if not args.no_e2e:
+        e2e = e2e_leg(rig, L, code, eng, llr, B, args.steps, args.warmup, posterior, bits)
+        if posterior:
+            e2e_decode_only = e2e_leg(rig, L, code, eng, llr, B, max(3, min(args.steps, 5)), 1, False, bits)
+    del llr, out, bits
+    release(eng)
+    del dec, eng
+    torch.cuda.empty_cache()
+
+    configs = None if args.no_configs else config_legs(rig, L, args)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _, _ = cpu_leg(L, code, kind, args.cpu_seconds, os.cpu_count() or 1)
+    if rig.rank == 0 and rig.world == 1 and not args.no_cpu:
+        cpu = cpu_leg(code, kind, args.cpu_seconds, os.cpu_count() or 1, posterior)
 
-    if rank == 0:
+    if rig.rank == 0:
+        roof = head["roofline"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if f64 else "f32", "data": "synthetic",
-            "frames_per_s": fps, "edge_msgs_per_s": fps * T_ITERS * 2 * g.E, "avg_iterations": avg_iters,
-            "config": {"workload": workload_name(args), "frames_per_gpu": B, "global_frames": world * B,
+            "metric": METRIC, "value": head["info_gbps"], "unit": UNIT, "n_gpus": rig.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if f64 else "f32", "data": "synthetic",
+            "frames_per_s": head["frames_per_s"], "edge_msgs_per_s": head["edge_msgs_per_s"],
+            "avg_iterations": head["avg_iterations"],
+            "config": {"workload": workload_name(kind, args.code),
+                       "call": "forward(): decisions + posterior + iterations" if posterior else "decode(): decisions + success + iterations",
+                       "frames_per_gpu": B, "global_frames": rig.world * B,
                        "n": g.n, "k": code.k, "E": g.E, "iterations": T_ITERS, "early_stop": True,
-                       "l2": "inputs larger than L2 (message arrays %.1f GB per GPU)" % (2 * 4 * g.E * Bp / 1e9),
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "host_affinity": (f"{len(numa)} CPUs next to the GPU (NVML)" if numa else "unbound")},
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "early_stop_mc": early,
-            "gpu_launches": int(prof["launches"]),
+                       "l2": "inputs larger than L2 (message arrays %.1f GB per GPU)" % (algorithmic_bytes(code, kind, False)["cn"] * B / 1e9),
+                       "parallelism": f"frames sharded over {rig.world} GPU(s), no data-path collective",
+                       "host_affinity": (f"{len(rig.numa)} CPUs next to the GPU (NVML)" if rig.numa else "unbound")},
+            "roofline": roof, "e2e": e2e, "decode_only": decode_only, "e2e_decode_only": e2e_decode_only,
+            "cpu_baseline": cpu, "configs": configs,
+            "mc_parity": (next((c.get("mc_parity") for c in configs if c["config"] == "C5"), None) if configs else None),
+            "gpu_launches": head["launches"],
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if rig.world > 1:
+        rig.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

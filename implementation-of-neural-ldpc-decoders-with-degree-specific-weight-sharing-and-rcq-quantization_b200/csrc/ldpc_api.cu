@@ -477,6 +477,11 @@ struct ldpc_decoder {
     void* d_alpha = nullptr;               // [T][n_alpha]
     float* d_thr = nullptr;                // [Q][nth]
     float* d_lut = nullptr;                // [Q][2^bc]
+    int32_t* d_qoi = nullptr;              // [T] quantiser of each iteration (on-chip decode)
+    int32_t* d_mono = nullptr;             // [Q]
+    int all_mono = 1;
+    int use_small = 1;                     // LDPC_SMALL=0: never take the on-chip decode for small codes
+    int64_t stat_small = 0;
     HostPipe pipe;
     int64_t host_chunk = 0;
     int layered_levels = 1;       // LDPC_LAYERED_LEVELS=0: always the sequential layered kernel
@@ -817,6 +822,49 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
     return LDPC_OK;
 }
 
+// On-chip decode (ldpc_small.cu) of the frames resident in `ws`, if the code is small enough for it.
+bool fill_small(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, SmallLaunch& sp) {
+    const ldpc_graph* g = d->g;
+    if (!d->use_small || d->schedule != LDPC_SCHEDULE_FLOODING) return false;
+    sp.llrT = ws.llrT;
+    sp.postT = want_post ? ws.post : nullptr;
+    sp.hardw = ws.hardw;
+    sp.Wn = Bp / 32;
+    sp.done = ws.done;
+    sp.iters = ws.iters;
+    sp.success = ws.success;
+    sp.B = B;
+    sp.Bp = Bp;
+    sp.T = d->T;
+    sp.early_stop = d->early_stop;
+    sp.n = g->n;
+    sp.E = (int)g->E;
+    sp.n_checks = (int)g->cn[1].items.size();
+    sp.cn_items = g->cn[1].d;
+    sp.vn_items = g->vn[1].d;
+    sp.slot_var = g->d_slot_var;
+    sp.vslots = g->d_vslots;
+    sp.vpos_var = g->d_vpos_var;
+    sp.bidx = d->d_bidx;
+    sp.beta_per_edge = d->beta_per_edge;
+    sp.beta = d->d_beta;
+    sp.n_beta = d->n_beta;
+    sp.aidx = d->d_aidx;
+    sp.aidx_slot = d->d_aidx_slot;
+    sp.alpha = d->d_alpha;
+    sp.n_alpha = d->n_alpha;
+    sp.check_rule = d->check_rule;
+    sp.bc = d->bc;
+    sp.nth = d->nth;
+    sp.n_quant = d->Q;
+    sp.thr = d->d_thr;
+    sp.lut = d->d_lut;
+    sp.q_of_iter = d->d_qoi;
+    sp.mono = d->d_mono;
+    sp.all_mono = d->all_mono;
+    return small_decode_fits(d->dtype, sp);
+}
+
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
 // Large batches can afford a look after every iteration (an iteration is milliseconds long); smaller ones
 // space the checkpoints out so that the syncs stay a small part of the decode.  `quiet` counts the
@@ -1002,6 +1050,15 @@ int job_start(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, i
         int rc = run_layered(d, root, B, Bp, j.want_post, stream);
         if (rc) return rc;
         return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
+    }
+    {
+        SmallLaunch sp{};
+        if (fill_small(d, root, B, Bp, j.want_post, sp)) {
+            // small code: the whole decode in one launch, messages in shared memory
+            LAUNCH(K_OTHER, launch_small_decode(d->dtype, sp, stream));
+            d->stat_small++;
+            return emit_level(d, root, B, Bp, nullptr, nullptr, o, stream);
+        }
     }
     if (launch_bound(d, Bp)) {
         int rc = replay_graph(d, root, B, Bp, j.want_post, stream);
@@ -1263,6 +1320,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* cf = getenv("LDPC_COMPACT_PERCENT")) d->compact_percent = std::min(95, std::max(5, atoi(cf)));
     if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
     if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp) != 0;
+    if (const char* sm = getenv("LDPC_SMALL")) d->use_small = atoi(sm) != 0;
     if (const char* pm = getenv("LDPC_POST_MODE")) d->post_mode = std::min(2, std::max(0, atoi(pm)));
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
@@ -1326,6 +1384,12 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
             if (d->q_of_iter[t] < 0 || d->q_of_iter[t] >= d->Q) rc = fail(LDPC_ERR_INVALID, "quantizer_of_iter[%d] out of range", t);
         if (!rc) rc = upload(&d->d_thr, thr);
         if (!rc) rc = upload(&d->d_lut, lut);
+        if (!rc) rc = upload(&d->d_qoi, d->q_of_iter);
+        if (!rc) {
+            std::vector<int32_t> mono(d->mono.begin(), d->mono.end());
+            for (int mq : d->mono) d->all_mono &= mq;
+            rc = upload(&d->d_mono, mono);
+        }
     }
     if (rc) {
         ldpc_decoder_destroy(d);
@@ -1385,6 +1449,8 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     cudaFree(d->d_alpha);
     cudaFree(d->d_thr);
     cudaFree(d->d_lut);
+    cudaFree(d->d_qoi);
+    cudaFree(d->d_mono);
     delete d;
     return LDPC_OK;
 }
@@ -1649,9 +1715,10 @@ extern "C" int ldpc_decoder_profile_read(ldpc_decoder* d, ldpc_profile* out, int
     d->prof.compactions = d->stat_compactions;
     d->prof.early_exits = d->stat_early_exits;
     d->prof.graph_replays = d->stat_graph_replays;
+    d->prof.small_decodes = d->stat_small;
     *out = d->prof;
     if (reset) {
-        d->stat_compactions = d->stat_early_exits = d->stat_graph_replays = 0;
+        d->stat_compactions = d->stat_early_exits = d->stat_graph_replays = d->stat_small = 0;
         int64_t fp = d->prof.frames_padded;
         d->prof = ldpc_profile{};
         d->prof.frames_padded = fp;

@@ -82,6 +82,42 @@ struct SynLaunch {
     uint32_t* unsat;            // [Wn] OR-accumulated syndrome words
 };
 
+// On-chip decode of a whole frame in one launch (ldpc_small.cu): inputs llrT [n][Bp], results in the workspace layout.
+struct SmallLaunch {
+    const void* llrT;           // Real [n][Bp]
+    void* postT;                // Real [n][Bp] or nullptr
+    uint32_t* hardw;            // [n][Wn]
+    int64_t Wn;
+    uint8_t* done;              // [Bp] (set to 1 for every frame)
+    int32_t* iters;             // [Bp]
+    uint8_t* success;           // [Bp]
+    int64_t B, Bp;
+    int T, early_stop;
+    int n, E, n_checks;         // n_checks: non-empty checks = entries of cn_items
+    const WorkItem* cn_items;   // one check per item (the graph's fine list)
+    const WorkItem* vn_items;   // one variable per item, all n of them
+    const int32_t* slot_var;
+    const int32_t* vslots;
+    const int32_t* vpos_var;
+    const int32_t* bidx;        // per slot, or nullptr
+    int beta_per_edge;
+    const void* beta;           // [T][n_beta] or nullptr
+    int n_beta;
+    const int32_t* aidx;        // per degree-sorted position, or nullptr
+    const int32_t* aidx_slot;   // per slot (offset rule), or nullptr
+    const void* alpha;          // [T][n_alpha] or nullptr
+    int n_alpha;
+    int check_rule;             // 0 normalised, 1 offset
+    int bc, nth, n_quant;
+    const float* thr;           // [Q][nth]
+    const float* lut;           // [Q][2^bc]
+    const int32_t* q_of_iter;   // device [T]
+    const int32_t* mono;        // device [Q]: thresholds of quantiser q are non-decreasing
+    int all_mono;
+};
+bool small_decode_fits(int dtype, const SmallLaunch& p);
+cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream);
+
 // All launchers enqueue on `stream` and return the CUDA launch status.
 cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream);
 cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream);

@@ -133,9 +133,10 @@ class TannerGraph:
 
     def __del__(self):
         try:
-            lib = _lib.load()
-            for h in self._handles.values():
-                lib.ldpc_graph_destroy(h)
+            if self._handles:          # device handles exist only if the library was loaded
+                lib = _lib.load()
+                for h in self._handles.values():
+                    lib.ldpc_graph_destroy(h)
         except Exception:
             pass
 
