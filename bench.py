@@ -424,6 +424,17 @@ def kernel_roofline(prof, ab, Bp, steps, T, step_ms, kind, code_name):
     """Roofline of the dominant kernel from the library's per-launch CUDA-event durations (profiling mode) inside the
     timed region: algorithmic bytes per launch / average launch duration, against the measured HBM peak."""
     peak, peak_src = peak_hbm()
+    if prof["vn_launches"] == 0 or prof["cn_launches"] == 0:
+        # on-chip decode (small codes): one launch for all T iterations, the messages never reach HBM.  The same
+        # algorithmic byte count over the step time is an EFFECTIVE bandwidth and may exceed the HBM peak.
+        step_bytes = T * ab["frame_iter"] * Bp
+        gbs = step_bytes / (step_ms * 1e-3) / 1e9
+        zero = {"gbs": 0.0, "frac": 0.0, "ms_total": 0.0, "launches": 0}
+        return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                "traffic_source": "on-chip decode: messages stay in shared memory (effective bandwidth)", "kernel": "small_decode_kernel",
+                "peak_source": peak_src, "bytes_per_launch": step_bytes, "avg_launch_ms": step_ms,
+                "vn_kernel": zero, "cn_kernel": zero, "other_ms_total": prof["other_ms"],
+                "whole_step": {"gbs": gbs, "frac": gbs / peak, "bytes_per_frame_iter": ab["frame_iter"]}}
     vn_per_step = prof["vn_launches"] / steps
     vn_bytes = ((vn_per_step - 1) * ab["vn"] + ab["vn_final"]) / vn_per_step * Bp
     cn_bytes = ab["cn"] * Bp
@@ -485,13 +496,15 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     return rec, dec, eng, llr, out, clocks
 
 
-def e2e_leg(rig, L, code, eng, llr, B, steps, warmup, posterior, check_bits):
-    """ldpc_decode_host on pinned host buffers: H2D of the LLRs, decode, D2H of every output, all inside the timed
-    region (host wall clock around the blocking call; max over ranks)."""
+def e2e_leg(rig, L, code, eng, llr, B, steps, warmup, posterior, check_bits, packed=True):
+    """ldpc_decode_host[_packed] on pinned host buffers: H2D of the LLRs, decode, D2H of every output, all inside the
+    timed region (host wall clock around the blocking call; max over ranks).  `packed`: the hard decisions come back as
+    bit-packed rows (n/8 bytes per frame, straight from the kernels' decision words) instead of one byte per bit."""
     torch = rig.torch
     g = code.graph
     rdt = np.float64 if eng.dtype == np.float64 else np.float32
-    pins = {"llr": L.PinnedBuffer((B, g.n), rdt), "bits": L.PinnedBuffer((B, g.n), np.uint8),
+    pins = {"llr": L.PinnedBuffer((B, g.n), rdt),
+            "bits": L.PinnedBuffer((B, eng.row_words), np.uint32) if packed else L.PinnedBuffer((B, g.n), np.uint8),
             "iterations": L.PinnedBuffer((B,), np.int32), "success": L.PinnedBuffer((B,), np.uint8)}
     if posterior:
         pins["posterior"] = L.PinnedBuffer((B, g.n), rdt)
@@ -500,25 +513,63 @@ def e2e_leg(rig, L, code, eng, llr, B, steps, warmup, posterior, check_bits):
         pins["llr"].array[s:s + chunk] = llr[s:s + chunk].cpu().numpy()
     outs = {k: p.array for k, p in pins.items() if k != "llr"}
     for _ in range(max(1, min(warmup, 2))):
-        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs)
+        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs, packed_bits=packed)
     rig.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs)
+        eng.decode_host(pins["llr"].array, want_posterior=posterior, out=outs, packed_bits=packed)
     torch.cuda.synchronize()
     dt = rig.max_over_ranks(time.perf_counter() - t0)
     fps = rig.world * B * steps / dt
-    same = bool(np.array_equal(pins["bits"].array[:256], check_bits[:256].cpu().numpy()))
-    d2h = B * g.n + B * 4 + B + (B * g.n * np.dtype(rdt).itemsize if posterior else 0)
+    got = eng.unpack_rows(pins["bits"].array[:256]) if packed else pins["bits"].array[:256]
+    same = bool(np.array_equal(got, check_bits[:256].cpu().numpy()))
+    bits_bytes = B * eng.row_words * 4 if packed else B * g.n
+    d2h = bits_bytes + B * 4 + B + (B * g.n * np.dtype(rdt).itemsize if posterior else 0)
     rec = {"value": fps * code.k / 1e9, "unit": UNIT, "frames_per_s": fps,
            "h2d_bytes_per_step": int(B * g.n * np.dtype(rdt).itemsize), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * dt / steps,
-           "api": "ldpc_decode_host (pinned host LLR in; hard decisions" + (" + posteriors" if posterior else "") +
+           "ms_per_step": 1e3 * dt / steps, "steps": steps,
+           "api": ("ldpc_decode_host_packed" if packed else "ldpc_decode_host") + " (pinned host LLR in; hard decisions" +
+                  (" as bit-packed rows" if packed else " one byte per bit") + (" + posteriors" if posterior else "") +
                   " + iterations + success out)",
            "matches_device_path": same}
     for p in pins.values():
         p.free()
     return rec
+
+
+def link_ceiling(rig, L, nbytes):
+    """What the host link of this box delivers for plain pinned copies of one step's size, all ranks at once: H2D
+    alone, D2H alone, and both directions together (the e2e call moves its inputs and outputs concurrently)."""
+    torch = rig.torch
+    n = int(nbytes // 4)
+    pin_a, pin_b = L.PinnedBuffer((n,), np.float32), L.PinnedBuffer((n,), np.float32)
+    ha, hb = torch.from_numpy(pin_a.array), torch.from_numpy(pin_b.array)
+    da = torch.empty(n, dtype=torch.float32, device=rig.dev)
+    db = torch.zeros(n, dtype=torch.float32, device=rig.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h, reps=2):
+        rig.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    da.copy_(ha, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    hb.copy_(db, non_blocking=True)
+        torch.cuda.synchronize()
+        return rig.max_over_ranks(time.perf_counter() - t0) / reps
+
+    run(True, True, 1)
+    gb = n * 4 / 1e9
+    t_h, t_d, t_b = run(True, False), run(False, True), run(True, True)
+    out = {"bytes_per_copy": n * 4, "ranks": rig.world, "h2d_gbs_per_rank": gb / t_h, "d2h_gbs_per_rank": gb / t_d,
+           "bidirectional_gbs_per_rank_each_way": gb / t_b}
+    del ha, hb, da, db
+    pin_a.free()
+    pin_b.free()
+    return out
 
 
 def release(*objs):
@@ -647,11 +698,14 @@ def run_ours(args):
                        "vn_frac": r["vn_kernel"]["frac"], "cn_frac": r["cn_kernel"]["frac"], "whole_step_frac": r["whole_step"]["frac"]}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers, copies inside) ----
-    e2e = e2e_decode_only = None
+    e2e = e2e_decode_only = e2e_u8 = None
     if not args.no_e2e:
         e2e = e2e_leg(rig, L, code, eng, llr, B, args.steps, args.warmup, posterior, bits)
+        few = max(3, min(args.steps, 5))
         if posterior:
-            e2e_decode_only = e2e_leg(rig, L, code, eng, llr, B, max(3, min(args.steps, 5)), 1, False, bits)
+            e2e_decode_only = e2e_leg(rig, L, code, eng, llr, B, few, 1, False, bits)
+        e2e_u8 = e2e_leg(rig, L, code, eng, llr, B, few, 1, False, bits, packed=False)   # round 1's call, for continuity
+        e2e["link_ceiling"] = link_ceiling(rig, L, e2e["h2d_bytes_per_step"])
     del llr, out, bits
     release(eng)
     del dec, eng
@@ -679,6 +733,7 @@ def run_ours(args):
                        "parallelism": f"frames sharded over {rig.world} GPU(s), no data-path collective",
                        "host_affinity": (f"{len(rig.numa)} CPUs next to the GPU (NVML)" if rig.numa else "unbound")},
             "roofline": roof, "e2e": e2e, "decode_only": decode_only, "e2e_decode_only": e2e_decode_only,
+            "e2e_decode_only_byte_per_bit": e2e_u8,
             "cpu_baseline": cpu, "configs": configs,
             "mc_parity": (next((c.get("mc_parity") for c in configs if c["config"] == "C5"), None) if configs else None),
             "gpu_launches": head["launches"],

@@ -89,7 +89,7 @@ class DecoderModule(EngineCache, nn.Module):
             if table.shape[0] < T:
                 raise KeyError(f"iter_{table.shape[0]}_...: the decoder was built with {table.shape[0]} iterations of "
                                f"weights, max_iterations is now {T}")
-            return np.ascontiguousarray(table.detach().cpu().numpy()[:T], dtype=np.float32)
+            return np.array(table.detach().cpu().numpy()[:T], dtype=np.float32, order="C", copy=True)   # a snapshot, not an alias
 
         beta = self._beta_table
         if beta is not None:

@@ -681,6 +681,7 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
 // Where the results of a decode go: row-major user buffers (decode) or error counters (Monte-Carlo round).
 struct OutSpec {
     uint8_t* bits = nullptr;
+    uint32_t* packed = nullptr;      // decisions as packed rows [B][ceil(n/32)] instead of / besides one byte per bit
     void* post = nullptr;
     int32_t* iters = nullptr;
     uint8_t* success = nullptr;
@@ -811,6 +812,7 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
     }
     // running frames of a parent level also write their (unfinished) rows here; the next level overwrites them
     if (o.bits) LAUNCH(K_OTHER, launch_unpack_bits(d->V, ws.hardw, Bp / 32, o.bits, B, g->n, map, stream));
+    if (o.packed) LAUNCH(K_OTHER, launch_pack_rows(d->V, ws.hardw, Bp / 32, o.packed, B, g->n, map, stream));
     if (o.post) LAUNCH(K_OTHER, launch_unpack_post(d->dtype, ws.post, o.post, B, Bp, g->n, map, stream));
     if (map) {
         if (o.iters || o.success)
@@ -823,16 +825,18 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
 }
 
 // On-chip decode (ldpc_small.cu) of the frames resident in `ws`, if the code is small enough for it.
-bool fill_small(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want_post, SmallLaunch& sp) {
+bool fill_small(ldpc_decoder* d, Workspace* ws, int64_t B, int64_t Bp, bool want_post, SmallLaunch& sp) {
     const ldpc_graph* g = d->g;
     if (!d->use_small || d->schedule != LDPC_SCHEDULE_FLOODING) return false;
-    sp.llrT = ws.llrT;
-    sp.postT = want_post ? ws.post : nullptr;
-    sp.hardw = ws.hardw;
+    if (ws) {
+        sp.llrT = ws->llrT;
+        sp.postT = want_post ? ws->post : nullptr;
+        sp.hardw = ws->hardw;
+        sp.done = ws->done;
+        sp.iters = ws->iters;
+        sp.success = ws->success;
+    }
     sp.Wn = Bp / 32;
-    sp.done = ws.done;
-    sp.iters = ws.iters;
-    sp.success = ws.success;
     sp.B = B;
     sp.Bp = Bp;
     sp.T = d->T;
@@ -1053,7 +1057,7 @@ int job_start(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, i
     }
     {
         SmallLaunch sp{};
-        if (fill_small(d, root, B, Bp, j.want_post, sp)) {
+        if (fill_small(d, &root, B, Bp, j.want_post, sp)) {
             // small code: the whole decode in one launch, messages in shared memory
             LAUNCH(K_OTHER, launch_small_decode(d->dtype, sp, stream));
             d->stat_small++;
@@ -1195,8 +1199,26 @@ int decode_resident(ldpc_decoder* d, ldpc_decoder::Ctx& cx, int64_t B, int64_t B
 
 // pack + job_start on the context's root workspace
 int job_start_on_device(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits,
-                        void* post, int32_t* iters, uint8_t* success, cudaStream_t stream) {
+                        uint32_t* packed, void* post, int32_t* iters, uint8_t* success, cudaStream_t stream) {
     const int64_t Bp = pad_frames(B);
+    {
+        SmallLaunch sp{};
+        if (fill_small(d, nullptr, B, Bp, post != nullptr, sp)) {
+            // small code: the whole decode in one launch on the caller's row-major buffers (no workspace, no layout
+            // conversion): LLR rows in, decisions / posteriors / iterations / success out
+            sp.llr_rows = llr;
+            sp.bits_rows = bits;
+            sp.packed_rows = packed;
+            sp.post_rows = post;
+            sp.iters = iters;
+            sp.success = success;
+            d->prof.frames_padded = Bp;
+            j = DecodeJob();
+            LAUNCH(K_OTHER, launch_small_decode(d->dtype, sp, stream));
+            d->stat_small++;
+            return LDPC_OK;
+        }
+    }
     int rc = ws_ensure(d, cx.root, Bp);
     if (rc) return rc;
     d->prof.frames_padded = Bp;
@@ -1204,6 +1226,7 @@ int job_start_on_device(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, co
     LAUNCH(K_OTHER, launch_pack(d->dtype, llr, ws.llrT, B, Bp, d->g->n, ws.done, ws.iters, ws.success, d->T, stream));
     OutSpec o;
     o.bits = bits;
+    o.packed = packed;
     o.post = post;
     o.iters = iters;
     o.success = success;
@@ -1239,10 +1262,10 @@ std::vector<std::pair<int64_t, int64_t>> plan_chunks(int64_t B, int64_t chunk, i
     return chunks;
 }
 
-int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits, void* post,
-                     int32_t* iters, uint8_t* success, cudaStream_t stream) {
+int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits, uint32_t* packed,
+                     void* post, int32_t* iters, uint8_t* success, cudaStream_t stream) {
     DecodeJob j;
-    int rc = job_start_on_device(j, d, cx, llr, B, bits, post, iters, success, stream);
+    int rc = job_start_on_device(j, d, cx, llr, B, bits, packed, post, iters, success, stream);
     return rc ? rc : job_drive(j);
 }
 
@@ -1461,27 +1484,55 @@ extern "C" int ldpc_decoder_reserve(ldpc_decoder* d, int64_t frames) {
     return ws_ensure(d, d->cx[0].root, pad_frames(frames));
 }
 
-extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
-                                  int32_t* iterations, uint8_t* success, void* stream) {
+namespace {
+int decode_device_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, uint32_t* packed, void* posterior,
+                       int32_t* iterations, uint8_t* success, void* stream) {
     if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
     if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
     DeviceGuard guard(d->g->device);
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
     int rc = ctx_enter(d->cx[0], (cudaStream_t)stream);
-    if (!rc) rc = decode_on_device(d, d->cx[0], llr, B, bits, posterior, iterations, success, (cudaStream_t)stream);
+    if (!rc) rc = decode_on_device(d, d->cx[0], llr, B, bits, packed, posterior, iterations, success, (cudaStream_t)stream);
     if (!rc) rc = ctx_leave(d->cx[0], (cudaStream_t)stream);
     return rc;
 }
+int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, uint32_t* packed, void* posterior,
+                     int32_t* iterations, uint8_t* success);
+}  // namespace
 
-// Host-buffer entry point: chunked pipeline with two decode jobs in flight (see HostPipe, DecodeJob).
+extern "C" int ldpc_decode_device(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
+                                  int32_t* iterations, uint8_t* success, void* stream) {
+    return decode_device_impl(d, llr, B, bits, nullptr, posterior, iterations, success, stream);
+}
+
+extern "C" int ldpc_decode_device_packed(ldpc_decoder* d, const void* llr, int64_t B, uint32_t* bits_packed, void* posterior,
+                                         int32_t* iterations, uint8_t* success, void* stream) {
+    return decode_device_impl(d, llr, B, nullptr, bits_packed, posterior, iterations, success, stream);
+}
+
 extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, void* posterior,
                                 int32_t* iterations, uint8_t* success) {
+    return decode_host_impl(d, llr, B, bits, nullptr, posterior, iterations, success);
+}
+
+extern "C" int ldpc_decode_host_packed(ldpc_decoder* d, const void* llr, int64_t B, uint32_t* bits_packed, void* posterior,
+                                       int32_t* iterations, uint8_t* success) {
+    return decode_host_impl(d, llr, B, nullptr, bits_packed, posterior, iterations, success);
+}
+
+// Host-buffer entry points: chunked pipeline with two decode jobs in flight (see HostPipe, DecodeJob).  The decisions
+// travel back either as one byte per bit (`bits`) or as packed rows (`packed`, an eighth of the bytes).
+namespace {
+int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits, uint32_t* packed, void* posterior,
+                     int32_t* iterations, uint8_t* success) {
     if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
     if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
     DeviceGuard guard(d->g->device);
     if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    if (bits && packed) return fail(LDPC_ERR_INVALID, "one decision format per call");
     const ldpc_graph* g = d->g;
     const int64_t n = g->n;
+    const int64_t row_words = (n + 31) / 32;
     HostPipe& pp = d->pipe;
     int64_t chunk = d->host_chunk > 0 ? d->host_chunk : 8192;   // enough frames to fill the GPU
     if (B <= chunk) chunk = B;
@@ -1501,7 +1552,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
             cudaFree(b.d_llr); cudaFree(b.d_bits); cudaFree(b.d_post); cudaFree(b.d_it); cudaFree(b.d_su);
             b.d_llr = nullptr; b.d_bits = nullptr; b.d_post = nullptr; b.d_it = nullptr; b.d_su = nullptr;
             CU(cudaMalloc(&b.d_llr, (size_t)chunk * n * d->rsz));
-            CU(cudaMalloc((void**)&b.d_bits, (size_t)chunk * n));
+            CU(cudaMalloc((void**)&b.d_bits, (size_t)chunk * std::max<int64_t>(n, 4 * row_words)));   // either decision format
             if (posterior) CU(cudaMalloc(&b.d_post, (size_t)chunk * n * d->rsz));
             CU(cudaMalloc((void**)&b.d_it, (size_t)chunk * sizeof(int32_t)));
             CU(cudaMalloc((void**)&b.d_su, (size_t)chunk));
@@ -1555,6 +1606,9 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         mark(2 + 3 * i, rs);
         CU(cudaStreamWaitEvent(pp.s_out, bf.run_done, 0));
         if (bits) CU(cudaMemcpyAsync(bits + (size_t)off * n, bf.d_bits, (size_t)b * n, cudaMemcpyDeviceToHost, pp.s_out));
+        if (packed)
+            CU(cudaMemcpyAsync(packed + (size_t)off * row_words, bf.d_bits, (size_t)b * row_words * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, pp.s_out));
         if (posterior)
             CU(cudaMemcpyAsync((char*)posterior + (size_t)off * n * d->rsz, bf.d_post, (size_t)b * n * d->rsz,
                                cudaMemcpyDeviceToHost, pp.s_out));
@@ -1600,6 +1654,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         sl.chunk = i;
         sl.busy = true;
         rc = job_start_on_device(sl.job, d, d->cx[1 + sidx], bf.d_llr, chunks[i].second, bits ? bf.d_bits : nullptr,
+                                 packed ? reinterpret_cast<uint32_t*>(bf.d_bits) : nullptr,
                                  posterior ? bf.d_post : nullptr, bf.d_it, bf.d_su, rs);
         if (rc) break;
         if (sl.job.waiting) sl.cp_seq = ++seq;
@@ -1628,6 +1683,7 @@ extern "C" int ldpc_decode_host(ldpc_decoder* d, const void* llr, int64_t B, uin
         if (e) cudaEventDestroy(e);
     return rc;
 }
+}  // namespace
 
 extern "C" int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t* frames_out, int32_t max_chunks,
                                     int32_t* n_chunks) {

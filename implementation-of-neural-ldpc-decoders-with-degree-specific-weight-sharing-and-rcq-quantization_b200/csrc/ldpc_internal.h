@@ -84,14 +84,20 @@ struct SynLaunch {
 
 // On-chip decode of a whole frame in one launch (ldpc_small.cu): inputs llrT [n][Bp], results in the workspace layout.
 struct SmallLaunch {
+    // row mode (llr_rows != nullptr): the caller's row-major buffers, no workspace involved
+    const void* llr_rows;       // Real [B][n]
+    uint8_t* bits_rows;         // [B][n] or nullptr
+    uint32_t* packed_rows;      // [B][ceil(n/32)] or nullptr (bit j & 31 of word j >> 5 = decision of variable j)
+    void* post_rows;            // Real [B][n] or nullptr
+    // workspace mode
     const void* llrT;           // Real [n][Bp]
     void* postT;                // Real [n][Bp] or nullptr
     uint32_t* hardw;            // [n][Wn]
     int64_t Wn;
     uint8_t* done;              // [Bp] (set to 1 for every frame)
-    int32_t* iters;             // [Bp]
-    uint8_t* success;           // [Bp]
-    int64_t B, Bp;
+    int32_t* iters;             // [Bp]; row mode: [B] or nullptr
+    uint8_t* success;           // [Bp]; row mode: [B] or nullptr
+    int64_t B, Bp;              // Bp: B rounded up to a multiple of 128
     int T, early_stop;
     int n, E, n_checks;         // n_checks: non-empty checks = entries of cn_items
     const WorkItem* cn_items;   // one check per item (the graph's fine list)
@@ -161,6 +167,9 @@ cudaError_t launch_reset_state(uint8_t* done, int32_t* iters, uint8_t* success, 
 // `map` (may be nullptr): output row of local frame f is map[f] (frames of a compacted level)
 cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t* bits, int64_t B,
                                int32_t n, const int32_t* map, cudaStream_t stream);
+// hardw -> packed rows [B][ceil(n/32)] u32 (bit j & 31 of word j >> 5 = decision of variable j)
+cudaError_t launch_pack_rows(int V, const uint32_t* hardw, int64_t Wn, uint32_t* rows, int64_t B, int32_t n,
+                             const int32_t* map, cudaStream_t stream);
 // postT [n][Bp] -> post [B][n]
 cudaError_t launch_unpack_post(int dtype, const void* postT, void* post, int64_t B, int64_t Bp,
                                int32_t n, const int32_t* map, cudaStream_t stream);

@@ -171,6 +171,39 @@ __global__ void unpack_bits_kernel(int V, const uint32_t* __restrict__ hardw, in
     }
 }
 
+// hardw -> packed decision rows [B][row_words] u32: bit (j & 31) of word (j >> 5) of row f = decision of variable j
+// of frame f (one eighth of the bytes of the one-byte-per-bit rows: what goes back over PCIe in the packed host
+// entry point).  One warp: one hard word (32 frames) x 128 variables.  Lane l loads the words of variables
+// 32 i + l (i < 4); a ballot over the lanes of bit b of those words is word i of frame b's row, kept by lane b.
+__global__ void pack_rows_kernel(int V, const uint32_t* __restrict__ hardw, int64_t Wn, uint32_t* __restrict__ rows,
+                                 int64_t B, int32_t n, int32_t row_words, const int32_t* __restrict__ map) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= Wn) return;
+    const int32_t j0 = blockIdx.x * 128;
+    uint32_t word[4], mine[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int32_t j = j0 + 32 * i + lane;
+        word[i] = (j < n) ? __ldg(hardw + (int64_t)j * Wn + w) : 0u;
+        mine[i] = 0u;
+    }
+#pragma unroll 4
+    for (int b = 0; b < 32; ++b) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (word[i] >> b) & 1u);
+            if (lane == b) mine[i] = bal;
+        }
+    }
+    const int64_t f = wordbit_to_frame(w, lane, V);
+    if (f >= B) return;
+    uint32_t* row = rows + (map ? (int64_t)map[f] : f) * row_words + blockIdx.x * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (blockIdx.x * 4 + i < row_words) row[i] = mine[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // AWGN channel (ldpc_decoder.py:286-302) with counter-based Philox4x32-10 noise.
 // ---------------------------------------------------------------------------------------------
@@ -538,6 +571,14 @@ cudaError_t launch_unpack_bits(int V, const uint32_t* hardw, int64_t Wn, uint8_t
     const int warps = 8;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)((Wn + warps - 1) / warps));
     unpack_bits_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, bits, B, n, map);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rows(int V, const uint32_t* hardw, int64_t Wn, uint32_t* rows, int64_t B, int32_t n,
+                             const int32_t* map, cudaStream_t stream) {
+    const int warps = 8;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)((Wn + warps - 1) / warps));
+    pack_rows_kernel<<<grid, warps * 32, 0, stream>>>(V, hardw, Wn, rows, B, n, (n + 31) / 32, map);
     return cudaGetLastError();
 }
 

@@ -12,8 +12,13 @@
 // first zero syndrome.  Reference: ldpc_decoder.py:80-153, neural_2d_decoder.py:133-225, neural_minsum_decoder.py:58-150,
 // rcq_decoder.py:190-279 / :495-597.
 //
-// Results leave in the workspace layout of the per-iteration path (packed decisions, per-frame iterations / success,
-// posterior rows), so delivery (unpack / error counting) is shared with it.
+// Two I/O modes.  Row mode (ldpc_decode_device / ldpc_decode_host): the kernel reads the caller's row-major LLRs and
+// writes the caller's row-major decisions / posteriors / iterations / success itself (coalesced through a shared-memory
+// transpose), so a decode is exactly one launch and no workspace exists.  Workspace mode (ldpc_mc_round): LLRs from
+// the interleaved llrT the AWGN kernel fills, results in the workspace layout (packed decisions, per-frame iterations)
+// that the error-counting kernels read.
+#include <type_traits>
+
 #include "ldpc_cn_common.cuh"
 
 namespace ldpc {
@@ -112,22 +117,49 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
     const float* const s_lut = s_thr + p.n_quant * p.nth;
     __syncthreads();
 
-    // ---- frame of this thread, in the order of the packed decision words: a warp holds bit `lane` of word `word` ----
+    // ---- frame of this thread ----
+    // workspace mode (llrT in, packed decisions out): frames in the order of the packed decision words, so that a
+    // warp holds bit `lane` of word `word`;  row mode (the caller's row-major buffers in and out): thread t of the
+    // CTA owns frame cta_base + t
+    const bool rows = p.llr_rows != nullptr;
     const int group = wid / V, v = wid % V;
-    const int64_t gbase = (int64_t)blockIdx.x * kSmallThreads + (int64_t)group * 32 * V;
-    const int64_t f = gbase + (int64_t)lane * V + v;
+    const int64_t cta_base = (int64_t)blockIdx.x * kSmallThreads;
+    const int64_t gbase = cta_base + (int64_t)group * 32 * V;
+    const int64_t f = rows ? cta_base + tid : gbase + (int64_t)lane * V + v;
     const int64_t word = (gbase / (32 * V)) * V + v;
     const bool active = f < p.B;
     constexpr int S = kSmallThreads;   // column stride
+    const int cta_frames = (int)min((int64_t)kSmallThreads, p.B - cta_base);   // row mode: frames of this CTA (> 0)
+    const int q128 = kSmallThreads / n, r128 = kSmallThreads % n;               // element e -> (frame e / n, variable e % n)
+
+    if (rows) {
+        // the CTA's LLR rows are one contiguous block: coalesced loads, transposed into the per-frame columns
+        const Real* __restrict__ src = static_cast<const Real*>(p.llr_rows) + cta_base * n;
+        const int total = cta_frames * n;
+        int fl = tid / n, j = tid % n;
+        for (int e = tid; e < total; e += kSmallThreads) {
+            (llr - tid)[j * S + fl] = src[e];
+            j += r128;
+            fl += q128;
+            if (j >= n) { j -= n; ++fl; }
+        }
+        __syncthreads();
+    }
 
     int it_done = p.T;
     bool ok = false;
+    uint64_t bits64_out = 0;
     if (active) {
-        const Real* __restrict__ gl = static_cast<const Real*>(p.llrT) + f;
-        for (int j = 0; j < n; ++j) llr[j * S] = gl[(int64_t)j * p.Bp];
+        if (!rows) {
+            const Real* __restrict__ gl = static_cast<const Real*>(p.llrT) + f;
+            for (int j = 0; j < n; ++j) llr[j * S] = gl[(int64_t)j * p.Bp];
+        }
         for (int s = 0; s < E; ++s) v2c[s * S] = llr[g.svar[s] * S];   // ldpc_decoder.py:84-87
         const bool has_beta = p.beta != nullptr;
         const bool has_alpha = p.alpha != nullptr && KIND != SMALL_OFFSET;
+        // hard decisions of the frame: in two registers while n <= 64, else in the frame's shared-memory words
+        const bool reg_bits = nw <= 2;
+        uint64_t bits64 = 0;
         for (int t = 0; t < p.T; ++t) {
             const Real* __restrict__ beta_t = has_beta ? static_cast<const Real*>(p.beta) + (size_t)t * p.n_beta : nullptr;
             const Real* __restrict__ alpha_t = p.alpha ? static_cast<const Real*>(p.alpha) + (size_t)t * p.n_alpha : nullptr;
@@ -138,62 +170,138 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
                 qz.load(s_thr + q * p.nth, p.nth, __ldg(p.mono + q) != 0);
                 lutq = s_lut + (q << p.bc);
             }
-            // ---- check nodes ----
-            for (int c = 0; c < nc; ++c) {
-                const int deg = g.cdeg[c], s0 = g.cslot[c];
+            const bool last = t == p.T - 1;
+            // ---- one check node.  DC > 0: compile-time degree, inputs held in registers (read once);
+            //      DC == 0: run-time degree, inputs read again for the output phase ----
+            auto cn_node = [&](auto dc_tag, const int deg, const int s0) {
+                constexpr int DC = decltype(dc_tag)::value;
+                const int D = DC > 0 ? DC : deg;
+                const Real* const in = v2c + s0 * S;
+                Real* const out = c2v + s0 * S;
+                Real x[DC > 0 ? DC : 1];
                 MinState<Real, false> st;
                 st.init();
-                for (int k = 0; k < deg; ++k) st.push(v2c[(s0 + k) * S], k);
-                if (deg == 1) st.m2 = st.m1;   // ldpc_decoder.py:112-113
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const Real xk = in[k * S];
+                    if constexpr (DC > 0) x[k] = xk;
+                    st.push(xk, k);
+                }
+                if (D == 1) st.m2 = st.m1;   // ldpc_decoder.py:112-113
+                auto input = [&](int k) -> Real {
+                    if constexpr (DC > 0) return x[k];
+                    else return in[k * S];
+                };
                 if constexpr (KIND == SMALL_OFFSET) {
                     Real beta_check = Real(0);
                     if (has_beta && !p.beta_per_edge) beta_check = beta_t[g.bidx ? g.bidx[s0] : 0];
-                    for (int k = 0; k < deg; ++k) {
-                        const Real x = v2c[(s0 + k) * S];
-                        const bool is_min = Arith<Real>::abs(x) == st.m1;
-                        const bool zero_others = deg > 1 && (st.m2 == Real(0) || (st.m1 == Real(0) && !is_min));
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const Real xk = input(k);
+                        const bool is_min = Arith<Real>::abs(xk) == st.m1;
+                        const bool zero_others = D > 1 && (st.m2 == Real(0) || (st.m1 == Real(0) && !is_min));
                         const Real beta = (has_beta && p.beta_per_edge) ? beta_t[g.bidx[s0 + k]] : beta_check;
                         const Real alpha = alpha_t ? alpha_t[g.aslot ? g.aslot[s0 + k] : 0] : Real(0);
-                        c2v[(s0 + k) * S] = offset_value<Real>(is_min ? st.m2 : st.m1, beta, has_beta, alpha, alpha_t != nullptr,
-                                                               st.par ^ Arith<Real>::hi(x), zero_others);
+                        out[k * S] = offset_value<Real>(is_min ? st.m2 : st.m1, beta, has_beta, alpha, alpha_t != nullptr,
+                                                        st.par ^ Arith<Real>::hi(xk), zero_others);
                     }
                 } else if (!p.beta_per_edge) {
                     const Real beta = has_beta ? beta_t[g.bidx ? g.bidx[s0] : 0] : Real(1);
                     CheckOut<Real, QUANT> co;
                     co.prepare(st.m1, st.m2, st.par, beta, has_beta, qz, p.bc);
-                    for (int k = 0; k < deg; ++k) {
-                        const Real x = v2c[(s0 + k) * S];
-                        const auto out = co.emit(Arith<Real>::abs(x) == st.m1, Arith<Real>::hi(x));
-                        if constexpr (QUANT) c2v[(s0 + k) * S] = (Real)lutq[out];
-                        else c2v[(s0 + k) * S] = out;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const Real xk = input(k);
+                        const auto o = co.emit(Arith<Real>::abs(xk) == st.m1, Arith<Real>::hi(xk));
+                        if constexpr (QUANT) out[k * S] = (Real)lutq[o];
+                        else out[k * S] = o;
                     }
                 } else {
-                    for (int k = 0; k < deg; ++k) {
-                        const Real x = v2c[(s0 + k) * S];
-                        const Real raw = (Arith<Real>::abs(x) == st.m1) ? st.m2 : st.m1;
-                        const auto out = cn_emit<Real, QUANT, NTH>(raw, beta_t[g.bidx[s0 + k]], st.par ^ Arith<Real>::hi(x), qz, p.bc);
-                        if constexpr (QUANT) c2v[(s0 + k) * S] = (Real)lutq[out];
-                        else c2v[(s0 + k) * S] = out;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const Real xk = input(k);
+                        const Real raw = (Arith<Real>::abs(xk) == st.m1) ? st.m2 : st.m1;
+                        const auto o = cn_emit<Real, QUANT, NTH>(raw, beta_t[g.bidx[s0 + k]], st.par ^ Arith<Real>::hi(xk), qz, p.bc);
+                        if constexpr (QUANT) out[k * S] = (Real)lutq[o];
+                        else out[k * S] = o;
                     }
                 }
+            };
+            for (int c = 0; c < nc; ++c) {
+                const int deg = g.cdeg[c], s0 = g.cslot[c];
+                switch (deg) {
+                    case 1: cn_node(std::integral_constant<int, 1>{}, 1, s0); break;
+                    case 2: cn_node(std::integral_constant<int, 2>{}, 2, s0); break;
+                    case 3: cn_node(std::integral_constant<int, 3>{}, 3, s0); break;
+                    case 4: cn_node(std::integral_constant<int, 4>{}, 4, s0); break;
+                    case 5: cn_node(std::integral_constant<int, 5>{}, 5, s0); break;
+                    case 6: cn_node(std::integral_constant<int, 6>{}, 6, s0); break;
+                    case 7: cn_node(std::integral_constant<int, 7>{}, 7, s0); break;
+                    case 8: cn_node(std::integral_constant<int, 8>{}, 8, s0); break;
+                    default: cn_node(std::integral_constant<int, 0>{}, deg, s0); break;
+                }
             }
-            // ---- variable nodes, posterior, hard decision ----
-            const bool last = t == p.T - 1;
-            for (int w = 0; w < nw; ++w) hb[w * S] = 0u;
-            for (int pos = 0; pos < n; ++pos) {
-                const int dv = g.vdeg[pos], lb = g.vbase[pos], j = g.vid[pos];
+            // ---- one variable node: posterior, hard decision, outgoing messages.  DV > 0: inputs in registers ----
+            if (reg_bits) bits64 = 0;
+            else
+                for (int w = 0; w < nw; ++w) hb[w * S] = 0u;
+            auto vn_node = [&](auto dv_tag, const int dvr, const int lb, const int pos) {
+                constexpr int DV = decltype(dv_tag)::value;
+                const int j = g.vid[pos];
                 const Real L = llr[j * S];
-                const Real tot = lib_sum<Real>([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dv);
-                const Real post = dv > 0 ? Arith<Real>::add(L, tot) : L;
-                if (post < Real(0)) hb[(j >> 5) * S] |= 1u << (j & 31);
-                if (!last) {   // the v2c update of iteration T-1 is dead
-                    Real alpha = Real(1);
-                    if (has_alpha) alpha = alpha_t[g.aidx ? g.aidx[pos] : 0];
-                    for (int d = 0; d < dv; ++d) {
-                        Real s = lib_sum<Real>([&](int i) { return c2v[g.vslot[lb + (i < d ? i : i + 1)] * S]; }, dv - 1);
-                        if (has_alpha) s = Arith<Real>::mul(alpha, s);
-                        v2c[g.vslot[lb + d] * S] = Arith<Real>::add(L, s);
+                Real post;
+                if constexpr (DV >= 0) {
+                    constexpr int D1 = DV > 0 ? DV : 1;
+                    int off[D1];
+                    Real c[D1];
+#pragma unroll
+                    for (int i = 0; i < DV; ++i) {
+                        off[i] = g.vslot[lb + i] * S;
+                        c[i] = c2v[off[i]];
                     }
+                    const Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
+                    post = DV > 0 ? Arith<Real>::add(L, tot) : L;
+                    if (!last) {   // the v2c update of iteration T-1 is dead
+                        Real alpha = Real(1);
+                        if (has_alpha) alpha = alpha_t[g.aidx ? g.aidx[pos] : 0];
+#pragma unroll
+                        for (int d = 0; d < DV; ++d) {
+                            Real sd = LibSum<Real>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[i < d ? i : i + 1]; });
+                            if (has_alpha) sd = Arith<Real>::mul(alpha, sd);
+                            v2c[off[d]] = Arith<Real>::add(L, sd);
+                        }
+                    }
+                } else {
+                    const Real tot = LibSum<Real>::dyn([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dvr);
+                    post = Arith<Real>::add(L, tot);
+                    if (!last) {
+                        Real alpha = Real(1);
+                        if (has_alpha) alpha = alpha_t[g.aidx ? g.aidx[pos] : 0];
+                        for (int d = 0; d < dvr; ++d) {
+                            Real sd = LibSum<Real>::dyn([&](int i) { return c2v[g.vslot[lb + (i < d ? i : i + 1)] * S]; }, dvr - 1);
+                            if (has_alpha) sd = Arith<Real>::mul(alpha, sd);
+                            v2c[g.vslot[lb + d] * S] = Arith<Real>::add(L, sd);
+                        }
+                    }
+                }
+                if (post < Real(0)) {
+                    if (reg_bits) bits64 |= 1ull << j;
+                    else hb[(j >> 5) * S] |= 1u << (j & 31);
+                }
+            };
+            for (int pos = 0; pos < n; ++pos) {
+                const int dv = g.vdeg[pos], lb = g.vbase[pos];
+                switch (dv) {
+                    case 0: vn_node(std::integral_constant<int, 0>{}, 0, lb, pos); break;
+                    case 1: vn_node(std::integral_constant<int, 1>{}, 1, lb, pos); break;
+                    case 2: vn_node(std::integral_constant<int, 2>{}, 2, lb, pos); break;
+                    case 3: vn_node(std::integral_constant<int, 3>{}, 3, lb, pos); break;
+                    case 4: vn_node(std::integral_constant<int, 4>{}, 4, lb, pos); break;
+                    case 5: vn_node(std::integral_constant<int, 5>{}, 5, lb, pos); break;
+                    case 6: vn_node(std::integral_constant<int, 6>{}, 6, lb, pos); break;
+                    case 7: vn_node(std::integral_constant<int, 7>{}, 7, lb, pos); break;
+                    case 8: vn_node(std::integral_constant<int, 8>{}, 8, lb, pos); break;
+                    default: vn_node(std::integral_constant<int, -1>{}, dv, lb, pos); break;
                 }
             }
             // ---- syndrome and early stop (ldpc_decoder.py:141-144) ----
@@ -202,9 +310,13 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
                 for (int c = 0; c < nc; ++c) {
                     const int deg = g.cdeg[c], s0 = g.cslot[c];
                     uint32_t par = 0;
-                    for (int k = 0; k < deg; ++k) {
-                        const int j = g.svar[s0 + k];
-                        par ^= hb[(j >> 5) * S] >> (j & 31);
+                    if (reg_bits) {
+                        for (int k = 0; k < deg; ++k) par ^= (uint32_t)(bits64 >> g.svar[s0 + k]);
+                    } else {
+                        for (int k = 0; k < deg; ++k) {
+                            const int j = g.svar[s0 + k];
+                            par ^= hb[(j >> 5) * S] >> (j & 31);
+                        }
                     }
                     unsat |= par & 1u;
                 }
@@ -215,6 +327,53 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
                 }
             }
         }
+        bits64_out = bits64;
+    }
+    if (active && nw <= 2) {   // the output code reads the decision words from shared memory
+        hb[0] = (uint32_t)bits64_out;
+        if (nw > 1) hb[S] = (uint32_t)(bits64_out >> 32);
+    }
+    if (rows) {
+        // ---- results straight into the caller's row-major buffers, staged through shared memory so that the
+        // CTA's contiguous output blocks leave with coalesced stores ----
+        if (p.iters && active) p.iters[f] = it_done;
+        if (p.success && active) p.success[f] = ok ? 1 : 0;
+        if (p.packed_rows && active)   // the frame's decision words ARE its packed row
+            for (int w = 0; w < nw; ++w) p.packed_rows[f * nw + w] = hb[w * S];
+        __syncthreads();   // every frame's v2c column is dead: the region becomes the byte stage of the decisions
+        uint8_t* const stage = small_smem;
+        if (p.bits_rows && active)
+            for (int j = 0; j < n; ++j) stage[tid * n + j] = (uint8_t)((hb[(j >> 5) * S] >> (j & 31)) & 1u);
+        if (p.post_rows && active) {
+            // the check->variable messages of the frame's last iteration are still in place; the posterior of
+            // variable j replaces its LLR in the frame's column
+            for (int pos = 0; pos < n; ++pos) {
+                const int dv = g.vdeg[pos], lb = g.vbase[pos], j = g.vid[pos];
+                const Real L = llr[j * S];
+                const Real tot = lib_sum<Real>([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dv);
+                llr[j * S] = dv > 0 ? Arith<Real>::add(L, tot) : L;
+            }
+        }
+        __syncthreads();
+        const int total = cta_frames * n;
+        if (p.bits_rows) {
+            uint8_t* __restrict__ dst = p.bits_rows + cta_base * n;   // cta_base * n is a multiple of 128
+            const int words = total >> 2;
+            for (int e = tid; e < words; e += kSmallThreads)
+                reinterpret_cast<uint32_t*>(dst)[e] = reinterpret_cast<const uint32_t*>(stage)[e];
+            for (int e = (words << 2) + tid; e < total; e += kSmallThreads) dst[e] = stage[e];
+        }
+        if (p.post_rows) {
+            Real* __restrict__ dst = static_cast<Real*>(p.post_rows) + cta_base * n;
+            int fl = tid / n, j = tid % n;
+            for (int e = tid; e < total; e += kSmallThreads) {
+                dst[e] = (llr - tid)[j * S + fl];
+                j += r128;
+                fl += q128;
+                if (j >= n) { j -= n; ++fl; }
+            }
+        }
+        return;
     }
     __syncwarp();
     // ---- results in the workspace layout ----
@@ -262,7 +421,8 @@ bool small_decode_fits(int dtype, const SmallLaunch& p) {
     if (p.E <= 0 || p.n <= 0) return false;
     const size_t rsz = dtype == 0 ? 4 : 8;
     const size_t per_frame = (size_t)(2 * p.E + p.n) * rsz + 4 * (size_t)((p.n + 31) / 32);
-    return per_frame <= 896 && small_smem_bytes(dtype, p) <= (size_t)160 * 1024;
+    // (row mode stages the decisions as n bytes per frame in the region of the v2c columns)
+    return per_frame <= 896 && (size_t)p.E * rsz >= (size_t)p.n && small_smem_bytes(dtype, p) <= (size_t)160 * 1024;
 }
 
 cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream) {

@@ -250,10 +250,22 @@ class Engine:
         _lib.check(_lib.load().ldpc_decoder_reserve(self._h, int(frames)))
 
     # ------------------------------------------------------------------ decode
-    def decode_host(self, llr: np.ndarray, want_posterior: bool = False,
-                    out: Optional[dict] = None) -> Tuple[np.ndarray, Optional[np.ndarray], np.ndarray, np.ndarray]:
+    @property
+    def row_words(self) -> int:
+        """uint32 words per frame of the packed decision rows."""
+        return (self.graph.n + 31) // 32
+
+    def unpack_rows(self, packed: np.ndarray) -> np.ndarray:
+        """Packed decision rows [B, row_words] uint32 -> one byte per bit [B, n] uint8 (host)."""
+        rows = np.ascontiguousarray(packed, dtype=np.uint32)
+        return np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")[:, :self.graph.n]
+
+    def decode_host(self, llr: np.ndarray, want_posterior: bool = False, out: Optional[dict] = None,
+                    packed_bits: bool = False) -> Tuple[np.ndarray, Optional[np.ndarray], np.ndarray, np.ndarray]:
         """llr: host [B, n] (pinned memory gives full PCIe rate).  Returns bits u8, posterior|None,
-        iterations i32, success u8 as host arrays (``out`` may supply preallocated ones)."""
+        iterations i32, success u8 as host arrays (``out`` may supply preallocated ones).  ``packed_bits``: the
+        decisions come back as packed rows [B, row_words] uint32 (bit j & 31 of word j >> 5 = variable j), an eighth
+        of the bytes over the host link; ``unpack_rows`` expands them."""
         llr = np.ascontiguousarray(llr, dtype=self.dtype)
         if llr.ndim != 2 or llr.shape[1] != self.graph.n:
             raise IndexError(f"llr must have shape [B, {self.graph.n}], got {llr.shape}")
@@ -270,16 +282,21 @@ class Engine:
                 raise ValueError(f"out[{name!r}] must be a writable C-contiguous {np.dtype(dtype).name} array of shape {shape}")
             return a
 
-        bits = buffer("bits", (B, self.graph.n), np.uint8)
+        if packed_bits:
+            bits = buffer("bits", (B, self.row_words), np.uint32)
+        else:
+            bits = buffer("bits", (B, self.graph.n), np.uint8)
         post = buffer("posterior", (B, self.graph.n), self.dtype, wanted=want_posterior)
         iters = buffer("iterations", (B,), np.int32)
         succ = buffer("success", (B,), np.uint8)
+        fn = _lib.load().ldpc_decode_host_packed if packed_bits else _lib.load().ldpc_decode_host
         with self._lock:
-            _lib.check(_lib.load().ldpc_decode_host(self._h, _ptr(llr), B, _ptr(bits), _ptr(post), _ptr(iters), _ptr(succ)))
+            _lib.check(fn(self._h, _ptr(llr), B, _ptr(bits), _ptr(post), _ptr(iters), _ptr(succ)))
         return bits, post, iters, succ
 
-    def decode_device(self, llr, want_posterior: bool = False, want_bits: bool = True):
-        """llr: CUDA torch tensor [B, n] on this engine's device.  Enqueued on the current torch stream."""
+    def decode_device(self, llr, want_posterior: bool = False, want_bits: bool = True, packed_bits: bool = False):
+        """llr: CUDA torch tensor [B, n] on this engine's device.  Enqueued on the current torch stream.
+        ``packed_bits``: decisions as packed rows [B, row_words] int32 (the uint32 words of ``decode_host``)."""
         import torch
 
         tdt = torch.float32 if self.dtype == np.float32 else torch.float64
@@ -290,13 +307,17 @@ class Engine:
         llr = llr.to(tdt).contiguous()
         B = llr.shape[0]
         dev = llr.device
-        bits = torch.empty((B, self.graph.n), dtype=torch.uint8, device=dev) if want_bits else None
+        if packed_bits:
+            bits = torch.empty((B, self.row_words), dtype=torch.int32, device=dev) if want_bits else None
+        else:
+            bits = torch.empty((B, self.graph.n), dtype=torch.uint8, device=dev) if want_bits else None
         post = torch.empty((B, self.graph.n), dtype=tdt, device=dev) if want_posterior else None
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         succ = torch.empty(B, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        fn = _lib.load().ldpc_decode_device_packed if packed_bits else _lib.load().ldpc_decode_device
         with self._lock:
-            _lib.check(_lib.load().ldpc_decode_device(
+            _lib.check(fn(
                 self._h, llr.data_ptr(), B, bits.data_ptr() if bits is not None else None,
                 post.data_ptr() if post is not None else None, iters.data_ptr(), succ.data_ptr(), stream))
         return bits, post, iters, succ

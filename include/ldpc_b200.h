@@ -146,6 +146,18 @@ int ldpc_decode_device(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bit
 int ldpc_decode_host(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bits, void *posterior,
                      int32_t *iterations, uint8_t *success);
 
+/*
+ * The same two calls with the hard decisions as PACKED rows (additive: the reference returns one integer per bit):
+ *   bits_packed [B][ceil(n/32)] uint32 -- bit (j & 31) of word (j >> 5) of row f is the decision of variable j of
+ *   frame f (numpy: np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")[:, :n]).  One eighth of the bytes of
+ *   `bits`: the decisions leave the device as the bit-packed words the kernels already hold, which is what matters
+ *   where the host link carries every output (ldpc_decode_host_packed).
+ */
+int ldpc_decode_device_packed(ldpc_decoder *d, const void *llr, int64_t B, uint32_t *bits_packed, void *posterior,
+                              int32_t *iterations, uint8_t *success, void *stream);
+int ldpc_decode_host_packed(ldpc_decoder *d, const void *llr, int64_t B, uint32_t *bits_packed, void *posterior,
+                            int32_t *iterations, uint8_t *success);
+
 /* Test hook: the chunk plan ldpc_decode_host uses for a batch of B frames (frames per chunk, in order).
  * chunk <= 0 selects the default (8192); frames_per_lane is 4 for F32 decoders, 2 for F64. */
 int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t *frames_out,

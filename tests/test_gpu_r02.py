@@ -205,3 +205,40 @@ def test_decode_host_validates_caller_buffers(built_lib):
     out = {"bits": np.empty((5, 7), np.uint8), "iterations": np.empty(5, np.int32), "success": np.empty(5, np.uint8)}
     b, _, i, s = eng.decode_host(llr, out=out)
     assert b is out["bits"] and i is out["iterations"] and s is out["success"] and not b.any() and s.all()
+
+
+@pytest.mark.parametrize("which", ["dvbs2_s20", "h74", "wide"])
+def test_packed_decision_rows_equal_the_byte_rows(built_lib, monkeypatch, which):
+    """ldpc_decode_{device,host}_packed: bit (j & 31) of word (j >> 5) of row f = decision of variable j of frame f,
+    through the per-iteration path with compaction (frame maps), the on-chip small-code path and ragged n."""
+    L = built_lib
+    monkeypatch.setenv("LDPC_COMPACT_MIN_FRAMES", "128")
+    rng = np.random.default_rng(11)
+    if which == "dvbs2_s20":
+        code, T, B = L.codes.dvbs2_shaped(max_iterations=30, scale=20), 30, 1500
+    elif which == "h74":
+        code, T, B = L.create_test_ldpc_code(), 10, 777
+    else:
+        H = (rng.random((40, 101)) < 0.08).astype(np.int64)
+        code, T, B = L.LDPCCode(101, 61, H, max_iterations=12), 12, 300
+    g = code.graph
+    llr = _mixed_llr(rng, B, g.n, (1.0, 2.5, 4.0, 6.0))
+    dec = L.Neural2DMinSumDecoder(code, weight_sharing_type=2, max_iterations=T)
+    with torch.no_grad():
+        dec._beta_table.uniform_(0.6, 0.9)
+        dec._alpha_table.uniform_(0.9, 1.0)
+    eng = dec._engine(0)
+    x = torch.from_numpy(llr).cuda()
+    bits, post, iters, succ = eng.decode_device(x, want_posterior=True)
+    pk, post2, iters2, succ2 = eng.decode_device(x, want_posterior=True, packed_bits=True)
+    assert pk.shape == (B, eng.row_words) and pk.dtype == torch.int32
+    assert np.array_equal(eng.unpack_rows(pk.cpu().numpy().view(np.uint32)), bits.cpu().numpy())
+    assert torch.equal(post, post2) and torch.equal(iters, iters2) and torch.equal(succ, succ2)
+    hb, hp, hi, hs = eng.decode_host(llr, want_posterior=True, packed_bits=True)
+    assert hb.dtype == np.uint32 and np.array_equal(eng.unpack_rows(hb), bits.cpu().numpy())
+    assert np.array_equal(hp, post.cpu().numpy()) and np.array_equal(hi, iters.cpu().numpy())
+    # bits beyond n in the last word are zero
+    if g.n % 32:
+        assert not (hb[:, -1] >> (g.n % 32)).any()
+    with pytest.raises(ValueError):
+        eng.decode_host(llr, out={"bits": np.empty((B, g.n), np.uint8)}, packed_bits=True)

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
     for name in declared:
         assert getattr(lib, name) is not None
     assert _lib.load().ldpc_version() == 103
-    assert ctypes.sizeof(_lib.DecoderConfig) == 88 and ctypes.sizeof(_lib.Profile) == 80
+    assert ctypes.sizeof(_lib.DecoderConfig) == 88 and ctypes.sizeof(_lib.Profile) == 88
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device failure mode")

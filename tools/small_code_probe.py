@@ -4,6 +4,7 @@ sys.path.insert(0, ".")
 import ldpc_b200 as L
 T = 10
 def run(name, dec, llr, fn):
+    import gc; gc.collect(); torch.cuda.synchronize()   # (a decoder freed inside the timed region stalls it)
     for _ in range(2): fn(llr)
     torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(3): out = fn(llr)
