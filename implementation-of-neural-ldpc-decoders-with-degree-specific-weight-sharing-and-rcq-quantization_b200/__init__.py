@@ -15,4 +15,5 @@ from .neural_minsum_decoder import NeuralMinSumDecoder, NeuralOffsetMinSumDecode
 from .rcq_decoder import NonUniformQuantizer, RCQMinSumDecoder, WeightedRCQDecoder  # noqa: E402,F401
 from .simulation_framework import (LDPSimulator, SimulationConfig, SimulationResult,  # noqa: E402,F401
                                    create_test_decoders)
+from .training_framework import GradientExplosionAnalyzer, PosteriorJointTrainer, TrainingConfig  # noqa: E402,F401
 from . import codes  # noqa: E402,F401

@@ -24,7 +24,7 @@ EXPORTS = [
     "ldpc_version", "ldpc_last_error", "ldpc_device_count", "ldpc_host_alloc", "ldpc_host_free",
     "ldpc_graph_create", "ldpc_graph_destroy", "ldpc_graph_query", "ldpc_graph_slot_of_edge",
     "ldpc_decoder_create", "ldpc_decoder_set_weights", "ldpc_decoder_destroy", "ldpc_decoder_reserve",
-    "ldpc_decode_device", "ldpc_decode_host", "ldpc_decode_device_packed", "ldpc_decode_host_packed", "ldpc_host_chunk_plan", "ldpc_awgn_llr", "ldpc_mc_round", "ldpc_count_errors",
+    "ldpc_decode_device", "ldpc_decode_host", "ldpc_decode_device_packed", "ldpc_decode_host_packed", "ldpc_host_chunk_plan", "ldpc_train_forward", "ldpc_train_backward", "ldpc_awgn_llr", "ldpc_mc_round", "ldpc_count_errors",
     "ldpc_decoder_profile_mode", "ldpc_decoder_profile_read",
 ]
 
@@ -86,6 +86,8 @@ def load():
     lib.ldpc_decode_host.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.ldpc_decode_device_packed.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     lib.ldpc_decode_host_packed.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.ldpc_train_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.ldpc_train_backward.argtypes = [vp, vp, vp, vp, vp]
     lib.ldpc_host_chunk_plan.argtypes = [i64, i64, i32, vp, i32, C.POINTER(i32)]
     lib.ldpc_awgn_llr.argtypes = [C.c_int, i32, i64, u64, u64, C.c_float, i32, vp, vp, vp]
     lib.ldpc_mc_round.argtypes = [vp, C.c_float, i32, u64, u64, i64, vp, vp, vp, vp, vp]

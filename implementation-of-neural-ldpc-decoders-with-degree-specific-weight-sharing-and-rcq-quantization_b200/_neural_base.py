@@ -156,9 +156,35 @@ class DecoderModule(EngineCache, nn.Module):
             post = torch.from_numpy(p) if p is not None else None
         return bits, post, iters, succ, single
 
+    def _trainable(self) -> bool:
+        """Posterior training exists for the normalised float rule (N-NMS, N-2D-NMS): the quantiser of W-RCQ passes no
+        gradient in the reference either, and the offset rule's backward pass is not built."""
+        if getattr(self, "_check_rule", 0) != 0 or self._quant_config()[0] != 0:
+            return False
+        return any(p is not None and p.requires_grad for p in (self._beta_table, self._alpha_table))
+
     def _forward_impl(self, llr):
+        if torch.is_grad_enabled() and self._trainable():
+            return self._forward_train(llr)
         bits, post, iters, _, single = self._run(llr, want_posterior=True)
         decoded = bits.to(torch.int32)  # (posterior < 0).int() in the reference
+        if single:
+            return decoded[0], post[0], int(iters[0].item())
+        return decoded, post, iters
+
+    def _forward_train(self, llr):
+        """forward() under autograd: the same decode, with ``posterior`` differentiable with respect to the weight
+        tables (the reference's forward is differentiable through torch's autograd; ours through the backward
+        kernels of csrc/ldpc_train.cu)."""
+        if not isinstance(llr, torch.Tensor):
+            llr = torch.as_tensor(np.asarray(llr))
+        single = llr.dim() == 1
+        batch = (llr[None] if single else llr).detach()
+        home = batch.device
+        dev = home if home.type == "cuda" else torch.device("cuda", default_device())
+        bits, post, iters = _PosteriorTraining.apply(self, batch.to(dev, torch.float32), self._beta_table, self._alpha_table)
+        bits, post, iters = bits.to(home), post.to(home), iters.to(home)
+        decoded = bits.to(torch.int32)
         if single:
             return decoded[0], post[0], int(iters[0].item())
         return decoded, post, iters
@@ -192,6 +218,37 @@ class DecoderModule(EngineCache, nn.Module):
             missing = [k for k in self.reference_state_dict() if k not in seen]
             if missing:
                 raise KeyError(f"missing keys: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+
+
+class _PosteriorTraining(torch.autograd.Function):
+    """Decode with the message history kept on the device; backward = ldpc_train_backward."""
+
+    @staticmethod
+    def forward(ctx, module, llr, beta_table, alpha_table):
+        eng = module._engine(llr.device.index)          # pushes the current weights (compared by content)
+        bits, post, iters, _ = eng.train_forward(llr)
+        ctx.eng, ctx.serial = eng, eng._train_serial
+        ctx.shapes = tuple((None if t is None else (tuple(t.shape), t.device, t.dtype)) for t in (beta_table, alpha_table))
+        ctx.mark_non_differentiable(bits, iters)
+        return bits, post, iters
+
+    @staticmethod
+    def backward(ctx, _gbits, gpost, _giters):
+        eng = ctx.eng
+        if eng._train_serial != ctx.serial:
+            raise RuntimeError("the decoder ran another training forward pass before this backward pass: its message "
+                               "history was overwritten")
+        gb, ga = eng.train_backward(gpost)
+        out = []
+        for g, spec in zip((gb, ga), ctx.shapes):
+            if spec is None or g is None or not ctx.needs_input_grad[2 + len(out)]:
+                out.append(None)
+                continue
+            shape, device, dtype = spec
+            full = torch.zeros(shape, dtype=dtype, device=device)   # rows beyond max_iterations were not used
+            full[:g.shape[0]] = g.to(device=device, dtype=dtype)
+            out.append(full)
+        return None, None, out[0], out[1]
 
 
 def _weight_views(module):

@@ -504,7 +504,10 @@ struct ldpc_decoder {
         int64_t scan_cap = 0;
         int32_t* d_total = nullptr;   // device int32
         // two checkpoints may be outstanding (the host decides one span late): slot = checkpoint number & 1
-        int32_t* h_total = nullptr;            // pinned host int32[2]
+        int32_t* h_total = nullptr;            // mapped pinned host int32[2], written by the scan kernel itself: a
+                                               // copy on the D2H engine would queue behind the output copies of the
+                                               // host pipeline (hundreds of MB with posteriors) and stall the job
+        int32_t* h_total_dev = nullptr;        // the same words as the device sees them
         cudaEvent_t ev[2] = {nullptr, nullptr};   // recorded after a checkpoint's count has been copied to h_total[slot]
         // end of the last call that used this context, and the stream it ran on: a call on ANOTHER stream first
         // waits for it (the workspace is shared), and so does a weight update
@@ -537,6 +540,17 @@ struct ldpc_decoder {
     int speculate = 0;            // LDPC_SPECULATE=1: keep a second span in flight while the host waits for a checkpoint (see DecodeJob)
     int post_mode = 0;            // LDPC_POST_MODE: 0 adaptive, 1 posterior rows refreshed every iteration, 2 written on stop
     int64_t stat_compactions = 0, stat_early_exits = 0;
+    // posterior training: the forward pass keeps every iteration's messages for the backward pass
+    struct TrainCtx {
+        Workspace ws;
+        float* v2c_hist = nullptr;   // [T][E][cap]
+        float* c2v_hist = nullptr;   // [T][E][cap]
+        float* g_v2c = nullptr;      // [E][cap]
+        float* g_c2v = nullptr;      // [E][cap]
+        float* g_post = nullptr;     // [n][cap]
+        int64_t cap = 0;
+        int64_t B = 0, Bp = 0;       // of the last forward pass (0: none yet)
+    } train;
     // instrumentation
     int prof_mode = 0;
     ldpc_profile prof{};
@@ -817,9 +831,10 @@ int emit_level(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, const int3
     if (map) {
         if (o.iters || o.success)
             LAUNCH(K_OTHER, launch_scatter_frames(ws.iters, ws.success, o.iters, o.success, map, B, stream));
-    } else {
-        if (o.iters) CU(cudaMemcpyAsync(o.iters, ws.iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-        if (o.success) CU(cudaMemcpyAsync(o.success, ws.success, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+    } else if (o.iters || o.success) {
+        // (a kernel, not cudaMemcpyAsync: copies of the run streams must not queue on a copy engine behind the host
+        // pipeline's bulk transfers)
+        LAUNCH(K_OTHER, launch_scatter_frames(ws.iters, ws.success, o.iters, o.success, nullptr, B, stream));
     }
     return LDPC_OK;
 }
@@ -895,7 +910,10 @@ int scan_ensure(ldpc_decoder::Ctx& cx, int64_t Bp) {
         cx.scan_cap = nb;
     }
     if (!cx.d_total) CU(cudaMalloc((void**)&cx.d_total, sizeof(int32_t)));
-    if (!cx.h_total) CU(cudaHostAlloc((void**)&cx.h_total, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    if (!cx.h_total) {
+        CU(cudaHostAlloc((void**)&cx.h_total, 2 * sizeof(int32_t), cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&cx.h_total_dev, cx.h_total, 0));
+    }
     for (auto& e : cx.ev)
         if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return LDPC_OK;
@@ -1019,8 +1037,7 @@ int job_enqueue(DecodeJob& j) {
         return emit_level(d, *j.ws, j.curB, j.curBp, j.map, nullptr, j.o, stream);
     }
     const uint32_t slot = j.cp_issued & 1u;
-    LAUNCH(K_OTHER, launch_pending_scan(j.ws->done, j.curBp, j.cx->d_scan, j.cx->d_total, stream));
-    CU(cudaMemcpyAsync(j.cx->h_total + slot, j.cx->d_total, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    LAUNCH(K_OTHER, launch_pending_scan(j.ws->done, j.curBp, j.cx->d_scan, j.cx->d_total, j.cx->h_total_dev + slot, stream));
     CU(cudaEventRecord(j.cx->ev[slot], stream));
     j.cp_t[slot] = j.t;
     j.cp_issued++;
@@ -1262,6 +1279,20 @@ std::vector<std::pair<int64_t, int64_t>> plan_chunks(int64_t B, int64_t chunk, i
     return chunks;
 }
 
+// With posteriors the outputs of a chunk are as large as its inputs, and nothing overlaps the copy-out of the LAST
+// chunk: split it so that the un-overlapped tail is a quarter of it (halves, then quarters; multiples of 128 frames).
+void taper_tail(std::vector<std::pair<int64_t, int64_t>>& chunks) {
+    if (chunks.size() < 3) return;
+    const std::pair<int64_t, int64_t> last = chunks.back();
+    if (last.second < 8 * kFrameAlign) return;
+    const int64_t half = last.second / 2 / kFrameAlign * kFrameAlign;
+    const int64_t quarter = (last.second - half) / 2 / kFrameAlign * kFrameAlign;
+    chunks.pop_back();
+    chunks.emplace_back(last.first, half);
+    chunks.emplace_back(last.first + half, quarter);
+    chunks.emplace_back(last.first + half + quarter, last.second - half - quarter);
+}
+
 int decode_on_device(ldpc_decoder* d, ldpc_decoder::Ctx& cx, const void* llr, int64_t B, uint8_t* bits, uint32_t* packed,
                      void* post, int32_t* iters, uint8_t* success, cudaStream_t stream) {
     DecodeJob j;
@@ -1465,6 +1496,12 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
     }
+    d->train.ws.release();
+    cudaFree(d->train.v2c_hist);
+    cudaFree(d->train.c2v_hist);
+    cudaFree(d->train.g_v2c);
+    cudaFree(d->train.g_c2v);
+    cudaFree(d->train.g_post);
     cudaFree(d->d_bidx);
     cudaFree(d->d_aidx);
     cudaFree(d->d_aidx_slot);
@@ -1561,7 +1598,8 @@ int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits,
         pp.post_cap = posterior != nullptr;
     }
     int rc = LDPC_OK;
-    const std::vector<std::pair<int64_t, int64_t>> chunks = plan_chunks(B, chunk, d->V);   // (offset, frames)
+    std::vector<std::pair<int64_t, int64_t>> chunks = plan_chunks(B, chunk, d->V);   // (offset, frames)
+    if (posterior) taper_tail(chunks);
     // Two chunks decode at a time (two contexts, two kernel streams): each is a resumable job, the host enqueues
     // one span per job in turn and blocks on the older of the two outstanding checkpoints, so that while one job
     // waits for its host round trip -- and while its kernels drain -- the other one keeps the SMs busy.  The
@@ -1691,6 +1729,143 @@ extern "C" int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per
     const auto plan = plan_chunks(B, chunk > 0 ? chunk : 8192, frames_per_lane);
     *n_chunks = (int32_t)plan.size();
     for (int32_t i = 0; i < (int32_t)plan.size() && i < max_chunks && frames_out; ++i) frames_out[i] = plan[(size_t)i].second;
+    return LDPC_OK;
+}
+
+// =================================================================================================
+// Posterior training
+// =================================================================================================
+namespace {
+int train_supported(const ldpc_decoder* d) {
+    if (d->dtype != LDPC_F32 || d->bc != 0 || d->check_rule != LDPC_RULE_NORMALIZED || d->schedule != LDPC_SCHEDULE_FLOODING)
+        return fail(LDPC_ERR_UNSUPPORTED, "training exists for the float32 normalised neural min-sum decoders (flooding)");
+    return LDPC_OK;
+}
+}  // namespace
+
+extern "C" int ldpc_train_forward(ldpc_decoder* d, const float* llr, int64_t B, uint8_t* bits, float* posterior,
+                                  int32_t* iterations, uint8_t* success, void* stream_) {
+    if (!d || !llr) return fail(LDPC_ERR_INVALID, "NULL argument");
+    if (B < 1) return fail(LDPC_ERR_INVALID, "B must be >= 1");
+    int rc = train_supported(d);
+    if (rc) return rc;
+    DeviceGuard guard(d->g->device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const ldpc_graph* g = d->g;
+    ldpc_decoder::TrainCtx& tc = d->train;
+    const int64_t Bp = pad_frames(B);
+    const size_t E = (size_t)std::max<int64_t>(g->E, 1);
+    tc.B = tc.Bp = 0;
+    if (tc.cap < Bp) {
+        cudaFree(tc.v2c_hist); cudaFree(tc.c2v_hist); cudaFree(tc.g_v2c); cudaFree(tc.g_c2v); cudaFree(tc.g_post);
+        tc.v2c_hist = tc.c2v_hist = tc.g_v2c = tc.g_c2v = tc.g_post = nullptr;
+        tc.cap = 0;
+        rc = ws_ensure(d, tc.ws, Bp);
+        if (rc) return rc;
+        CU(cudaMalloc((void**)&tc.v2c_hist, (size_t)d->T * E * Bp * sizeof(float)));
+        CU(cudaMalloc((void**)&tc.c2v_hist, (size_t)d->T * E * Bp * sizeof(float)));
+        CU(cudaMalloc((void**)&tc.g_v2c, E * Bp * sizeof(float)));
+        CU(cudaMalloc((void**)&tc.g_c2v, E * Bp * sizeof(float)));
+        CU(cudaMalloc((void**)&tc.g_post, (size_t)g->n * Bp * sizeof(float)));
+        tc.cap = tc.ws.cap;
+    }
+    Workspace& ws = tc.ws;
+    const int64_t cap = ws.cap;   // row stride of the history slices is the launch's Bp, slices are sized for cap
+    (void)cap;
+    rc = post_ensure(d, ws);
+    if (rc) return rc;
+    d->prof.frames_padded = Bp;
+    LAUNCH(K_OTHER, launch_pack(d->dtype, llr, ws.llrT, B, Bp, g->n, ws.done, ws.iters, ws.success, d->T, stream));
+    LAUNCH(K_OTHER, launch_reset_state(ws.done, ws.iters, ws.success, ws.unsat, B, Bp, d->T, stream));
+    const int64_t Wn = Bp / 32;
+    const size_t slice = E * (size_t)Bp;
+    for (int t = 0; t < d->T; ++t) {
+        CnLaunch cn{};
+        fill_cn(d, ws, Bp, t, cn);
+        cn.src = (t == 0) ? ws.llrT : (const void*)(tc.v2c_hist + (size_t)t * slice);
+        cn.dst = tc.c2v_hist + (size_t)t * slice;
+        LAUNCH(K_CN, launch_cn(d->dtype, cn, stream));
+        const bool last = (t == d->T - 1);
+        VnLaunch vn{};
+        fill_vn(d, ws, Bp, t, last, true, vn);
+        vn.c2v = tc.c2v_hist + (size_t)t * slice;
+        vn.v2c = last ? nullptr : (void*)(tc.v2c_hist + (size_t)(t + 1) * slice);
+        LAUNCH(K_VN, launch_vn(d->dtype, vn, stream));
+        uint32_t* cur = ws.unsat + (size_t)(t & 1) * Wn;
+        uint32_t* nxt = ws.unsat + (size_t)((t + 1) & 1) * Wn;
+        SynLaunch sy{};
+        sy.hardw = ws.hardw;
+        sy.Wn = Wn;
+        sy.slot_var = g->d_slot_var;
+        sy.items = g->cn[item_set(d, Bp)].d;
+        sy.n_items = (int)g->cn[item_set(d, Bp)].items.size();
+        sy.unsat = cur;
+        LAUNCH(K_OTHER, launch_syndrome(sy, stream));
+        LAUNCH(K_OTHER, launch_commit(d->V, cur, nxt, ws.done, ws.iters, ws.success, t + 1, Bp, stream));
+    }
+    OutSpec o;
+    o.bits = bits;
+    o.post = posterior;
+    o.iters = iterations;
+    o.success = success;
+    rc = emit_level(d, ws, B, Bp, nullptr, nullptr, o, stream);
+    if (rc) return rc;
+    tc.B = B;
+    tc.Bp = Bp;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_train_backward(ldpc_decoder* d, const float* grad_posterior, float* grad_beta, float* grad_alpha,
+                                   void* stream_) {
+    if (!d || !grad_posterior) return fail(LDPC_ERR_INVALID, "NULL argument");
+    int rc = train_supported(d);
+    if (rc) return rc;
+    ldpc_decoder::TrainCtx& tc = d->train;
+    if (tc.B < 1) return fail(LDPC_ERR_INVALID, "ldpc_train_backward needs a preceding ldpc_train_forward");
+    if (grad_beta && !d->d_beta) return fail(LDPC_ERR_INVALID, "decoder was created without beta");
+    if (grad_alpha && !d->d_alpha) return fail(LDPC_ERR_INVALID, "decoder was created without alpha");
+    DeviceGuard guard(d->g->device);
+    if (!guard.ok) return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", d->g->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const ldpc_graph* g = d->g;
+    const int64_t B = tc.B, Bp = tc.Bp;
+    const size_t E = (size_t)std::max<int64_t>(g->E, 1);
+    const size_t slice = E * (size_t)Bp;
+    LAUNCH(K_OTHER, launch_pack(LDPC_F32, grad_posterior, tc.g_post, B, Bp, g->n, nullptr, nullptr, nullptr, d->T, stream));
+    if (grad_beta) CU(cudaMemsetAsync(grad_beta, 0, (size_t)d->T * d->n_beta * sizeof(float), stream));
+    if (grad_alpha) CU(cudaMemsetAsync(grad_alpha, 0, (size_t)d->T * d->n_alpha * sizeof(float), stream));
+    TrainBwd p{};
+    p.B = B;
+    p.Bp = Bp;
+    p.iters = tc.ws.iters;
+    p.cn_items = g->cn[0].d;
+    p.n_cn_items = (int)g->cn[0].items.size();
+    p.vn_items = g->vn[0].d;
+    p.n_vn_items = (int)g->vn[0].items.size();
+    p.slot_var = g->d_slot_var;
+    p.vslots = g->d_vslots;
+    p.vpos_var = g->d_vpos_var;
+    p.bidx = d->d_bidx;
+    p.beta_per_edge = d->beta_per_edge;
+    p.beta = static_cast<const float*>(d->d_beta);
+    p.n_beta = d->n_beta;
+    p.beta_const = 1.f;
+    p.aidx = d->d_aidx;
+    p.alpha = static_cast<const float*>(d->d_alpha);
+    p.n_alpha = d->n_alpha;
+    p.llrT = static_cast<const float*>(tc.ws.llrT);
+    p.g_post = tc.g_post;
+    p.g_v2c = tc.g_v2c;
+    p.g_c2v = tc.g_c2v;
+    p.g_beta = grad_beta;
+    p.g_alpha = grad_alpha;
+    for (int t = d->T - 1; t >= 0; --t) {
+        p.v2c_t = tc.v2c_hist + (size_t)t * slice;
+        p.c2v_t = tc.c2v_hist + (size_t)t * slice;
+        LAUNCH(K_OTHER, launch_train_bwd_vn(p, t, stream));
+        LAUNCH(K_OTHER, launch_train_bwd_cn(p, t, stream));
+    }
     return LDPC_OK;
 }
 

@@ -124,6 +124,37 @@ struct SmallLaunch {
 bool small_decode_fits(int dtype, const SmallLaunch& p);
 cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream);
 
+// One iteration of the training backward pass (ldpc_train.cu); float32, normalised rule, frames in the [rows][Bp] layout.
+struct TrainBwd {
+    int64_t B, Bp;
+    const int32_t* iters;       // [Bp] iterations each frame executed (forward pass)
+    const WorkItem* cn_items;
+    int n_cn_items;
+    const WorkItem* vn_items;
+    int n_vn_items;
+    const int32_t* slot_var;
+    const int32_t* vslots;
+    const int32_t* vpos_var;
+    const int32_t* bidx;        // per slot or nullptr
+    int beta_per_edge;
+    const float* beta;          // [T][n_beta] or nullptr
+    int n_beta;
+    float beta_const;           // beta when there is no table
+    const int32_t* aidx;        // per position or nullptr
+    const float* alpha;         // [T][n_alpha] or nullptr
+    int n_alpha;
+    const float* llrT;          // [n][Bp]: inputs of the check nodes of iteration 0 (through slot_var)
+    const float* v2c_t;         // [E][Bp] inputs of the check nodes of iteration t (t > 0)
+    const float* c2v_t;         // [E][Bp] their outputs
+    const float* g_post;        // [n][Bp] gradient of the loss with respect to the posteriors
+    float* g_v2c;               // [E][Bp] in: g v2c_{t+1};  out (check side): g v2c_t
+    float* g_c2v;               // [E][Bp] g c2v_t
+    float* g_beta;              // [T][n_beta] accumulated, or nullptr
+    float* g_alpha;             // [T][n_alpha] accumulated, or nullptr
+};
+cudaError_t launch_train_bwd_vn(const TrainBwd& p, int t, cudaStream_t stream);
+cudaError_t launch_train_bwd_cn(const TrainBwd& p, int t, cudaStream_t stream);
+
 // All launchers enqueue on `stream` and return the CUDA launch status.
 cudaError_t launch_cn(int dtype, const CnLaunch& p, cudaStream_t stream);
 cudaError_t launch_vn(int dtype, const VnLaunch& p, cudaStream_t stream);
@@ -188,7 +219,9 @@ cudaError_t launch_count_packed(int V, const uint32_t* hardw, int64_t Wn, int32_
                                 const uint8_t* only_done, int32_t* frame_cnt /* scratch [Wn*32] */, cudaStream_t stream);
 // frame compaction bookkeeping: counts[ceil(Bp/1024)] becomes the exclusive scan of running frames per
 // 1024-frame block and total[0] their number; then idx[0..total) = the running frames in ascending order
-cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, cudaStream_t stream);
+// total_host (may be nullptr): device-visible address of a mapped pinned host word that receives the total as well
+cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, int32_t* total_host,
+                                cudaStream_t stream);
 cudaError_t launch_pending_indices(const uint8_t* done, int64_t Bp, const int32_t* offsets, int32_t* idx, cudaStream_t stream);
 // dst [rows][Bp_dst] column i = src [rows][Bp_src] column idx[i] (i < count), zero for the pad columns
 cudaError_t launch_gather_cols(int dtype, const void* src, int64_t Bp_src, void* dst, int64_t Bp_dst, const int32_t* idx,

@@ -430,7 +430,8 @@ __global__ void __launch_bounds__(kScanBlock) pending_count_kernel(const uint8_t
 
 // in-place exclusive scan of counts[nb] by one block; total[0] = sum
 __global__ void __launch_bounds__(kScanBlock) pending_scan_kernel(int32_t* __restrict__ counts, int nb,
-                                                                   int32_t* __restrict__ total) {
+                                                                   int32_t* __restrict__ total,
+                                                                   volatile int32_t* __restrict__ total_host) {
     __shared__ int32_t s_warp[kScanBlock / 32];
     __shared__ int32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -464,7 +465,13 @@ __global__ void __launch_bounds__(kScanBlock) pending_scan_kernel(int32_t* __res
         if (threadIdx.x == kScanBlock - 1) s_carry = before + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) total[0] = s_carry;
+    if (threadIdx.x == 0) {
+        total[0] = s_carry;
+        if (total_host) {   // mapped pinned host word: the checkpoint count reaches the host without a copy-engine hop
+            *total_host = s_carry;
+            __threadfence_system();
+        }
+    }
 }
 
 // idx[offsets[b] + r] = r-th running frame of block b (ascending frame order overall)
@@ -636,10 +643,11 @@ cudaError_t launch_count_bits(const uint8_t* bits, int32_t n, int64_t B, const u
     return cudaGetLastError();
 }
 
-cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, cudaStream_t stream) {
+cudaError_t launch_pending_scan(const uint8_t* done, int64_t Bp, int32_t* counts, int32_t* total, int32_t* total_host,
+                                cudaStream_t stream) {
     const int nb = (int)((Bp + kScanBlock - 1) / kScanBlock);
     pending_count_kernel<<<nb, kScanBlock, 0, stream>>>(done, Bp, counts);
-    pending_scan_kernel<<<1, kScanBlock, 0, stream>>>(counts, nb, total);
+    pending_scan_kernel<<<1, kScanBlock, 0, stream>>>(counts, nb, total, total_host);
     return cudaGetLastError();
 }
 

@@ -322,6 +322,47 @@ class Engine:
                 post.data_ptr() if post is not None else None, iters.data_ptr(), succ.data_ptr(), stream))
         return bits, post, iters, succ
 
+    # ------------------------------------------------------------------ posterior training
+    def train_forward(self, llr):
+        """forward() of a training step: llr CUDA float32 [B, n]; keeps every iteration's messages in the handle for
+        ``train_backward``.  Returns bits u8, posterior f32, iterations i32, success u8 (CUDA)."""
+        import torch
+
+        if llr.device.type != "cuda" or llr.device.index != self.device:
+            raise ValueError(f"llr must live on cuda:{self.device}")
+        if llr.dim() != 2 or llr.shape[1] != self.graph.n:
+            raise IndexError(f"llr must have shape [B, {self.graph.n}], got {tuple(llr.shape)}")
+        llr = llr.to(torch.float32).contiguous()
+        B, dev = llr.shape[0], llr.device
+        bits = torch.empty((B, self.graph.n), dtype=torch.uint8, device=dev)
+        post = torch.empty((B, self.graph.n), dtype=torch.float32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        succ = torch.empty(B, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with self._lock:
+            _lib.check(_lib.load().ldpc_train_forward(self._h, llr.data_ptr(), B, bits.data_ptr(), post.data_ptr(),
+                                                      iters.data_ptr(), succ.data_ptr(), stream))
+            self._train_serial = getattr(self, "_train_serial", 0) + 1
+            self._train_frames = B
+        return bits, post, iters, succ
+
+    def train_backward(self, grad_posterior):
+        """d loss / d posterior [B, n] (CUDA float32, the frames of the last ``train_forward``) ->
+        (d loss / d beta [T, n_beta] | None, d loss / d alpha [T, n_alpha] | None) as CUDA float32 tensors."""
+        import torch
+
+        g = grad_posterior.to(torch.float32).contiguous()
+        if g.shape != (getattr(self, "_train_frames", -1), self.graph.n):
+            raise ValueError("grad_posterior must match the batch of the last train_forward")
+        dev = g.device
+        gb = torch.empty((self.T, self._n_beta), dtype=torch.float32, device=dev) if self._n_beta else None
+        ga = torch.empty((self.T, self._n_alpha), dtype=torch.float32, device=dev) if self._n_alpha else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with self._lock:
+            _lib.check(_lib.load().ldpc_train_backward(self._h, g.data_ptr(), gb.data_ptr() if gb is not None else None,
+                                                       ga.data_ptr() if ga is not None else None, stream))
+        return gb, ga
+
     # ------------------------------------------------------------------ Monte-Carlo
     def mc_round(self, snr_db: float, frames: int, *, seed: int, frame0: int, llr_sign: int, counters,
                  codeword=None, frame_bit_errors=None, frame_iterations=None):

@@ -164,6 +164,26 @@ int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int6
                          int32_t max_chunks, int32_t *n_chunks);
 
 /* ---------------------------------------------------------------------------------------------
+ * Posterior training.  Replaces the forward + autograd backward of PosteriorJointTrainer.train_epoch
+ * (training_framework.py:108-165, which as shipped crashes -- SURVEY appendix C3; the two repairs are recorded in
+ * oracle/reference_training_repairs.patch) for the float32 normalised neural min-sum decoders
+ * (NeuralMinSumDecoder, Neural2DMinSumDecoder types 1-4), batched over frames.
+ *
+ * ldpc_train_forward : ldpc_decode_device with every iteration's messages kept in the handle (2*T*E floats per frame).
+ * ldpc_train_backward: given d loss / d posterior [B][n] (device, of the frames of the last forward call) writes
+ *                      d loss / d beta [T][n_beta] and d loss / d alpha [T][n_alpha] (device float32, either may be
+ *                      NULL), i.e. what torch.autograd accumulates into the reference's ParameterDict entries:
+ *                      the posterior of a frame is the one of the iteration it stopped at, min1 sends its gradient to
+ *                      the first argmin, min2 shares it among ties, sign() and the quantities derived from it carry
+ *                      none.  Gradients are summed over the frames with float32 atomics (order not fixed: compare
+ *                      with a tolerance).
+ * ------------------------------------------------------------------------------------------- */
+int ldpc_train_forward(ldpc_decoder *d, const float *llr, int64_t B, uint8_t *bits, float *posterior,
+                       int32_t *iterations, uint8_t *success, void *stream);
+int ldpc_train_backward(ldpc_decoder *d, const float *grad_posterior, float *grad_beta, float *grad_alpha,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Monte-Carlo leg.  Replaces simulate_awgn_channel (ldpc_decoder.py:286-302) and the per-frame
  * body of LDPSimulator.simulate_single_snr (simulation_framework.py:110-131).
  *

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _tiny_graph(rng, f64):
     """Random H whose per-frame state fits the on-chip budget (896 bytes: 2E + n values + decision words)."""
-    budget = 111 if f64 else 223
+    budget = 108 if f64 else 218     # (2E + n) values + the decision words within 896 bytes
     while True:
         m, n = int(rng.integers(2, 9)), int(rng.integers(4, 22))
         H = np.zeros((m, n), dtype=np.int64)
@@ -24,7 +24,7 @@ def _tiny_graph(rng, f64):
         if rng.random() < 0.3:
             H[:, rng.integers(0, n)] = 0                                          # degree-0 variable
         E = int(H.sum())
-        if 0 < E and 2 * E + n <= budget:
+        if 0 < E and 2 * E + n <= budget and E * (8 if f64 else 4) >= n:   # (decisions are staged in the v2c columns)
             return H
 
 

@@ -165,3 +165,59 @@ def test_ldpccode_notices_a_new_H(built_lib):
     assert code.graph.E == 14
     code.invalidate()
     assert code.graph.E == 15 and code.variable_node_degrees[6] == 2
+
+
+def test_the_recorded_repairs_make_the_reference_trainer_run(built_lib):
+    """oracle/reference_training_repairs.patch (the oracle agreed for training): applied to the reference's
+    training_framework.py in memory, one epoch of its PosteriorJointTrainer runs on the (7,4) code."""
+    import os
+    import sys
+    import types
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("live reference only exists in the build container")
+    ref = ref_shim.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "training_framework.py"), newline="").read().split("\n")
+    patch = open(os.path.join(root, "oracle", "reference_training_repairs.patch"), newline="").read().split("\n")
+    out, pos, i = [], 0, 0
+    while i < len(patch):
+        line = patch[i]
+        if line.startswith("@@"):
+            start = int(line.split()[1].split(",")[0][1:]) - 1
+            out += src[pos:start]
+            pos = start
+            i += 1
+            while i < len(patch) and not patch[i].startswith("@@"):
+                h = patch[i]
+                if h.startswith("+"):
+                    out.append(h[1:])
+                elif h.startswith("-"):
+                    assert src[pos] == h[1:], (src[pos], h)
+                    pos += 1
+                elif h.startswith(" "):
+                    assert src[pos] == h[1:], (src[pos], h)
+                    out.append(src[pos])
+                    pos += 1
+                i += 1
+        else:
+            i += 1
+    out += src[pos:]
+    mod = types.ModuleType("ref_training_repaired")
+    saved = {k: sys.modules.get(k) for k in ("ldpc_decoder", "neural_2d_decoder", "rcq_decoder")}
+    sys.modules.update(ldpc_decoder=ref.ldpc_decoder, neural_2d_decoder=ref.neural_2d_decoder, rcq_decoder=ref.rcq_decoder)
+    try:
+        exec(compile("\n".join(out).replace("\r", ""), "training_framework_repaired.py", "exec"), mod.__dict__)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    code = ref.ldpc_decoder.create_test_ldpc_code()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = ref.neural_2d_decoder.Neural2DMinSumDecoder(code, 2, 3)
+    tr = mod.PosteriorJointTrainer(model, mod.TrainingConfig(batch_size=4, num_epochs=1))
+    hist = tr.train(code, num_train_samples=8, num_val_samples=4)
+    assert len(hist["train_losses"]) == 1 and np.isfinite(hist["train_losses"][0]) and hist["gradient_norms"][0] > 0
