@@ -182,6 +182,7 @@ class DecoderModule(EngineCache, nn.Module):
         batch = (llr[None] if single else llr).detach()
         home = batch.device
         dev = home if home.type == "cuda" else torch.device("cuda", default_device())
+        self._engine(dev.index)     # no device -> LdpcError here, like the inference path (there is no CPU fallback)
         bits, post, iters = _PosteriorTraining.apply(self, batch.to(dev, torch.float32), self._beta_table, self._alpha_table)
         bits, post, iters = bits.to(home), post.to(home), iters.to(home)
         decoded = bits.to(torch.int32)

@@ -21,7 +21,7 @@ def golden_cases():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         stem = os.path.splitext(os.path.basename(f))[0]
-        if stem == "quantizer_kat" or stem.endswith("_next") or stem.startswith("fullsize_"):
+        if stem == "quantizer_kat" or stem.endswith("_next") or stem.startswith(("fullsize_", "train_")):
             continue
         z = np.load(f)
         for c in sorted(set(k.split("/")[0] for k in z.files)):
