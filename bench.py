@@ -480,8 +480,9 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
         out = step()
     rig.barrier()
     avg_iters = float(out[2].float().mean().item())
-    eng.profile_read(reset=True)
-    eng.profile_mode(1)
+    on_chip = eng.profile_read(reset=True)["small_decodes"] > 0
+    # per-launch CUDA events for the check / variable node kernels (a one-launch on-chip decode has nothing to split)
+    eng.profile_mode(0 if on_chip else 1)
     if sampler is not None:
         sampler.start()
     ms, out = rig.timed_device(step, steps, 0)
@@ -629,7 +630,8 @@ def mc_sweep_leg(rig, L, args):
     cfg = L.SimulationConfig(snr_range=(0.0, 6.0), snr_step=0.5, max_frames=per_gpu * rig.world * 2, max_errors=200,
                              batch_frames=per_gpu, seed=20, save_results=False)
     sim = L.LDPSimulator(cfg)
-    sim.simulate_single_snr(dec, code, 3.0, per_gpu * rig.world, 10 ** 9)     # warm-up / workspace allocation
+    for snr in (0.5, 1.0, 1.5, 3.0):     # warm-up: the workspaces of every compaction pattern are allocated here
+        sim.simulate_single_snr(dec, code, snr, per_gpu * rig.world, 10 ** 9)
     rig.barrier()
     t0 = time.perf_counter()
     res = sim.simulate_decoder(dec, code, "N-2D-NMS Type 2")

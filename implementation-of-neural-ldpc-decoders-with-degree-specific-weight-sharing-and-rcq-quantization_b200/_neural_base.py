@@ -71,6 +71,10 @@ class DecoderModule(EngineCache, nn.Module):
         self.max_iterations = max_iterations
         self._engines = {}
         self._pushed = {}
+        # forward() under autograd is differentiable with respect to the weights only when asked for (the trainer
+        # classes switch it on): the training forward keeps 2*T*E floats per frame, which inference batches of
+        # tens of thousands of frames must never pay just because torch's grad mode is on by default
+        self.differentiable = False
         # state_dict() / load_state_dict() speak the reference's ParameterDict layout (see the hooks below)
         self._register_state_dict_hook(_export_reference_keys)
         self._register_load_state_dict_pre_hook(_import_reference_keys, with_module=True)
@@ -159,7 +163,7 @@ class DecoderModule(EngineCache, nn.Module):
     def _trainable(self) -> bool:
         """Posterior training exists for the normalised float rule (N-NMS, N-2D-NMS): the quantiser of W-RCQ passes no
         gradient in the reference either, and the offset rule's backward pass is not built."""
-        if getattr(self, "_check_rule", 0) != 0 or self._quant_config()[0] != 0:
+        if not self.differentiable or getattr(self, "_check_rule", 0) != 0 or self._quant_config()[0] != 0:
             return False
         return any(p is not None and p.requires_grad for p in (self._beta_table, self._alpha_table))
 

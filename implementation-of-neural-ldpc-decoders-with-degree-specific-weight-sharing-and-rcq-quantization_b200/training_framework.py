@@ -67,6 +67,8 @@ class PosteriorJointTrainer:
     def __init__(self, model: nn.Module, config: TrainingConfig):
         self.model = model
         self.config = config
+        if hasattr(model, "differentiable"):
+            model.differentiable = True     # forward() under autograd now keeps the message history (see DecoderModule)
         # the weight tables stay where the module keeps them (they are a few KB; the decode runs on the GPU anyway)
         self.device = torch.device(config.device if torch.cuda.is_available() or config.device == 'cpu' else 'cpu')
         self.optimizer = optim.Adam(self.model.parameters(), lr=config.learning_rate)
@@ -164,6 +166,8 @@ class GradientExplosionAnalyzer:
     def __init__(self, model: nn.Module, code: LDPCCode):
         self.model = model
         self.code = code
+        if hasattr(model, "differentiable"):
+            model.differentiable = True
 
     def analyze_gradient_explosion(self, num_samples: int = 100) -> Dict[str, List[float]]:
         self.model.eval()

@@ -22,6 +22,7 @@ def _load(L, z, name):
     dec = L.NeuralMinSumDecoder(code, T) if kind == "nnms" else L.Neural2DMinSumDecoder(code, int(kind[-1]), T)
     keys = [str(k) for k in z[f"{name}/keys"]]
     dec.load_state_dict({k: torch.tensor([v]) for k, v in zip(keys, z[f"{name}/weights"])})
+    dec.differentiable = True      # (off by default: inference batches must not keep the message history)
     return dec, keys
 
 
@@ -127,6 +128,8 @@ def test_backward_needs_its_own_forward(built_lib):
     code = L.create_test_ldpc_code()
     dec = L.Neural2DMinSumDecoder(code, 3, 4)
     x = torch.randn(8, 7, device="cuda") * 2
+    assert not dec(x)[1].requires_grad         # differentiable only when asked for
+    dec.differentiable = True
     _, p1, _ = dec(x)
     _, p2, _ = dec(x + 1)                     # overwrites the message history of the first pass
     with pytest.raises(RuntimeError):
