@@ -51,7 +51,7 @@ class Profile(C.Structure):
         ("launches", C.c_int64), ("cn_launches", C.c_int64), ("vn_launches", C.c_int64),
         ("cn_ms", C.c_double), ("vn_ms", C.c_double), ("other_ms", C.c_double),
         ("frames_padded", C.c_int64), ("compactions", C.c_int64), ("early_exits", C.c_int64),
-        ("graph_replays", C.c_int64), ("small_decodes", C.c_int64),
+        ("graph_replays", C.c_int64), ("small_decodes", C.c_int64), ("resident_decodes", C.c_int64),
     ]
 
 

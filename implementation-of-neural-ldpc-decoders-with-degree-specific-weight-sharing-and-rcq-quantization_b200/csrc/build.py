@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.realpath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, f) for f in ("ldpc_cn.cu", "ldpc_vn.cu", "ldpc_misc.cu", "ldpc_small.cu", "ldpc_train.cu", "ldpc_api.cu")]
+SOURCES = [os.path.join(HERE, f) for f in ("ldpc_cn.cu", "ldpc_vn.cu", "ldpc_misc.cu", "ldpc_small.cu", "ldpc_resident.cu", "ldpc_train.cu", "ldpc_api.cu")]
 HEADERS = [os.path.join(HERE, "ldpc_device.cuh"), os.path.join(HERE, "ldpc_kernel_common.cuh"), os.path.join(HERE, "ldpc_cn_common.cuh"),
            os.path.join(HERE, "ldpc_internal.h"), os.path.join(os.path.dirname(PKG), "include", "ldpc_b200.h")]
 OBJDIR = os.path.join(HERE, "build")

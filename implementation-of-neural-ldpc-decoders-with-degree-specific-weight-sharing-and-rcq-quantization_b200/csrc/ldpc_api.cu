@@ -482,6 +482,10 @@ struct ldpc_decoder {
     int all_mono = 1;
     int use_small = 1;                     // LDPC_SMALL=0: never take the on-chip decode for small codes
     int64_t stat_small = 0;
+    int use_resident = -1;                 // LDPC_RESIDENT: 1 always / 0 never take the CTA-resident decode; -1 = policy
+    int sm_count = 0;
+    int64_t stat_resident = 0;
+    bool resident_default = false;         // what the policy says for this decoder (set at creation)
     HostPipe pipe;
     int64_t host_chunk = 0;
     int layered_levels = 1;       // LDPC_LAYERED_LEVELS=0: always the sequential layered kernel
@@ -884,6 +888,47 @@ bool fill_small(ldpc_decoder* d, Workspace* ws, int64_t B, int64_t Bp, bool want
     return small_decode_fits(d->dtype, sp);
 }
 
+// CTA-resident decode (ldpc_resident.cu), if a frame's messages fit one SM's shared memory.
+bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
+    const ldpc_graph* g = d->g;
+    if (d->use_resident == 0 || d->dtype != LDPC_F32 || d->schedule != LDPC_SCHEDULE_FLOODING) return false;
+    rp.B = B;
+    rp.T = d->T;
+    rp.early_stop = d->early_stop;
+    rp.n = g->n;
+    rp.E = (int)g->E;
+    rp.n_checks = (int)g->cn[1].items.size();
+    rp.max_dv = g->max_dv;
+    rp.cn_items = g->cn[1].d;
+    rp.vn_items = g->vn[1].d;
+    rp.slot_var = g->d_slot_var;
+    rp.vslots = g->d_vslots;
+    rp.vpos_var = g->d_vpos_var;
+    rp.bidx = d->d_bidx;
+    rp.beta_per_edge = d->beta_per_edge;
+    rp.beta = static_cast<const float*>(d->d_beta);
+    rp.n_beta = d->n_beta;
+    rp.aidx = d->d_aidx;
+    rp.aidx_slot = d->d_aidx_slot;
+    rp.alpha = static_cast<const float*>(d->d_alpha);
+    rp.n_alpha = d->n_alpha;
+    rp.check_rule = d->check_rule;
+    rp.bc = d->bc;
+    rp.nth = d->nth;
+    rp.n_quant = d->Q;
+    rp.thr = d->d_thr;
+    rp.lut = d->d_lut;
+    rp.q_of_iter = d->d_qoi;
+    rp.mono = d->d_mono;
+    rp.all_mono = d->all_mono;
+    rp.sm_count = d->sm_count > 0 ? d->sm_count : 148;
+    if (!resident_decode_fits(rp)) return false;
+    if (d->use_resident == 1) return true;
+    // policy: the resident decode is instruction- / shared-memory-bound (~25 instructions per edge and iteration),
+    // the per-iteration kernels are HBM-bound (16 bytes per edge and iteration, 10 with RCQ codes); see DESIGN.md
+    return d->resident_default;
+}
+
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
 // Large batches can afford a look after every iteration (an iteration is milliseconds long); smaller ones
 // space the checkpoints out so that the syncs stay a small part of the decode.  `quiet` counts the
@@ -1236,6 +1281,24 @@ int job_start_on_device(DecodeJob& j, ldpc_decoder* d, ldpc_decoder::Ctx& cx, co
             return LDPC_OK;
         }
     }
+    {
+        ResidentLaunch rp{};
+        if (fill_resident(d, B, rp)) {
+            // messages of a frame fit one SM: one thread block per frame keeps them in shared memory for all T
+            // iterations (row-major LLRs in, results out; no workspace, no message traffic through HBM)
+            rp.llr_rows = static_cast<const float*>(llr);
+            rp.bits_rows = bits;
+            rp.packed_rows = packed;
+            rp.post_rows = static_cast<float*>(post);
+            rp.iters = iters;
+            rp.success = success;
+            d->prof.frames_padded = Bp;
+            j = DecodeJob();
+            LAUNCH(K_OTHER, launch_resident_decode(rp, stream));
+            d->stat_resident++;
+            return LDPC_OK;
+        }
+    }
     int rc = ws_ensure(d, cx.root, Bp);
     if (rc) return rc;
     d->prof.frames_padded = Bp;
@@ -1375,6 +1438,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
     if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp) != 0;
     if (const char* sm = getenv("LDPC_SMALL")) d->use_small = atoi(sm) != 0;
+    if (const char* rs = getenv("LDPC_RESIDENT")) d->use_resident = atoi(rs) != 0;
     if (const char* pm = getenv("LDPC_POST_MODE")) d->post_mode = std::min(2, std::max(0, atoi(pm)));
     if (const char* cm = getenv("LDPC_COMPACT_MIN_FRAMES")) d->compact_min_frames = std::max<int64_t>(atoll(cm), kFrameAlign);
 
@@ -1384,6 +1448,11 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
         return fail(LDPC_ERR_CUDA, "cannot select CUDA device %d", g->device);
     }
     int rc = LDPC_OK;
+    cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, g->device);
+    // measured (tools/resident_probe.py, r02k): the CTA-resident decode beats the HBM-bound per-iteration kernels only
+    // for unquantised float32 codes whose per-frame state is a few KB (many frames resident per SM): (3,6)-regular
+    // n = 504 26.2 M vs 22.0 M frames/s; RCQ on the same code 22.8 M vs 32.8 M, (16200,7200)-shaped 0.41 M vs 0.75 M
+    d->resident_default = cfg->bc == 0 && (size_t)E * sizeof(float) + (size_t)g->n <= (size_t)12 * 1024;
     if (cfg->n_beta > 0 && cfg->beta_index) {
         std::vector<int32_t> bidx((size_t)E);
         for (int64_t e = 0; e < E; ++e) bidx[(size_t)g->slot_of_edge[(size_t)e]] = cfg->beta_index[e];
@@ -1947,9 +2016,10 @@ extern "C" int ldpc_decoder_profile_read(ldpc_decoder* d, ldpc_profile* out, int
     d->prof.early_exits = d->stat_early_exits;
     d->prof.graph_replays = d->stat_graph_replays;
     d->prof.small_decodes = d->stat_small;
+    d->prof.resident_decodes = d->stat_resident;
     *out = d->prof;
     if (reset) {
-        d->stat_compactions = d->stat_early_exits = d->stat_graph_replays = d->stat_small = 0;
+        d->stat_compactions = d->stat_early_exits = d->stat_graph_replays = d->stat_small = d->stat_resident = 0;
         int64_t fp = d->prof.frames_padded;
         d->prof = ldpc_profile{};
         d->prof.frames_padded = fp;

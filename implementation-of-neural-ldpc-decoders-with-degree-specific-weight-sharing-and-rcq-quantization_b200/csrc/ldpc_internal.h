@@ -124,6 +124,42 @@ struct SmallLaunch {
 bool small_decode_fits(int dtype, const SmallLaunch& p);
 cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream);
 
+// CTA-resident decode (ldpc_resident.cu): one thread block per frame, messages in shared memory, row-major I/O.
+struct ResidentLaunch {
+    const float* llr_rows;      // [B][n]
+    uint8_t* bits_rows;         // [B][n] or nullptr
+    uint32_t* packed_rows;      // [B][ceil(n/32)] or nullptr
+    float* post_rows;           // [B][n] or nullptr
+    int32_t* iters;             // [B] or nullptr
+    uint8_t* success;           // [B] or nullptr
+    int64_t B;
+    int T, early_stop;
+    int n, E, n_checks, max_dv;
+    const WorkItem* cn_items;   // one check per item
+    const WorkItem* vn_items;   // one variable per item
+    const int32_t* slot_var;
+    const int32_t* vslots;
+    const int32_t* vpos_var;
+    const int32_t* bidx;
+    int beta_per_edge;
+    const float* beta;
+    int n_beta;
+    const int32_t* aidx;
+    const int32_t* aidx_slot;
+    const float* alpha;
+    int n_alpha;
+    int check_rule;
+    int bc, nth, n_quant;
+    const float* thr;
+    const float* lut;
+    const int32_t* q_of_iter;
+    const int32_t* mono;
+    int all_mono;
+    int sm_count;
+};
+bool resident_decode_fits(const ResidentLaunch& p);
+cudaError_t launch_resident_decode(const ResidentLaunch& p, cudaStream_t stream);
+
 // One iteration of the training backward pass (ldpc_train.cu); float32, normalised rule, frames in the [rows][Bp] layout.
 struct TrainBwd {
     int64_t B, Bp;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LDPC_B200_VERSION 103
+#define LDPC_B200_VERSION 104
 
 enum {
     LDPC_OK = 0,
@@ -231,6 +231,7 @@ typedef struct ldpc_profile {
     int64_t early_exits;      /* decodes that ended before T because every frame had stopped       */
     int64_t graph_replays;    /* launch-bound decodes replayed from a captured CUDA graph          */
     int64_t small_decodes;    /* decodes that ran as ONE on-chip launch (small codes, messages in shared memory) */
+    int64_t resident_decodes; /* decodes that ran CTA-resident (one thread block per frame, messages in shared memory) */
 } ldpc_profile;
 /* mode 0: count launches only (no overhead); mode 1: also bracket every kernel with CUDA events. */
 int ldpc_decoder_profile_mode(ldpc_decoder *d, int32_t mode);

@@ -20,8 +20,8 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert _lib.load().ldpc_version() == 103
-    assert ctypes.sizeof(_lib.DecoderConfig) == 88 and ctypes.sizeof(_lib.Profile) == 88
+    assert _lib.load().ldpc_version() == 104
+    assert ctypes.sizeof(_lib.DecoderConfig) == 88 and ctypes.sizeof(_lib.Profile) == 96
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device failure mode")
