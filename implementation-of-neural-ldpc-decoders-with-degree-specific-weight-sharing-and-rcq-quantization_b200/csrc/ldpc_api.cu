@@ -485,7 +485,8 @@ struct ldpc_decoder {
     int use_resident = -1;                 // LDPC_RESIDENT: 1 always / 0 never take the CTA-resident decode; -1 = policy
     int sm_count = 0;
     int64_t stat_resident = 0;
-    bool resident_default = false;         // what the policy says for this decoder (set at creation)
+    int64_t resident_max_frames = -1;      // LDPC_RESIDENT_MAX_FRAMES: batches up to this many frames decode CTA-resident (-1: one wave)
+    int64_t resident_wave_frames = -1;     // frames one wave of the resident kernel holds (occupancy query, first use)
     HostPipe pipe;
     int64_t host_chunk = 0;
     int layered_levels = 1;       // LDPC_LAYERED_LEVELS=0: always the sequential layered kernel
@@ -924,9 +925,17 @@ bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
     rp.sm_count = d->sm_count > 0 ? d->sm_count : 148;
     if (!resident_decode_fits(rp)) return false;
     if (d->use_resident == 1) return true;
-    // policy: the resident decode is instruction- / shared-memory-bound (~25 instructions per edge and iteration),
-    // the per-iteration kernels are HBM-bound (16 bytes per edge and iteration, 10 with RCQ codes); see DESIGN.md
-    return d->resident_default;
+    // policy (tools/resident_latency_probe.py, profiles/r02m_resident_latency.jsonl): the resident decode is
+    // instruction- / shared-memory-bound (~300 G edge-iterations/s) where the per-iteration kernels are HBM-bound (16
+    // bytes per edge and iteration: ~400 G edge-iterations/s), so large batches stay with those.  A batch of at most ONE
+    // WAVE (every frame has its own thread block; the call lasts as long as one frame) is latency-bound there -- one
+    // lane per frame, ~4 launches per iteration -- and goes resident: (16200,7200)-shaped 148 frames 360 vs 648 us,
+    // n = 504 1184 frames 77 vs 318 us.  A single frame of a LARGE code is the exception (343 vs 291 us: 47 edges per
+    // thread in sequence against fine-grained work items over the whole device), hence the 64-frame floor above 64 KB.
+    if (d->resident_wave_frames < 0) d->resident_wave_frames = resident_wave_frames(rp);
+    const int64_t max_frames = d->resident_max_frames >= 0 ? d->resident_max_frames : d->resident_wave_frames;
+    if (B > max_frames) return false;
+    return B >= 64 || (size_t)rp.E * sizeof(float) <= (size_t)64 * 1024 || d->resident_max_frames >= 0;
 }
 
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).
@@ -1449,10 +1458,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     }
     int rc = LDPC_OK;
     cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, g->device);
-    // measured (tools/resident_probe.py, r02k): the CTA-resident decode beats the HBM-bound per-iteration kernels only
-    // for unquantised float32 codes whose per-frame state is a few KB (many frames resident per SM): (3,6)-regular
-    // n = 504 26.2 M vs 22.0 M frames/s; RCQ on the same code 22.8 M vs 32.8 M, (16200,7200)-shaped 0.41 M vs 0.75 M
-    d->resident_default = cfg->bc == 0 && (size_t)E * sizeof(float) + (size_t)g->n <= (size_t)12 * 1024;
+    if (const char* rm = getenv("LDPC_RESIDENT_MAX_FRAMES")) d->resident_max_frames = atoll(rm);
     if (cfg->n_beta > 0 && cfg->beta_index) {
         std::vector<int32_t> bidx((size_t)E);
         for (int64_t e = 0; e < E; ++e) bidx[(size_t)g->slot_of_edge[(size_t)e]] = cfg->beta_index[e];
@@ -1640,7 +1646,10 @@ int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits,
     const int64_t n = g->n;
     const int64_t row_words = (n + 31) / 32;
     HostPipe& pp = d->pipe;
-    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : 8192;   // enough frames to fill the GPU
+    // enough frames to fill the GPU.  With posteriors the copy-out is as large as the copy-in and the link, busy in
+    // both directions, is what bounds the call: small chunks get the output flowing early and keep it flowing
+    // (65 536 frames of the (16200,7200)-shaped code, tools/e2e_trace.py: 116.2 ms with 8192-frame chunks, 104.1 with 2048)
+    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : (posterior ? 2048 : 8192);
     if (B <= chunk) chunk = B;
     if (!pp.s_in) {
         CU(cudaStreamCreateWithFlags(&pp.s_in, cudaStreamNonBlocking));

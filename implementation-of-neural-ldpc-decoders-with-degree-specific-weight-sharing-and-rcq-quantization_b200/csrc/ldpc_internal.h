@@ -159,6 +159,7 @@ struct ResidentLaunch {
 };
 bool resident_decode_fits(const ResidentLaunch& p);
 cudaError_t launch_resident_decode(const ResidentLaunch& p, cudaStream_t stream);
+int64_t resident_wave_frames(const ResidentLaunch& p);
 
 // One iteration of the training backward pass (ldpc_train.cu); float32, normalised rule, frames in the [rows][Bp] layout.
 struct TrainBwd {

@@ -248,20 +248,43 @@ int resident_threads(const ResidentLaunch& p) {
     return t;
 }
 
+// thread blocks of this kernel that one SM holds at a time (0: the launch is impossible)
 template <int KIND, int NTH>
-cudaError_t launch_resident_t(const ResidentLaunch& p, cudaStream_t stream) {
+cudaError_t resident_blocks_per_sm(const ResidentLaunch& p, int* per_sm) {
     const size_t smem = resident_smem_bytes(p);
-    const int threads = resident_threads(p);
     cudaError_t e = cudaFuncSetAttribute(resident_decode_kernel<KIND, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, resident_decode_kernel<KIND, NTH>, resident_threads(p), smem);
+}
+
+template <int KIND, int NTH>
+cudaError_t launch_resident_t(const ResidentLaunch& p, cudaStream_t stream) {
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_decode_kernel<KIND, NTH>, threads, smem);
+    cudaError_t e = resident_blocks_per_sm<KIND, NTH>(p, &per_sm);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     int64_t grid = (int64_t)per_sm * p.sm_count;
     if (grid > p.B) grid = p.B;
-    resident_decode_kernel<KIND, NTH><<<(unsigned)grid, threads, smem, stream>>>(p);
+    resident_decode_kernel<KIND, NTH><<<(unsigned)grid, resident_threads(p), resident_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();
+}
+
+// the kernel variant of a decoder
+#define LDPC_RESIDENT_DISPATCH(p, CALL)                                      \
+    do {                                                                     \
+        if ((p).check_rule == 1) return CALL(RES_OFFSET, 0);                 \
+        if ((p).bc) {                                                        \
+            if ((p).all_mono && (p).nth <= 4) return CALL(RES_QUANT, 4);     \
+            if ((p).all_mono && (p).nth <= 8) return CALL(RES_QUANT, 8);     \
+            return CALL(RES_QUANT, 0);                                       \
+        }                                                                    \
+        return CALL(RES_NORMALIZED, 0);                                      \
+    } while (0)
+
+cudaError_t resident_blocks_per_sm_any(const ResidentLaunch& p, int* per_sm) {
+#define LDPC_RES_CALL(K, N) resident_blocks_per_sm<K, N>(p, per_sm)
+    LDPC_RESIDENT_DISPATCH(p, LDPC_RES_CALL);
+#undef LDPC_RES_CALL
 }
 
 }  // namespace
@@ -272,13 +295,19 @@ bool resident_decode_fits(const ResidentLaunch& p) {
 }
 
 cudaError_t launch_resident_decode(const ResidentLaunch& p, cudaStream_t stream) {
-    if (p.check_rule == 1) return launch_resident_t<RES_OFFSET, 0>(p, stream);
-    if (p.bc) {
-        if (p.all_mono && p.nth <= 4) return launch_resident_t<RES_QUANT, 4>(p, stream);
-        if (p.all_mono && p.nth <= 8) return launch_resident_t<RES_QUANT, 8>(p, stream);
-        return launch_resident_t<RES_QUANT, 0>(p, stream);
+#define LDPC_RES_CALL(K, N) launch_resident_t<K, N>(p, stream)
+    LDPC_RESIDENT_DISPATCH(p, LDPC_RES_CALL);
+#undef LDPC_RES_CALL
+}
+
+// frames that decode at the same time: one thread block each, as many blocks as the device holds (0 on error)
+int64_t resident_wave_frames(const ResidentLaunch& p) {
+    int per_sm = 0;
+    if (resident_blocks_per_sm_any(p, &per_sm) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
-    return launch_resident_t<RES_NORMALIZED, 0>(p, stream);
+    return (int64_t)per_sm * p.sm_count;
 }
 
 }  // namespace ldpc

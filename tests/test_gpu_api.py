@@ -298,7 +298,8 @@ def test_launch_bound_decodes_replay_a_cuda_graph(built_lib, monkeypatch):
             d._alpha_table.uniform_(0.8, 1.0)
         return d
 
-    monkeypatch.setenv("LDPC_SMALL", "0")     # (this code would otherwise take the one-launch on-chip decode)
+    monkeypatch.setenv("LDPC_SMALL", "0")     # (this code would otherwise take the one-launch on-chip decode,
+    monkeypatch.setenv("LDPC_RESIDENT", "0")  #  batches of a few frames the CTA-resident one)
     monkeypatch.setenv("LDPC_GRAPHS", "0")
     plain = make()
     ref = [plain(llr), plain(llr[:5]), plain(llr[7])]
