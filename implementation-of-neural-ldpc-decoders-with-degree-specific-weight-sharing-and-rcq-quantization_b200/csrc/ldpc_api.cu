@@ -1646,10 +1646,12 @@ int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits,
     const int64_t n = g->n;
     const int64_t row_words = (n + 31) / 32;
     HostPipe& pp = d->pipe;
-    // enough frames to fill the GPU.  With posteriors the copy-out is as large as the copy-in and the link, busy in
-    // both directions, is what bounds the call: small chunks get the output flowing early and keep it flowing
-    // (65 536 frames of the (16200,7200)-shaped code, tools/e2e_trace.py: 116.2 ms with 8192-frame chunks, 104.1 with 2048)
-    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : (posterior ? 2048 : 8192);
+    // Two chunks decode at a time, so 2 x 4096 frames fill the GPU, and the smaller the chunk the shorter the ramp and
+    // the tail (65 536 frames of the (16200,7200)-shaped code, tools/e2e_trace.py: 98.3 ms with 8192-frame chunks, 94.2
+    // with 4096 or 2048).  With posteriors the copy-out is as large as the copy-in and the link, busy in both directions,
+    // is what bounds the call: small chunks get the output flowing early and keep it flowing (116.2 ms with 8192-frame
+    // chunks, 105.3 with 4096, 103.3 with 2048, 107.0 with 1024).
+    int64_t chunk = d->host_chunk > 0 ? d->host_chunk : (posterior ? 2048 : 4096);
     if (B <= chunk) chunk = B;
     if (!pp.s_in) {
         CU(cudaStreamCreateWithFlags(&pp.s_in, cudaStreamNonBlocking));
@@ -1804,7 +1806,7 @@ int decode_host_impl(ldpc_decoder* d, const void* llr, int64_t B, uint8_t* bits,
 extern "C" int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t* frames_out, int32_t max_chunks,
                                     int32_t* n_chunks) {
     if (B < 1 || !n_chunks || frames_per_lane < 1) return fail(LDPC_ERR_INVALID, "bad arguments");
-    const auto plan = plan_chunks(B, chunk > 0 ? chunk : 8192, frames_per_lane);
+    const auto plan = plan_chunks(B, chunk > 0 ? chunk : 4096, frames_per_lane);
     *n_chunks = (int32_t)plan.size();
     for (int32_t i = 0; i < (int32_t)plan.size() && i < max_chunks && frames_out; ++i) frames_out[i] = plan[(size_t)i].second;
     return LDPC_OK;

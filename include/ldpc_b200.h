@@ -159,7 +159,7 @@ int ldpc_decode_host_packed(ldpc_decoder *d, const void *llr, int64_t B, uint32_
                             int32_t *iterations, uint8_t *success);
 
 /* Test hook: the chunk plan ldpc_decode_host uses for a batch of B frames (frames per chunk, in order).
- * chunk <= 0 selects the default of calls without posteriors (8192; with posteriors the default is 2048); frames_per_lane is 4 for F32 decoders, 2 for F64. */
+ * chunk <= 0 selects the default of calls without posteriors (4096; with posteriors the default is 2048); frames_per_lane is 4 for F32 decoders, 2 for F64. */
 int ldpc_host_chunk_plan(int64_t B, int64_t chunk, int32_t frames_per_lane, int64_t *frames_out,
                          int32_t max_chunks, int32_t *n_chunks);
 

@@ -45,6 +45,15 @@ class Golden:
         return str(self["kind"])
 
 
+@pytest.fixture(autouse=True)
+def _per_iteration_kernels_by_default(request, monkeypatch):
+    """The parity suites use small codes and batches to exercise the per-iteration kernels, compaction, graph
+    replay ...; left to the policy, such batches (at most one wave of thread blocks) would decode CTA-resident
+    instead.  tests/test_gpu_resident.py covers that path and the policy itself and sets the variable on its own."""
+    if request.module.__name__.rsplit(".", 1)[-1] != "test_gpu_resident":
+        monkeypatch.setenv("LDPC_RESIDENT", "0")
+
+
 @pytest.fixture(scope="session")
 def built_lib():
     """The in-tree CUDA library (built on demand where nvcc exists; on the GPU box it is prebuilt)."""

@@ -140,3 +140,38 @@ def test_resident_equals_per_iteration_path_on_a_full_size_shape(built_lib, monk
             assert b is None
         else:
             assert torch.equal(a, b)
+
+
+def test_policy_takes_the_resident_decode_for_at_most_one_wave(built_lib, monkeypatch):
+    """Without LDPC_RESIDENT the library decides (ldpc_api.cu fill_resident): a batch of at most one wave of thread
+    blocks decodes CTA-resident, a larger one with the per-iteration kernels, a single frame of a code above 64 KB
+    too; results are the same either way."""
+    L = built_lib
+    monkeypatch.delenv("LDPC_RESIDENT", raising=False)
+    monkeypatch.delenv("LDPC_RESIDENT_MAX_FRAMES", raising=False)
+    T = 8
+    small = L.codes.dvbs2_shaped(max_iterations=T, scale=20)        # ~10 KB per frame: many blocks per SM
+    big = L.codes.dvbs2_shaped(max_iterations=T)                    # 194 KB per frame: one block per SM
+    for code, cases in ((small, ((1, 1), (300, 1), (60000, 0))), (big, ((1, 0), (100, 1), (400, 0)))):
+        dec = L.Neural2DMinSumDecoder(code, 2, T)
+        with torch.no_grad():
+            dec._beta_table.fill_(0.8)
+            dec._alpha_table.fill_(0.95)
+        eng = dec._engine(0)
+        for B, want in cases:
+            x = L.awgn_llr(code.n, B, 3.0, seed=B, llr_sign=1)
+            eng.profile_read(reset=True)
+            got = eng.decode_device(x, want_posterior=True)
+            assert eng.profile_read()["resident_decodes"] == want, (code.n, B)
+            monkeypatch.setenv("LDPC_RESIDENT", str(1 - want))
+            other = L.Neural2DMinSumDecoder(code, 2, T)
+            with torch.no_grad():
+                other._beta_table.fill_(0.8)
+                other._alpha_table.fill_(0.95)
+            e2 = other._engine(0)
+            ref = e2.decode_device(x, want_posterior=True)
+            assert e2.profile_read()["resident_decodes"] == 1 - want
+            monkeypatch.delenv("LDPC_RESIDENT")
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+            e2.close()

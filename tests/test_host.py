@@ -195,14 +195,14 @@ def test_host_pipeline_chunk_plan(built_lib):
 
     assert plan(65536, 8192) == [1024, 2048, 3072, 5120, 8192, 8192, 8192, 8192, 7168, 7168, 7168]
     assert plan(1, 8192) == [1] and plan(100, 8192) == [100] and plan(8192, 8192) == [8192]
-    assert plan(65536, 0) == plan(65536, 8192)                       # default chunk
+    assert plan(65536, 0) == plan(65536, 4096)                       # default chunk
     rng = np.random.default_rng(0)
     for _ in range(300):
         B = int(rng.integers(1, 300000))
         chunk = int(rng.choice([0, 100, 512, 1000, 4096, 8192, 16384]))
         V = int(rng.choice([2, 4]))
         p = plan(B, chunk, V)
-        lim = min(B, chunk if chunk > 0 else 8192)
+        lim = min(B, chunk if chunk > 0 else 4096)
         assert sum(p) == B and all(0 < c <= lim for c in p), (B, chunk, p)
         if B > 4 * lim and lim >= 1024:
             assert p[-1] >= lim // 2, (B, chunk, p)                   # no small un-overlapped tail
