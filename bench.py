@@ -632,6 +632,8 @@ def mc_sweep_leg(rig, L, args):
     sim = L.LDPSimulator(cfg)
     for snr in (0.5, 1.0, 1.5, 3.0):     # warm-up: the workspaces of every compaction pattern are allocated here
         sim.simulate_single_snr(dec, code, snr, per_gpu * rig.world, 10 ** 9)
+    for snr in (0.0, 1.0):               # ... and the short rounds of the adaptive schedule
+        sim.simulate_single_snr(dec, code, snr, cfg.max_frames, cfg.max_errors)
     rig.barrier()
     t0 = time.perf_counter()
     res = sim.simulate_decoder(dec, code, "N-2D-NMS Type 2")
@@ -641,6 +643,8 @@ def mc_sweep_leg(rig, L, args):
     leg = {"config": "C5", "workload": f"LDPSimulator.simulate_decoder, {DECODERS['n2d2']}, T = {T}, {SHAPES['dvbs2']}, "
                                        f"SNR 0..6 dB step 0.5 (13 points), all-zero codeword, converging sign convention, Philox AWGN on device",
            "max_frames_per_point": cfg.max_frames, "max_errors": cfg.max_errors, "batch_frames_per_gpu": per_gpu,
+           "rounds": "pilot round of 4 x max_errors frames, then rounds sized from the error rate so far (at most batch_frames "
+                     "per GPU); the reference's sequential stop rule is applied exactly, so the counters do not depend on it",
            "frames": frames, "seconds": dt, "frames_per_s": frames / dt, "info_gbps": frames / dt * code.k / 1e9,
            "snr_db": [float(s) for s in res.snr_values], "fer": res.frame_error_rates, "ber": res.bit_error_rates,
            "avg_iterations": res.average_iterations, "frames_per_point": res.total_frames,

@@ -50,6 +50,7 @@ class SimulationConfig:
     seed: int = 0
     reference_convention: bool = False  # True: bit 0 -> -1 like ldpc_decoder.py:289 (FER ~ 1)
     exact_stop: bool = True           # truncate the last round at the frame where max_errors is reached
+    adaptive_rounds: bool = True      # size the rounds from the error rate seen so far (needs exact_stop; same results)
 
 
 class SimulationResult:
@@ -93,6 +94,27 @@ def split_round(total: int, world: int, rank: int) -> Tuple[int, int]:
     return offset, count
 
 
+def next_round_frames(full: int, left: int, max_errors: int, total_frames: int, frame_errors: int,
+                      world: int = 1) -> int:
+    """Frames of the next Monte-Carlo round.  The reference stops at the frame that brings the error count to
+    ``max_errors`` (simulation_framework.py:110): with the exact stop rule a round larger than what is still needed
+    decodes frames whose results are thrown away -- at 0 dB every frame fails, 200 errors need 200 frames, and a
+    full round would decode tens of thousands at the maximum iteration count.  So: a pilot round of a few times
+    ``max_errors`` frames, then rounds sized from the error rate seen so far (30 % head-room), never above ``full``
+    (= ``batch_frames`` per GPU).  Depends only on the all-reduced counters, so every rank computes the same
+    schedule, and -- frames being keyed by their global index and the last round truncated in frame order -- the
+    reported numbers do not depend on it."""
+    if total_frames == 0:
+        want = max(4 * max_errors, 1024)
+    elif frame_errors == 0:
+        want = full
+    else:
+        want = int(1.3 * (max_errors - frame_errors) * total_frames / frame_errors) + 64
+    unit = 128 * world                       # whole warps of 4-frame lanes on every rank
+    want = (max(want, unit) + unit - 1) // unit * unit
+    return max(1, min(full, left, want))
+
+
 def truncate_in_frame_order(bit_errors: np.ndarray, iterations: np.ndarray, errors_before: int,
                             max_errors: int) -> Tuple[int, int, int, int]:
     """Sequential stop rule on one round given per-frame results in global frame order: keep frames
@@ -129,6 +151,9 @@ class LDPSimulator:
         frame_errors = bit_errors = total_iterations = total_frames = 0
         while total_frames < max_frames and frame_errors < max_errors:
             round_frames = min(per_gpu * world, max_frames - total_frames)
+            if cfg.adaptive_rounds and cfg.exact_stop:
+                round_frames = next_round_frames(per_gpu * world, max_frames - total_frames, max_errors,
+                                                 total_frames, frame_errors, world)
             off, cnt = split_round(round_frames, world, rank)
             round_counters.zero_()
             if cnt > 0:

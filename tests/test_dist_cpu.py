@@ -75,7 +75,8 @@ def _worker(rank, world, port, cases, out):
     dist.destroy_process_group()
 
 
-CASES = [(64, 10000, 25), (37, 500, 1000), (128, 1000, 3), (16, 50, 1)]
+# the last three are large enough for the adaptive round schedule (pilot round, rounds sized from the error rate)
+CASES = [(64, 10000, 25), (37, 500, 1000), (128, 1000, 3), (16, 50, 1), (4096, 30000, 400), (8192, 6000, 5), (2048, 9000, 10 ** 6)]
 
 
 def test_single_process_matches_sequential_rule():
@@ -100,3 +101,30 @@ def test_gloo_ranks_match_sequential_rule(world):
         assert p.exitcode == 0
     for (batch, max_frames, max_errors), got in zip(CASES, res):
         assert got == sequential_reference(max_frames, max_errors, _Code.n), (batch, max_frames, max_errors)
+
+
+def test_adaptive_rounds_decode_fewer_frames_for_the_same_answer():
+    """Round sizes follow the error rate seen so far (simulation_framework.next_round_frames); with the exact stop rule
+    the reported numbers cannot depend on them."""
+    Sim, Cfg = _make_sim()
+    from ldpc_b200.simulation_framework import next_round_frames
+    assert next_round_frames(32768, 10 ** 6, 200, 0, 0) == 1024                 # pilot: a few times max_errors
+    assert next_round_frames(32768, 10 ** 6, 1000, 0, 0) == 4096
+    assert next_round_frames(32768, 10 ** 6, 200, 1024, 0) == 32768             # nothing seen yet: a full round
+    assert next_round_frames(32768, 10 ** 6, 200, 1024, 1024) <= 128            # every frame fails: pilot was enough
+    assert next_round_frames(32768, 500, 200, 1024, 1) == 500                   # never beyond max_frames
+    assert next_round_frames(65536, 10 ** 6, 200, 2048, 10, world=2) % 256 == 0   # whole warps on every rank
+    decoded = {}
+    for adaptive in (False, True):
+        class Counting(Sim):
+            def _make_round_runner(self, *a):
+                run = super()._make_round_runner(*a)
+
+                def counted(count, *rest):
+                    decoded[adaptive] = decoded.get(adaptive, 0) + count
+                    run(count, *rest)
+                return counted
+        sim = Counting(Cfg(batch_frames=8192, save_results=False, adaptive_rounds=adaptive))
+        out = sim.simulate_single_snr(None, _Code, 2.0, 100000, 40)
+        assert (out[0], out[1], out[2], out[4], out[5]) == sequential_reference(100000, 40, _Code.n)
+    assert decoded[True] < decoded[False] // 4, decoded
