@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import argparse
 import csv
+import gc
 import glob
 import importlib
 import json
@@ -478,6 +479,8 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
 
     for _ in range(warmup):
         out = step()
+    gc.collect()                       # (buffers of an earlier leg freed inside the timed region would stall it)
+    torch.cuda.synchronize()
     rig.barrier()
     avg_iters = float(out[2].float().mean().item())
     on_chip = eng.profile_read(reset=True)["small_decodes"] > 0

@@ -20,7 +20,7 @@ import logging
 import os
 import time
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Tuple, Union
+from typing import Callable, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -95,7 +95,7 @@ def split_round(total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def next_round_frames(full: int, left: int, max_errors: int, total_frames: int, frame_errors: int,
-                      world: int = 1) -> int:
+                      world: int = 1, fer_hint: Optional[float] = None) -> int:
     """Frames of the next Monte-Carlo round.  The reference stops at the frame that brings the error count to
     ``max_errors`` (simulation_framework.py:110): with the exact stop rule a round larger than what is still needed
     decodes frames whose results are thrown away -- at 0 dB every frame fails, 200 errors need 200 frames, and a
@@ -103,8 +103,11 @@ def next_round_frames(full: int, left: int, max_errors: int, total_frames: int, 
     ``max_errors`` frames, then rounds sized from the error rate seen so far (30 % head-room), never above ``full``
     (= ``batch_frames`` per GPU).  Depends only on the all-reduced counters, so every rank computes the same
     schedule, and -- frames being keyed by their global index and the last round truncated in frame order -- the
-    reported numbers do not depend on it."""
-    if total_frames == 0:
+    reported numbers do not depend on it.  ``fer_hint``: the frame error rate of the same decoder at the previous
+    (lower) SNR point of a sweep, an upper bound in expectation, replaces the pilot round."""
+    if total_frames == 0 and fer_hint is not None:
+        want = full if fer_hint <= 0.0 else int(1.3 * max_errors / fer_hint) + 64
+    elif total_frames == 0:
         want = max(4 * max_errors, 1024)
     elif frame_errors == 0:
         want = full
@@ -133,6 +136,7 @@ class LDPSimulator:
     def __init__(self, config: SimulationConfig):
         self.config = config
         self.results: Dict[str, SimulationResult] = {}
+        self._fer_seen: Dict[int, Tuple[float, float, int]] = {}   # id(decoder) -> (snr_db, fer, max_errors) of its last point
         if config.save_results:
             os.makedirs(config.results_dir, exist_ok=True)
 
@@ -149,11 +153,14 @@ class LDPSimulator:
         fbe = torch.zeros(per_gpu, dtype=torch.int32, device=device)
         fit = torch.zeros(per_gpu, dtype=torch.int32, device=device)
         frame_errors = bit_errors = total_iterations = total_frames = 0
+        # sweeps go up in SNR: the error rate of the previous point bounds this one's (round sizing only)
+        prev = self._fer_seen.get(id(decoder))
+        hint = prev[1] if prev is not None and prev[0] <= snr_db and prev[2] == max_errors else None
         while total_frames < max_frames and frame_errors < max_errors:
             round_frames = min(per_gpu * world, max_frames - total_frames)
             if cfg.adaptive_rounds and cfg.exact_stop:
                 round_frames = next_round_frames(per_gpu * world, max_frames - total_frames, max_errors,
-                                                 total_frames, frame_errors, world)
+                                                 total_frames, frame_errors, world, hint)
             off, cnt = split_round(round_frames, world, rank)
             round_counters.zero_()
             if cnt > 0:
@@ -169,6 +176,7 @@ class LDPSimulator:
             total_iterations += it
             total_frames += nf
         fer = frame_errors / total_frames if total_frames > 0 else 0.0
+        self._fer_seen[id(decoder)] = (snr_db, fer, max_errors)
         ber = bit_errors / (total_frames * code.n) if total_frames > 0 else 0.0
         avg_iterations = total_iterations / total_frames if total_frames > 0 else 0.0
         return fer, ber, avg_iterations, time.time() - start, total_frames, frame_errors

@@ -114,6 +114,9 @@ def test_adaptive_rounds_decode_fewer_frames_for_the_same_answer():
     assert next_round_frames(32768, 10 ** 6, 200, 1024, 1024) <= 128            # every frame fails: pilot was enough
     assert next_round_frames(32768, 500, 200, 1024, 1) == 500                   # never beyond max_frames
     assert next_round_frames(65536, 10 ** 6, 200, 2048, 10, world=2) % 256 == 0   # whole warps on every rank
+    assert next_round_frames(32768, 10 ** 6, 200, 0, 0, fer_hint=1.0) == 384     # previous SNR point: every frame failed
+    assert next_round_frames(32768, 10 ** 6, 200, 0, 0, fer_hint=1e-4) == 32768
+    assert next_round_frames(32768, 10 ** 6, 200, 0, 0, fer_hint=0.0) == 32768
     decoded = {}
     for adaptive in (False, True):
         class Counting(Sim):
@@ -125,6 +128,7 @@ def test_adaptive_rounds_decode_fewer_frames_for_the_same_answer():
                     run(count, *rest)
                 return counted
         sim = Counting(Cfg(batch_frames=8192, save_results=False, adaptive_rounds=adaptive))
-        out = sim.simulate_single_snr(None, _Code, 2.0, 100000, 40)
-        assert (out[0], out[1], out[2], out[4], out[5]) == sequential_reference(100000, 40, _Code.n)
+        for snr in (2.0, 2.5):      # the second point starts from the first one's error rate instead of a pilot
+            out = sim.simulate_single_snr(None, _Code, snr, 100000, 40)
+            assert (out[0], out[1], out[2], out[4], out[5]) == sequential_reference(100000, 40, _Code.n)
     assert decoded[True] < decoded[False] // 4, decoded
