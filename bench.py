@@ -461,11 +461,16 @@ def kernel_roofline(prof, ab, Bp, steps, T, step_ms, kind, code_name):
     }
 
 
-def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampler=None):
+def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampler=None, min_timed_ms=0.0):
     """One device-resident leg: LLRs generated on the device (Philox, distinct frames per rank, reference sign
-    convention at SNR_DB), resident before timing; returns the result record and the pieces the caller reuses."""
+    convention at SNR_DB), resident before timing; returns the result record and the pieces the caller reuses.
+    `min_timed_ms` (configuration legs only; the headline times exactly `steps`): a leg whose step is a few
+    milliseconds gets enough steps that the timed region is at least this long -- measured over 10 ms, the idle gap of
+    the barrier in front of it (clocks ramping back up) dominated the (7,4) leg: 1.9 ms per step on one run, 4.8 on
+    the next, 32 with eight ranks."""
     torch = rig.torch
     g = code.graph
+    gc.collect()                       # (buffers of an earlier leg freed inside the timed region would stall it)
     dec = build_decoder(L, code, kind)
     eng = dec._engine(rig.local_rank)
     eng.reserve(B)
@@ -479,8 +484,16 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
 
     for _ in range(warmup):
         out = step()
-    gc.collect()                       # (buffers of an earlier leg freed inside the timed region would stall it)
-    torch.cuda.synchronize()
+    if min_timed_ms > 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        est = rig.max_over_ranks(e0.elapsed_time(e1))
+        steps = max(steps, min(500, int(np.ceil(min_timed_ms / max(est, 1e-3)))))
+        for _ in range(min(steps, 100) if est < 10.0 else 0):    # keep the device busy up to the timed region
+            out = step()
     rig.barrier()
     avg_iters = float(out[2].float().mean().item())
     on_chip = eng.profile_read(reset=True)["small_decodes"] > 0
@@ -495,7 +508,7 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     fps = rig.world * B * steps / (ms * steps / 1e3)
     ab = algorithmic_bytes(code, kind, posterior)
     roof = kernel_roofline(prof, ab, prof["frames_padded"], steps, T_ITERS, ms, kind, code_name)
-    rec = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "avg_iterations": avg_iters,
+    rec = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "avg_iterations": avg_iters, "steps": steps,
            "edge_msgs_per_s": fps * T_ITERS * 2 * g.E, "launches": int(prof["launches"]), "roofline": roof}
     return rec, dec, eng, llr, out, clocks
 
@@ -593,10 +606,10 @@ def config_legs(rig, L, args):
 
     def kernel_leg(tag, code_name, kind, B, posterior):
         code = make_code(L, code_name)
-        rec, dec, eng, llr, out, _ = device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior)
+        rec, dec, eng, llr, out, _ = device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, min_timed_ms=250.0)
         r = rec["roofline"]
         leg = {"config": tag, "workload": workload_name(kind, code_name), "frames_per_gpu": B,
-               "call": "forward()" if posterior else "decode()", "steps": steps, "warmup": warmup,
+               "call": "forward()" if posterior else "decode()", "steps": rec["steps"], "warmup": warmup,
                "frames_per_s": rec["frames_per_s"], "info_gbps": rec["info_gbps"], "ms_per_step": rec["ms_per_step"],
                "avg_iterations": rec["avg_iterations"],
                "roofline": {"cn_frac": r["cn_kernel"]["frac"], "vn_frac": r["vn_kernel"]["frac"],

@@ -97,6 +97,18 @@ struct ldpc_graph {
     // check has more than kLayerMaxDeg edges
     std::vector<LayerRec> lay_recs;
     LayerRec* d_lay_recs = nullptr;
+    // CTA-resident decode (ldpc_resident.cu): degree classes and 16-bit index tables in the kernel's own slot order
+    // ("physical" slots: edge k of check c of a class of `count` checks at first_slot + k * count + c, so that the
+    // lanes of a warp -- consecutive checks -- touch consecutive shared-memory words).  Built when E, n < 65536.
+    struct Resident {
+        bool ok = false;
+        int n_cclass = 0, n_vclass = 0;
+        std::vector<int32_t> phys;           // [E] slot -> physical slot
+        WorkItem* d_classes = nullptr;       // check classes, then variable classes
+        uint16_t* d_slot_var = nullptr;      // [E] physical slot -> variable
+        uint16_t* d_vslots = nullptr;        // per variable class: entry d of its i-th variable at first_slot + d * count + i
+        uint16_t* d_vpos_var = nullptr;      // [n] position -> variable
+    } res;
     // device copies
     int64_t* d_chk_ptr = nullptr;
     int32_t* d_chk_var = nullptr;
@@ -326,6 +338,44 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             if (L.wide_end < L.wide_begin) L.wide_begin = L.wide_end;   // no degree in 9..64
         }
     }
+    // ---- tables of the CTA-resident decode ----
+    std::vector<WorkItem> res_classes;
+    std::vector<uint16_t> res_slot_var, res_vslots, res_vpos_var;
+    if (E > 0 && E < 65536 && n < 65536) {
+        auto classes_of = [](const std::vector<WorkItem>& fine) {
+            std::vector<WorkItem> cls;
+            for (const WorkItem& it : fine) {
+                if (!cls.empty() && cls.back().deg == it.deg) cls.back().count++;
+                else cls.push_back(it);   // count == 1, first_node / first_slot of the class's first node
+            }
+            return cls;
+        };
+        const std::vector<WorkItem> cc = classes_of(g->cn[1].items), vc = classes_of(g->vn[1].items);
+        if ((int)cc.size() <= kResMaxClasses && (int)vc.size() <= kResMaxClasses) {
+            ldpc_graph::Resident& r = g->res;
+            r.ok = true;
+            r.n_cclass = (int)cc.size();
+            r.n_vclass = (int)vc.size();
+            r.phys.assign((size_t)E, 0);
+            res_slot_var.assign((size_t)E, 0);
+            for (const WorkItem& cl : cc)
+                for (int c = 0; c < cl.count; ++c)
+                    for (int k = 0; k < cl.deg; ++k) {
+                        const int32_t slot = cl.first_slot + c * cl.deg + k, ph = cl.first_slot + k * cl.count + c;
+                        r.phys[(size_t)slot] = ph;
+                        res_slot_var[(size_t)ph] = (uint16_t)g->slot_var[(size_t)slot];
+                    }
+            res_vslots.assign((size_t)E, 0);
+            for (const WorkItem& cl : vc)
+                for (int i = 0; i < cl.count; ++i)
+                    for (int dd = 0; dd < cl.deg; ++dd)
+                        res_vslots[(size_t)(cl.first_slot + dd * cl.count + i)] =
+                            (uint16_t)r.phys[(size_t)g->vslots[(size_t)(cl.first_slot + i * cl.deg + dd)]];
+            res_vpos_var.assign(g->vpos_var.begin(), g->vpos_var.end());
+            res_classes = cc;
+            res_classes.insert(res_classes.end(), vc.begin(), vc.end());
+        }
+    }
     // ---- upload ----
     DeviceGuard guard(device);
     if (!guard.ok) {
@@ -343,6 +393,12 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
     if (!rc) rc = upload(&g->d_chk_var, g->chk_var);
     if (!rc) rc = upload(&g->d_level_chk, g->level_chk);
     if (!rc) rc = upload(&g->d_lay_recs, g->lay_recs);
+    if (!rc && g->res.ok) {
+        rc = upload(&g->res.d_classes, res_classes);
+        if (!rc) rc = upload(&g->res.d_slot_var, res_slot_var);
+        if (!rc) rc = upload(&g->res.d_vslots, res_vslots);
+        if (!rc) rc = upload(&g->res.d_vpos_var, res_vpos_var);
+    }
     if (rc) {
         ldpc_graph_destroy(g);
         return rc;
@@ -365,6 +421,10 @@ extern "C" int ldpc_graph_destroy(ldpc_graph* g) {
     cudaFree(g->d_chk_var);
     cudaFree(g->d_level_chk);
     cudaFree(g->d_lay_recs);
+    cudaFree(g->res.d_classes);
+    cudaFree(g->res.d_slot_var);
+    cudaFree(g->res.d_vslots);
+    cudaFree(g->res.d_vpos_var);
     delete g;
     return LDPC_OK;
 }
@@ -471,6 +531,8 @@ struct ldpc_decoder {
     int beta_per_edge = 0;                 // some check mixes beta columns
     int32_t* d_aidx = nullptr;             // per vpos
     int32_t* d_aidx_slot = nullptr;        // per slot (offset rule: alpha is applied at the check node)
+    int32_t* d_res_bidx = nullptr;         // d_bidx / d_aidx_slot in the slot order of the CTA-resident decode
+    int32_t* d_res_aidx_slot = nullptr;
     int check_rule = 0, schedule = 0;
     int wide_ring = 1;                     // checks of degree 9..64 through the bulk-async row ring
     void* d_beta = nullptr;                // [T][n_beta]
@@ -892,25 +954,25 @@ bool fill_small(ldpc_decoder* d, Workspace* ws, int64_t B, int64_t Bp, bool want
 // CTA-resident decode (ldpc_resident.cu), if a frame's messages fit one SM's shared memory.
 bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
     const ldpc_graph* g = d->g;
-    if (d->use_resident == 0 || d->dtype != LDPC_F32 || d->schedule != LDPC_SCHEDULE_FLOODING) return false;
+    if (d->use_resident == 0 || d->dtype != LDPC_F32 || d->schedule != LDPC_SCHEDULE_FLOODING || !g->res.ok) return false;
     rp.B = B;
     rp.T = d->T;
     rp.early_stop = d->early_stop;
     rp.n = g->n;
     rp.E = (int)g->E;
-    rp.n_checks = (int)g->cn[1].items.size();
     rp.max_dv = g->max_dv;
-    rp.cn_items = g->cn[1].d;
-    rp.vn_items = g->vn[1].d;
-    rp.slot_var = g->d_slot_var;
-    rp.vslots = g->d_vslots;
-    rp.vpos_var = g->d_vpos_var;
-    rp.bidx = d->d_bidx;
+    rp.n_cclass = g->res.n_cclass;
+    rp.n_vclass = g->res.n_vclass;
+    rp.classes = g->res.d_classes;
+    rp.slot_var = g->res.d_slot_var;
+    rp.vslots = g->res.d_vslots;
+    rp.vpos_var = g->res.d_vpos_var;
+    rp.bidx = d->d_res_bidx;
     rp.beta_per_edge = d->beta_per_edge;
     rp.beta = static_cast<const float*>(d->d_beta);
     rp.n_beta = d->n_beta;
     rp.aidx = d->d_aidx;
-    rp.aidx_slot = d->d_aidx_slot;
+    rp.aidx_slot = d->d_res_aidx_slot;
     rp.alpha = static_cast<const float*>(d->d_alpha);
     rp.n_alpha = d->n_alpha;
     rp.check_rule = d->check_rule;
@@ -1470,6 +1532,11 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
                         break;
                     }
         rc = upload(&d->d_bidx, bidx);
+        if (!rc && g->res.ok) {   // the same columns in the slot order of the CTA-resident decode
+            std::vector<int32_t> rb((size_t)E);
+            for (int64_t sl = 0; sl < E; ++sl) rb[(size_t)g->res.phys[(size_t)sl]] = bidx[(size_t)sl];
+            rc = upload(&d->d_res_bidx, rb);
+        }
     }
     if (!rc && cfg->n_alpha > 0 && cfg->alpha_index) {
         std::vector<int32_t> aidx((size_t)g->n);
@@ -1479,6 +1546,11 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
             std::vector<int32_t> as((size_t)E);
             for (int64_t sl = 0; sl < E; ++sl) as[(size_t)sl] = cfg->alpha_index[g->slot_var[(size_t)sl]];
             rc = upload(&d->d_aidx_slot, as);
+            if (!rc && g->res.ok) {
+                std::vector<int32_t> ra((size_t)E);
+                for (int64_t sl = 0; sl < E; ++sl) ra[(size_t)g->res.phys[(size_t)sl]] = as[(size_t)sl];
+                rc = upload(&d->d_res_aidx_slot, ra);
+            }
         }
     }
     if (!rc && cfg->n_beta > 0) {
@@ -1580,6 +1652,8 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     cudaFree(d->d_bidx);
     cudaFree(d->d_aidx);
     cudaFree(d->d_aidx_slot);
+    cudaFree(d->d_res_bidx);
+    cudaFree(d->d_res_aidx_slot);
     cudaFree(d->d_beta);
     cudaFree(d->d_alpha);
     cudaFree(d->d_thr);

@@ -125,6 +125,8 @@ bool small_decode_fits(int dtype, const SmallLaunch& p);
 cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream);
 
 // CTA-resident decode (ldpc_resident.cu): one thread block per frame, messages in shared memory, row-major I/O.
+// Index tables in the kernel's own ("physical") slot order -- see ldpc_graph::Resident in ldpc_api.cu.
+constexpr int kResMaxClasses = 24;   // degree classes per side
 struct ResidentLaunch {
     const float* llr_rows;      // [B][n]
     uint8_t* bits_rows;         // [B][n] or nullptr
@@ -134,18 +136,19 @@ struct ResidentLaunch {
     uint8_t* success;           // [B] or nullptr
     int64_t B;
     int T, early_stop;
-    int n, E, n_checks, max_dv;
-    const WorkItem* cn_items;   // one check per item
-    const WorkItem* vn_items;   // one variable per item
-    const int32_t* slot_var;
-    const int32_t* vslots;
-    const int32_t* vpos_var;
-    const int32_t* bidx;
+    int n, E, max_dv;
+    int n_cclass, n_vclass;
+    const WorkItem* classes;    // [n_cclass] check classes (first_slot: first physical slot), then [n_vclass] variable
+                                // classes (first_node: first position, first_slot: offset of the class's lists in vslots)
+    const uint16_t* slot_var;   // [E] physical slot -> variable
+    const uint16_t* vslots;     // [E] entry d of the i-th variable of a class at first_slot + d * count + i: a physical slot
+    const uint16_t* vpos_var;   // [n] position -> variable
+    const int32_t* bidx;        // [E] beta column per physical slot, or nullptr
     int beta_per_edge;
     const float* beta;
     int n_beta;
-    const int32_t* aidx;
-    const int32_t* aidx_slot;
+    const int32_t* aidx;        // [n] alpha column per position, or nullptr
+    const int32_t* aidx_slot;   // [E] alpha column per physical slot (offset rule), or nullptr
     const float* alpha;
     int n_alpha;
     int check_rule;
