@@ -547,7 +547,7 @@ struct ldpc_decoder {
     int use_resident = -1;                 // LDPC_RESIDENT: 1 always / 0 never take the CTA-resident decode; -1 = policy
     int sm_count = 0;
     int64_t stat_resident = 0;
-    int64_t resident_max_frames = -1;      // LDPC_RESIDENT_MAX_FRAMES: batches up to this many frames decode CTA-resident (-1: one wave)
+    int64_t resident_max_frames = -1;      // LDPC_RESIDENT_MAX_FRAMES: batches up to this many frames decode CTA-resident (-1: a few waves)
     int64_t resident_wave_frames = -1;     // frames one wave of the resident kernel holds (occupancy query, first use)
     HostPipe pipe;
     int64_t host_chunk = 0;
@@ -987,17 +987,17 @@ bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
     rp.sm_count = d->sm_count > 0 ? d->sm_count : 148;
     if (!resident_decode_fits(rp)) return false;
     if (d->use_resident == 1) return true;
-    // policy (tools/resident_latency_probe.py, profiles/r02m_resident_latency.jsonl): the resident decode is
-    // instruction- / shared-memory-bound (~300 G edge-iterations/s) where the per-iteration kernels are HBM-bound (16
-    // bytes per edge and iteration: ~400 G edge-iterations/s), so large batches stay with those.  A batch of at most ONE
-    // WAVE (every frame has its own thread block; the call lasts as long as one frame) is latency-bound there -- one
-    // lane per frame, ~4 launches per iteration -- and goes resident: (16200,7200)-shaped 148 frames 360 vs 648 us,
-    // n = 504 1184 frames 77 vs 318 us.  A single frame of a LARGE code is the exception (343 vs 291 us: 47 edges per
-    // thread in sequence against fine-grained work items over the whole device), hence the 64-frame floor above 64 KB.
+    // policy (tools/resident_latency_probe.py, profiles/r02t_resident_latency.jsonl): the resident decode is issue-bound
+    // (~400 G edge-iterations/s with every SM busy) where the per-iteration kernels are HBM-bound (16 bytes per edge and
+    // iteration: ~400 G edge-iterations/s as well, 650 G with RCQ codes) -- but those need lanes-over-frames batches of
+    // thousands of frames to fill the machine and ~4 launches per iteration, so a batch of a few WAVES (one thread block
+    // per frame, as many blocks as the device holds) is faster resident: (16200,7200)-shaped 1 / 148 / 592 frames
+    // 237 / 239 / 937 us against 295 / 652 / 1239 us, QC shape 148 frames 176 against 1044 us, n = 504 1184 frames 58
+    // against 323 us; break-even at 4-8 waves with one block per SM, ~2 waves where an SM holds many small frames.
     if (d->resident_wave_frames < 0) d->resident_wave_frames = resident_wave_frames(rp);
-    const int64_t max_frames = d->resident_max_frames >= 0 ? d->resident_max_frames : d->resident_wave_frames;
-    if (B > max_frames) return false;
-    return B >= 64 || (size_t)rp.E * sizeof(float) <= (size_t)64 * 1024 || d->resident_max_frames >= 0;
+    const int64_t waves = d->resident_wave_frames <= rp.sm_count ? 4 : 2;
+    const int64_t max_frames = d->resident_max_frames >= 0 ? d->resident_max_frames : waves * d->resident_wave_frames;
+    return B <= max_frames;
 }
 
 // Iterations after which the number of running frames is read back (one 4-byte copy + stream sync each).

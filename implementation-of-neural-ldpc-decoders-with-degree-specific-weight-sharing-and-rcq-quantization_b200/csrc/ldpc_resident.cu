@@ -18,7 +18,9 @@
 // so the lanes of a warp -- consecutive checks -- read and write consecutive shared-memory words (no bank conflicts
 // on the check side) and consecutive entries of every index table (coalesced 16-bit loads: E and n are below 65 536
 // for anything that fits an SM).  The variable side gathers through its slot lists, stored transposed the same way.
-// Low-degree classes take two nodes per thread at a time so that the index loads of both are in flight together.
+// A thread's nodes of a class are visited in a software-pipelined loop: the index-table entries (and the LLR / weight
+// they lead to) of the thread's NEXT node are requested before its current node is worked on, so the L2 round trips
+// of the tables -- 194 KB of messages leave no room for them in an SM -- overlap the shared-memory work.
 //
 // Same arithmetic contract as the per-iteration kernels (helpers shared through ldpc_cn_common.cuh / ldpc_device.cuh):
 // first-argmin / min2 rule, fl(beta*raw) with the sign product as an XOR of sign bits, float32 threshold compares and
@@ -35,14 +37,11 @@ namespace {
 
 enum { RES_NORMALIZED = 0, RES_QUANT = 1, RES_OFFSET = 2 };
 constexpr int kResMaxDv = 64;
-// nodes of degree <= these take two nodes per thread at a time (tuning macros).  Off: at 1024 threads a thread has 64
-// registers and the paired variants spill ((16200,7200)-shaped, 148 frames: 273 us unpaired, 288 us with pairs for
-// variable degrees <= 3, 326 us with pairs up to degree 4 on both sides).
-#ifndef LDPC_RES_CN_U2_MAX
-#define LDPC_RES_CN_U2_MAX 0
-#endif
-#ifndef LDPC_RES_VN_U2_MAX
-#define LDPC_RES_VN_U2_MAX -1
+// variable degrees up to this run the software-pipelined loop (tuning macro): with 1024 threads a thread has 64
+// registers, and the pipeline registers of higher degrees spill ((16200,7200)-shaped, 148 frames: 235 us with 2,
+// 241 us with 3, 245 us with 4; unpipelined 273 us)
+#ifndef LDPC_RES_PIPE_MAX_DV
+#define LDPC_RES_PIPE_MAX_DV 2
 #endif
 
 template <int N>
@@ -89,160 +88,197 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
             }
             const bool last = t == p.T - 1;
 
-            // ---- check nodes of one degree class.  DC > 0: inputs in registers, U checks per thread at a time;
-            //      DC == 0: run-time degree, inputs read again for the output phase ----
-            auto cn_class = [&](auto dc_tag, auto u_tag, const WorkItem cl) {
+            // ---- check nodes of one degree class.  DC > 0: inputs in registers; DC == 0: run-time degree, inputs read
+            //      again for the output phase.  The beta of the thread's next check is fetched while this one is worked on
+            //      (column index two checks ahead, value one ahead). ----
+            auto cn_class = [&](auto dc_tag, const WorkItem cl) {
                 constexpr int DC = decltype(dc_tag)::value;
-                constexpr int U = decltype(u_tag)::value;
                 constexpr int X = DC > 0 ? DC : 1;
                 const int D = DC > 0 ? DC : cl.deg;
                 const int m = cl.count;
-                for (int c0 = tid; c0 < m; c0 += nthr * U) {
-                    float x[U][X];
-                    float betac[U];
-                    bool live[U];
+                const bool one_beta = has_beta && !p.beta_per_edge;
+                const int32_t* __restrict__ bx = (one_beta && p.bidx) ? p.bidx + cl.first_slot : nullptr;   // column of edge 0
+                float beta = 1.f, beta_next = 1.f;
+                int col_next = 0;
+                if (one_beta) {
+                    if (!bx) {
+                        beta = beta_next = __ldg(beta_t);
+                    } else {
+                        if (tid < m) beta = __ldg(beta_t + __ldg(bx + tid));
+                        if (tid + nthr < m) col_next = __ldg(bx + tid + nthr);
+                    }
+                }
+                for (int c = tid; c < m; c += nthr) {
+                    int col_next2 = 0;
+                    if (bx) {
+                        if (c + nthr < m) beta_next = __ldg(beta_t + col_next);
+                        if (c + 2 * nthr < m) col_next2 = __ldg(bx + c + 2 * nthr);
+                    }
+                    float* const io = msg + cl.first_slot + c;        // edge k at io[k * m]
+                    const int s0 = cl.first_slot + c;                 // physical slot of edge k: s0 + k * m
+                    float x[X];
+                    if constexpr (DC > 0) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int c = c0 + u * nthr;
-                        live[u] = c < m;
-                        betac[u] = 1.f;
-                        if (live[u]) {
-                            if constexpr (DC > 0) {
+                        for (int k = 0; k < DC; ++k) x[k] = io[k * m];
+                    }
+                    auto input = [&](int k) -> float {
+                        if constexpr (DC > 0) return x[k];
+                        else return io[k * m];
+                    };
+                    MinState<float, false> st;
+                    st.init();
 #pragma unroll
-                                for (int k = 0; k < DC; ++k) x[u][k] = msg[cl.first_slot + k * m + c];
-                            }
-                            if (has_beta && !p.beta_per_edge)
-                                betac[u] = __ldg(beta_t + (p.bidx ? __ldg(p.bidx + cl.first_slot + c) : 0));
+                    for (int k = 0; k < D; ++k) st.push(input(k), k);
+                    if (D == 1) st.m2 = st.m1;   // ldpc_decoder.py:112-113
+                    if constexpr (KIND == RES_OFFSET) {
+                        const float beta_check = one_beta ? beta : 0.f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float xk = input(k);
+                            const bool is_min = fabsf(xk) == st.m1;
+                            const bool zero_others = D > 1 && (st.m2 == 0.f || (st.m1 == 0.f && !is_min));
+                            const float b = (has_beta && p.beta_per_edge) ? __ldg(beta_t + __ldg(p.bidx + s0 + k * m)) : beta_check;
+                            const float alpha = alpha_t ? __ldg(alpha_t + (p.aidx_slot ? __ldg(p.aidx_slot + s0 + k * m) : 0)) : 0.f;
+                            io[k * m] = offset_value<float>(is_min ? st.m2 : st.m1, b, has_beta, alpha, alpha_t != nullptr,
+                                                            st.par ^ __float_as_uint(xk), zero_others);
+                        }
+                    } else if (!p.beta_per_edge) {
+                        CheckOut<float, QUANT> co;
+                        co.prepare(st.m1, st.m2, st.par, beta, has_beta, qz, p.bc);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float xk = input(k);
+                            const auto o = co.emit(fabsf(xk) == st.m1, __float_as_uint(xk));
+                            if constexpr (QUANT) io[k * m] = lutq[o];
+                            else io[k * m] = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float xk = input(k);
+                            const float raw = (fabsf(xk) == st.m1) ? st.m2 : st.m1;
+                            const auto o = cn_emit<float, QUANT, NTH>(raw, __ldg(beta_t + __ldg(p.bidx + s0 + k * m)),
+                                                                      st.par ^ __float_as_uint(xk), qz, p.bc);
+                            if constexpr (QUANT) io[k * m] = lutq[o];
+                            else io[k * m] = o;
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (!live[u]) continue;
-                        const int c = c0 + u * nthr;
-                        float* const io = msg + cl.first_slot + c;        // edge k at io[k * m]
-                        const int s0 = cl.first_slot + c;                 // physical slot of edge k: s0 + k * m
-                        auto input = [&](int k) -> float {
-                            if constexpr (DC > 0) return x[u][k];
-                            else return io[k * m];
-                        };
-                        MinState<float, false> st;
-                        st.init();
-#pragma unroll
-                        for (int k = 0; k < D; ++k) st.push(input(k), k);
-                        if (D == 1) st.m2 = st.m1;   // ldpc_decoder.py:112-113
-                        if constexpr (KIND == RES_OFFSET) {
-                            const float beta_check = (has_beta && !p.beta_per_edge) ? betac[u] : 0.f;
-#pragma unroll
-                            for (int k = 0; k < D; ++k) {
-                                const float xk = input(k);
-                                const bool is_min = fabsf(xk) == st.m1;
-                                const bool zero_others = D > 1 && (st.m2 == 0.f || (st.m1 == 0.f && !is_min));
-                                const float beta = (has_beta && p.beta_per_edge) ? __ldg(beta_t + __ldg(p.bidx + s0 + k * m)) : beta_check;
-                                const float alpha = alpha_t ? __ldg(alpha_t + (p.aidx_slot ? __ldg(p.aidx_slot + s0 + k * m) : 0)) : 0.f;
-                                io[k * m] = offset_value<float>(is_min ? st.m2 : st.m1, beta, has_beta, alpha, alpha_t != nullptr,
-                                                                st.par ^ __float_as_uint(xk), zero_others);
-                            }
-                        } else if (!p.beta_per_edge) {
-                            CheckOut<float, QUANT> co;
-                            co.prepare(st.m1, st.m2, st.par, betac[u], has_beta, qz, p.bc);
-#pragma unroll
-                            for (int k = 0; k < D; ++k) {
-                                const float xk = input(k);
-                                const auto o = co.emit(fabsf(xk) == st.m1, __float_as_uint(xk));
-                                if constexpr (QUANT) io[k * m] = lutq[o];
-                                else io[k * m] = o;
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < D; ++k) {
-                                const float xk = input(k);
-                                const float raw = (fabsf(xk) == st.m1) ? st.m2 : st.m1;
-                                const auto o = cn_emit<float, QUANT, NTH>(raw, __ldg(beta_t + __ldg(p.bidx + s0 + k * m)),
-                                                                          st.par ^ __float_as_uint(xk), qz, p.bc);
-                                if constexpr (QUANT) io[k * m] = lutq[o];
-                                else io[k * m] = o;
-                            }
-                        }
-                    }
+                    beta = beta_next;
+                    col_next = col_next2;
                 }
             };
             for (int ci = 0; ci < ncc; ++ci) {
                 const WorkItem cl = s_cls[ci];
                 switch (cl.deg) {   // block-uniform
-                    case 1: cn_class(IntC<1>{}, IntC<(1 <= LDPC_RES_CN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 2: cn_class(IntC<2>{}, IntC<(2 <= LDPC_RES_CN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 3: cn_class(IntC<3>{}, IntC<(3 <= LDPC_RES_CN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 4: cn_class(IntC<4>{}, IntC<(4 <= LDPC_RES_CN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 5: cn_class(IntC<5>{}, IntC<1>{}, cl); break;
-                    case 6: cn_class(IntC<6>{}, IntC<1>{}, cl); break;
-                    case 7: cn_class(IntC<7>{}, IntC<1>{}, cl); break;
-                    case 8: cn_class(IntC<8>{}, IntC<1>{}, cl); break;
-                    default: cn_class(IntC<0>{}, IntC<1>{}, cl); break;
+                    case 1: cn_class(IntC<1>{}, cl); break;
+                    case 2: cn_class(IntC<2>{}, cl); break;
+                    case 3: cn_class(IntC<3>{}, cl); break;
+                    case 4: cn_class(IntC<4>{}, cl); break;
+                    case 5: cn_class(IntC<5>{}, cl); break;
+                    case 6: cn_class(IntC<6>{}, cl); break;
+                    case 7: cn_class(IntC<7>{}, cl); break;
+                    case 8: cn_class(IntC<8>{}, cl); break;
+                    default: cn_class(IntC<0>{}, cl); break;
                 }
             }
             __syncthreads();
 
-            // ---- variable nodes of one degree class: inputs in registers (DV <= 8, U variables per thread at a time) or
-            //      a local array ----
-            auto vn_class = [&](auto dv_tag, auto u_tag, const WorkItem cl) {
+            // ---- variable nodes of one degree class: inputs in registers (DV <= 8) or a local array.  Software pipeline
+            //      over the thread's variables: while variable i is worked on, the slot list, LLR and alpha of i + nthr and
+            //      the variable id / alpha column of i + 2 nthr are on their way. ----
+            auto vn_class = [&](auto dv_tag, const WorkItem cl) {
                 constexpr int DV = decltype(dv_tag)::value;
-                constexpr int U = decltype(u_tag)::value;
                 const int m = cl.count;
                 const uint16_t* __restrict__ lists = p.vslots + cl.first_slot;   // entry d of variable i at lists[d * m + i]
-                if constexpr (DV >= 0) {
+                const uint16_t* __restrict__ vp = p.vpos_var + cl.first_node;
+                const bool use_alpha = has_alpha && !last;
+                const int32_t* __restrict__ ax = (use_alpha && p.aidx) ? p.aidx + cl.first_node : nullptr;
+                const float alpha_one = (use_alpha && !ax) ? __ldg(alpha_t) : 1.f;
+                if constexpr (DV >= 0 && DV <= LDPC_RES_PIPE_MAX_DV) {
                     constexpr int D1 = DV > 0 ? DV : 1;
-                    for (int i0 = tid; i0 < m; i0 += nthr * U) {
-                        int sl[U][D1];
-                        int j[U];
-                        float c[U][D1];
-                        float L[U], alpha[U];
-                        bool live[U];
+                    int sl[D1];
+                    int j = 0, j_next = 0, acol_next = 0;
+                    float L = 0.f, alpha = alpha_one;
+                    if (tid < m) {
+                        j = __ldg(vp + tid);
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int i = i0 + u * nthr;
-                            live[u] = i < m;
-                            j[u] = 0;
-                            if (live[u]) {
-                                j[u] = __ldg(p.vpos_var + cl.first_node + i);
+                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + d * m + tid);
+                    }
+                    if (tid + nthr < m) {
+                        j_next = __ldg(vp + tid + nthr);
+                        if (ax) acol_next = __ldg(ax + tid + nthr);
+                    }
+                    if (tid < m) {
+                        L = __ldg(llr + j);
+                        if (ax) alpha = __ldg(alpha_t + __ldg(ax + tid));
+                    }
+                    for (int i = tid; i < m; i += nthr) {
+                        int sl_next[D1];
+                        int j_next2 = 0, acol_next2 = 0;
+                        float L_next = 0.f, alpha_next = alpha_one;
+                        if (i + nthr < m) {
 #pragma unroll
-                                for (int d = 0; d < DV; ++d) sl[u][d] = __ldg(lists + d * m + i);
+                            for (int d = 0; d < DV; ++d) sl_next[d] = __ldg(lists + d * m + i + nthr);
+                            L_next = __ldg(llr + j_next);
+                            if (ax) alpha_next = __ldg(alpha_t + acol_next);
+                        }
+                        if (i + 2 * nthr < m) {
+                            j_next2 = __ldg(vp + i + 2 * nthr);
+                            if (ax) acol_next2 = __ldg(ax + i + 2 * nthr);
+                        }
+                        float c[D1];
+#pragma unroll
+                        for (int d = 0; d < DV; ++d) c[d] = msg[sl[d]];
+                        const float tot = LibSum<float>::template stat<DV>([&](int k) { return c[k]; });
+                        const float pv = DV > 0 ? __fadd_rn(L, tot) : L;
+                        if (!last) {   // the v2c update of iteration T-1 is dead
+#pragma unroll
+                            for (int d = 0; d < DV; ++d) {
+                                float sd = LibSum<float>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int k) { return c[k < d ? k : k + 1]; });
+                                if (has_alpha) sd = __fmul_rn(alpha, sd);
+                                msg[sl[d]] = __fadd_rn(L, sd);
                             }
                         }
+                        hbit[j] = pv < 0.f ? 1 : 0;
+                        if (post) post[j] = pv;   // refreshed every iteration: the row holds the posterior of the stop iteration
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            L[u] = 0.f;
-                            alpha[u] = 1.f;
-                            if (live[u]) {
-                                L[u] = __ldg(llr + j[u]);
-                                if (has_alpha && !last) alpha[u] = __ldg(alpha_t + (p.aidx ? __ldg(p.aidx + cl.first_node + i0 + u * nthr) : 0));
+                        for (int d = 0; d < DV; ++d) sl[d] = sl_next[d];
+                        j = j_next;
+                        j_next = j_next2;
+                        L = L_next;
+                        alpha = alpha_next;
+                        acol_next = acol_next2;
+                    }
+                } else if constexpr (DV >= 0) {   // higher degrees: the pipeline registers would spill (64 per thread)
+                    for (int i = tid; i < m; i += nthr) {
+                        const int j = __ldg(vp + i);
+                        int sl[DV];
 #pragma unroll
-                                for (int d = 0; d < DV; ++d) c[u][d] = msg[sl[u][d]];
+                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + d * m + i);
+                        const float L = __ldg(llr + j);
+                        const float alpha = ax ? __ldg(alpha_t + __ldg(ax + i)) : alpha_one;
+                        float c[DV];
+#pragma unroll
+                        for (int d = 0; d < DV; ++d) c[d] = msg[sl[d]];
+                        const float tot = LibSum<float>::template stat<DV>([&](int k) { return c[k]; });
+                        const float pv = __fadd_rn(L, tot);
+                        if (!last) {
+#pragma unroll
+                            for (int d = 0; d < DV; ++d) {
+                                float sd = LibSum<float>::template stat<DV - 1>([&](int k) { return c[k < d ? k : k + 1]; });
+                                if (has_alpha) sd = __fmul_rn(alpha, sd);
+                                msg[sl[d]] = __fadd_rn(L, sd);
                             }
                         }
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            if (!live[u]) continue;
-                            const float tot = LibSum<float>::template stat<DV>([&](int i) { return c[u][i]; });
-                            const float pv = DV > 0 ? __fadd_rn(L[u], tot) : L[u];
-                            if (!last) {   // the v2c update of iteration T-1 is dead
-#pragma unroll
-                                for (int d = 0; d < DV; ++d) {
-                                    float sd = LibSum<float>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[u][i < d ? i : i + 1]; });
-                                    if (has_alpha) sd = __fmul_rn(alpha[u], sd);
-                                    msg[sl[u][d]] = __fadd_rn(L[u], sd);
-                                }
-                            }
-                            hbit[j[u]] = pv < 0.f ? 1 : 0;
-                            if (post) post[j[u]] = pv;   // refreshed every iteration: the row holds the posterior of the stop iteration
-                        }
+                        hbit[j] = pv < 0.f ? 1 : 0;
+                        if (post) post[j] = pv;
                     }
                 } else {
                     const int dvr = cl.deg;
                     for (int i = tid; i < m; i += nthr) {
-                        const int j = __ldg(p.vpos_var + cl.first_node + i);
+                        const int j = __ldg(vp + i);
                         const float L = __ldg(llr + j);
-                        float alpha = 1.f;
-                        if (has_alpha && !last) alpha = __ldg(alpha_t + (p.aidx ? __ldg(p.aidx + cl.first_node + i) : 0));
+                        const float alpha = ax ? __ldg(alpha_t + __ldg(ax + i)) : alpha_one;
                         int sl[kResMaxDv];
                         float c[kResMaxDv];
                         for (int d = 0; d < dvr; ++d) {
@@ -266,16 +302,16 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
             for (int vi = 0; vi < nvc; ++vi) {
                 const WorkItem cl = s_cls[ncc + vi];
                 switch (cl.deg) {   // block-uniform
-                    case 0: vn_class(IntC<0>{}, IntC<(0 <= LDPC_RES_VN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 1: vn_class(IntC<1>{}, IntC<(1 <= LDPC_RES_VN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 2: vn_class(IntC<2>{}, IntC<(2 <= LDPC_RES_VN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 3: vn_class(IntC<3>{}, IntC<(3 <= LDPC_RES_VN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 4: vn_class(IntC<4>{}, IntC<(4 <= LDPC_RES_VN_U2_MAX ? 2 : 1)>{}, cl); break;
-                    case 5: vn_class(IntC<5>{}, IntC<1>{}, cl); break;
-                    case 6: vn_class(IntC<6>{}, IntC<1>{}, cl); break;
-                    case 7: vn_class(IntC<7>{}, IntC<1>{}, cl); break;
-                    case 8: vn_class(IntC<8>{}, IntC<1>{}, cl); break;
-                    default: vn_class(IntC<-1>{}, IntC<1>{}, cl); break;
+                    case 0: vn_class(IntC<0>{}, cl); break;
+                    case 1: vn_class(IntC<1>{}, cl); break;
+                    case 2: vn_class(IntC<2>{}, cl); break;
+                    case 3: vn_class(IntC<3>{}, cl); break;
+                    case 4: vn_class(IntC<4>{}, cl); break;
+                    case 5: vn_class(IntC<5>{}, cl); break;
+                    case 6: vn_class(IntC<6>{}, cl); break;
+                    case 7: vn_class(IntC<7>{}, cl); break;
+                    case 8: vn_class(IntC<8>{}, cl); break;
+                    default: vn_class(IntC<-1>{}, cl); break;
                 }
             }
             __syncthreads();
@@ -283,13 +319,49 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
             // ---- syndrome and early stop (ldpc_decoder.py:141-144) ----
             if (p.early_stop || last) {
                 int unsat = 0;
+                // two checks per thread at a time, all their variable ids requested before the first decision is read
+                auto syn_class = [&](auto dc_tag, const WorkItem cl) {
+                    constexpr int DC = decltype(dc_tag)::value;
+                    constexpr int X = DC > 0 ? DC : 1;
+                    const int m = cl.count;
+                    const uint16_t* __restrict__ sv = p.slot_var + cl.first_slot;
+                    if constexpr (DC > 0) {
+                        for (int c = tid; c < m; c += 2 * nthr) {
+                            const bool two = c + nthr < m;
+                            int v0[X], v1[X];
+#pragma unroll
+                            for (int k = 0; k < DC; ++k) {
+                                v0[k] = __ldg(sv + k * m + c);
+                                v1[k] = two ? __ldg(sv + k * m + c + nthr) : 0;
+                            }
+                            uint32_t par0 = 0, par1 = 0;
+#pragma unroll
+                            for (int k = 0; k < DC; ++k) {
+                                par0 ^= hbit[v0[k]];
+                                par1 ^= hbit[v1[k]];
+                            }
+                            unsat |= (int)(par0 | (two ? par1 : 0u));
+                        }
+                    } else {
+                        for (int c = tid; c < m; c += nthr) {
+                            uint32_t par = 0;
+                            for (int k = 0; k < cl.deg; ++k) par ^= hbit[__ldg(sv + k * m + c)];
+                            unsat |= (int)par;
+                        }
+                    }
+                };
                 for (int ci = 0; ci < ncc; ++ci) {
                     const WorkItem cl = s_cls[ci];
-                    const uint16_t* __restrict__ sv = p.slot_var + cl.first_slot;
-                    for (int c = tid; c < cl.count; c += nthr) {
-                        uint32_t par = 0;
-                        for (int k = 0; k < cl.deg; ++k) par ^= hbit[__ldg(sv + k * cl.count + c)];
-                        unsat |= (int)par;
+                    switch (cl.deg) {   // block-uniform
+                        case 1: syn_class(IntC<1>{}, cl); break;
+                        case 2: syn_class(IntC<2>{}, cl); break;
+                        case 3: syn_class(IntC<3>{}, cl); break;
+                        case 4: syn_class(IntC<4>{}, cl); break;
+                        case 5: syn_class(IntC<5>{}, cl); break;
+                        case 6: syn_class(IntC<6>{}, cl); break;
+                        case 7: syn_class(IntC<7>{}, cl); break;
+                        case 8: syn_class(IntC<8>{}, cl); break;
+                        default: syn_class(IntC<0>{}, cl); break;
                     }
                 }
                 if (!__syncthreads_or(unsat)) {   // block-uniform

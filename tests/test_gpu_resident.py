@@ -142,17 +142,17 @@ def test_resident_equals_per_iteration_path_on_a_full_size_shape(built_lib, monk
             assert torch.equal(a, b)
 
 
-def test_policy_takes_the_resident_decode_for_at_most_one_wave(built_lib, monkeypatch):
-    """Without LDPC_RESIDENT the library decides (ldpc_api.cu fill_resident): a batch of at most one wave of thread
-    blocks decodes CTA-resident, a larger one with the per-iteration kernels, a single frame of a code above 64 KB
-    too; results are the same either way."""
+def test_policy_takes_the_resident_decode_for_a_few_waves(built_lib, monkeypatch):
+    """Without LDPC_RESIDENT the library decides (ldpc_api.cu fill_resident): a batch of at most a few waves of thread
+    blocks (4 with one block per SM, 2 where an SM holds several frames) decodes CTA-resident, a larger one with the
+    per-iteration kernels; results are the same either way."""
     L = built_lib
     monkeypatch.delenv("LDPC_RESIDENT", raising=False)
     monkeypatch.delenv("LDPC_RESIDENT_MAX_FRAMES", raising=False)
     T = 8
     small = L.codes.dvbs2_shaped(max_iterations=T, scale=20)        # ~10 KB per frame: many blocks per SM
     big = L.codes.dvbs2_shaped(max_iterations=T)                    # 194 KB per frame: one block per SM
-    for code, cases in ((small, ((1, 1), (300, 1), (60000, 0))), (big, ((1, 0), (100, 1), (400, 0)))):
+    for code, cases in ((small, ((1, 1), (300, 1), (60000, 0))), (big, ((1, 1), (400, 1), (2000, 0)))):
         dec = L.Neural2DMinSumDecoder(code, 2, T)
         with torch.no_grad():
             dec._beta_table.fill_(0.8)
