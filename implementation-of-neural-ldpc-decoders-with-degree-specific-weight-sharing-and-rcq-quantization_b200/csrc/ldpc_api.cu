@@ -98,11 +98,13 @@ struct ldpc_graph {
     std::vector<LayerRec> lay_recs;
     LayerRec* d_lay_recs = nullptr;
     // CTA-resident decode (ldpc_resident.cu): degree classes and 16-bit index tables in the kernel's own slot order
-    // ("physical" slots: edge k of check c of a class of `count` checks at first_slot + k * count + c, so that the
-    // lanes of a warp -- consecutive checks -- touch consecutive shared-memory words).  Built when E, n < 65536.
+    // ("physical" slots: the checks of a class in tiles of 32, edge k of check (tile, lane) at
+    // first_slot + tile * 32 * deg + k * 32 + lane, so that the lanes of a warp -- consecutive checks -- touch
+    // consecutive shared-memory words at compile-time strides).  Built when E, n < 65536.
     struct Resident {
         bool ok = false;
         int n_cclass = 0, n_vclass = 0;
+        int32_t E_phys = 0;                  // physical slots (classes padded to whole 32-node tiles)
         std::vector<int32_t> phys;           // [E] slot -> physical slot
         WorkItem* d_classes = nullptr;       // check classes, then variable classes
         uint16_t* d_slot_var = nullptr;      // [E] physical slot -> variable
@@ -350,30 +352,43 @@ extern "C" int ldpc_graph_create(int device, int32_t n, int32_t m, const int64_t
             }
             return cls;
         };
-        const std::vector<WorkItem> cc = classes_of(g->cn[1].items), vc = classes_of(g->vn[1].items);
+        std::vector<WorkItem> cc = classes_of(g->cn[1].items), vc = classes_of(g->vn[1].items);
         if ((int)cc.size() <= kResMaxClasses && (int)vc.size() <= kResMaxClasses) {
+            // tiles of 32 nodes: inside a tile, edge k of node (lane) at tile_base + k * 32 + lane -- compile-time strides
+            // for the kernel's unrolled node code; a class is padded to whole tiles
+            auto tiled = [](int32_t base, int node, int k, int deg) { return base + (node >> 5) * (32 * deg) + k * 32 + (node & 31); };
             ldpc_graph::Resident& r = g->res;
             r.ok = true;
             r.n_cclass = (int)cc.size();
             r.n_vclass = (int)vc.size();
             r.phys.assign((size_t)E, 0);
-            res_slot_var.assign((size_t)E, 0);
-            for (const WorkItem& cl : cc)
+            int32_t pbase = 0;
+            for (WorkItem& cl : cc) {
                 for (int c = 0; c < cl.count; ++c)
-                    for (int k = 0; k < cl.deg; ++k) {
-                        const int32_t slot = cl.first_slot + c * cl.deg + k, ph = cl.first_slot + k * cl.count + c;
-                        r.phys[(size_t)slot] = ph;
-                        res_slot_var[(size_t)ph] = (uint16_t)g->slot_var[(size_t)slot];
-                    }
-            res_vslots.assign((size_t)E, 0);
-            for (const WorkItem& cl : vc)
+                    for (int k = 0; k < cl.deg; ++k) r.phys[(size_t)(cl.first_slot + c * cl.deg + k)] = tiled(pbase, c, k, cl.deg);
+                cl.first_slot = pbase;
+                pbase += (cl.count + 31) / 32 * 32 * cl.deg;
+            }
+            r.E_phys = pbase;
+            res_slot_var.assign((size_t)r.E_phys, 0);
+            for (int64_t sl = 0; sl < E; ++sl) res_slot_var[(size_t)r.phys[(size_t)sl]] = (uint16_t)g->slot_var[(size_t)sl];
+            int32_t vbase = 0;
+            std::vector<std::pair<size_t, uint16_t>> entries;
+            entries.reserve((size_t)E);
+            for (WorkItem& cl : vc) {
                 for (int i = 0; i < cl.count; ++i)
                     for (int dd = 0; dd < cl.deg; ++dd)
-                        res_vslots[(size_t)(cl.first_slot + dd * cl.count + i)] =
-                            (uint16_t)r.phys[(size_t)g->vslots[(size_t)(cl.first_slot + i * cl.deg + dd)]];
+                        entries.emplace_back((size_t)tiled(vbase, i, dd, cl.deg),
+                                             (uint16_t)r.phys[(size_t)g->vslots[(size_t)(cl.first_slot + i * cl.deg + dd)]]);
+                cl.first_slot = vbase;
+                vbase += (cl.count + 31) / 32 * 32 * cl.deg;
+            }
+            res_vslots.assign((size_t)std::max<int32_t>(vbase, 1), 0);
+            for (const auto& e : entries) res_vslots[e.first] = e.second;
             res_vpos_var.assign(g->vpos_var.begin(), g->vpos_var.end());
             res_classes = cc;
             res_classes.insert(res_classes.end(), vc.begin(), vc.end());
+            if (r.E_phys >= 65536) r.ok = false;   // physical slots are 16-bit table entries
         }
     }
     // ---- upload ----
@@ -926,6 +941,7 @@ bool fill_small(ldpc_decoder* d, Workspace* ws, int64_t B, int64_t Bp, bool want
     sp.n = g->n;
     sp.E = (int)g->E;
     sp.n_checks = (int)g->cn[1].items.size();
+    sp.max_dv = g->max_dv;
     sp.cn_items = g->cn[1].d;
     sp.vn_items = g->vn[1].d;
     sp.slot_var = g->d_slot_var;
@@ -959,7 +975,7 @@ bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
     rp.T = d->T;
     rp.early_stop = d->early_stop;
     rp.n = g->n;
-    rp.E = (int)g->E;
+    rp.E = g->res.E_phys;
     rp.max_dv = g->max_dv;
     rp.n_cclass = g->res.n_cclass;
     rp.n_vclass = g->res.n_vclass;
@@ -1533,7 +1549,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
                     }
         rc = upload(&d->d_bidx, bidx);
         if (!rc && g->res.ok) {   // the same columns in the slot order of the CTA-resident decode
-            std::vector<int32_t> rb((size_t)E);
+            std::vector<int32_t> rb((size_t)g->res.E_phys, 0);
             for (int64_t sl = 0; sl < E; ++sl) rb[(size_t)g->res.phys[(size_t)sl]] = bidx[(size_t)sl];
             rc = upload(&d->d_res_bidx, rb);
         }
@@ -1547,7 +1563,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
             for (int64_t sl = 0; sl < E; ++sl) as[(size_t)sl] = cfg->alpha_index[g->slot_var[(size_t)sl]];
             rc = upload(&d->d_aidx_slot, as);
             if (!rc && g->res.ok) {
-                std::vector<int32_t> ra((size_t)E);
+                std::vector<int32_t> ra((size_t)g->res.E_phys, 0);
                 for (int64_t sl = 0; sl < E; ++sl) ra[(size_t)g->res.phys[(size_t)sl]] = as[(size_t)sl];
                 rc = upload(&d->d_res_aidx_slot, ra);
             }

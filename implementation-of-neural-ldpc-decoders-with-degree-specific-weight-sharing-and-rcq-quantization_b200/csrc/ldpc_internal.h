@@ -100,6 +100,7 @@ struct SmallLaunch {
     int64_t B, Bp;              // Bp: B rounded up to a multiple of 128
     int T, early_stop;
     int n, E, n_checks;         // n_checks: non-empty checks = entries of cn_items
+    int max_dv;
     const WorkItem* cn_items;   // one check per item (the graph's fine list)
     const WorkItem* vn_items;   // one variable per item, all n of them
     const int32_t* slot_var;
@@ -136,12 +137,14 @@ struct ResidentLaunch {
     uint8_t* success;           // [B] or nullptr
     int64_t B;
     int T, early_stop;
-    int n, E, max_dv;
+    int n, E, max_dv;           // E: PHYSICAL message slots (classes padded to whole 32-node tiles)
     int n_cclass, n_vclass;
     const WorkItem* classes;    // [n_cclass] check classes (first_slot: first physical slot), then [n_vclass] variable
                                 // classes (first_node: first position, first_slot: offset of the class's lists in vslots)
-    const uint16_t* slot_var;   // [E] physical slot -> variable
-    const uint16_t* vslots;     // [E] entry d of the i-th variable of a class at first_slot + d * count + i: a physical slot
+    const uint16_t* slot_var;   // [E] physical slot -> variable.  Physical slot of edge k of the c-th check of a class:
+                                //     first_slot + (c / 32) * 32 * deg + k * 32 + c % 32
+    const uint16_t* vslots;     // entry d of the i-th variable of a class (a physical slot) at
+                                //     first_slot + (i / 32) * 32 * deg + d * 32 + i % 32
     const uint16_t* vpos_var;   // [n] position -> variable
     const int32_t* bidx;        // [E] beta column per physical slot, or nullptr
     int beta_per_edge;

@@ -13,11 +13,14 @@
 // Layout (second version; the first one walked one WorkItem per node with 32-bit tables and check-major slots: 71
 // instructions per edge-iteration, 12 warps per issue waiting on index loads, 2.5 shared-memory wavefronts per access).
 // Nodes are visited by DEGREE CLASS (all checks / variables of one degree: the class loop is block-uniform, the node
-// loop inside it is straight-line code for that degree), and the messages of a class are stored edge-major:
-//     edge k of the c-th check of a class of `count` checks at  first_slot + k * count + c
+// loop inside it is straight-line code for that degree), and the messages of a class are stored in tiles of 32 checks,
+// edge-major inside a tile:
+//     edge k of the c-th check of a class at  first_slot + (c / 32) * 32 * deg + k * 32 + c % 32
 // so the lanes of a warp -- consecutive checks -- read and write consecutive shared-memory words (no bank conflicts
 // on the check side) and consecutive entries of every index table (coalesced 16-bit loads: E and n are below 65 536
-// for anything that fits an SM).  The variable side gathers through its slot lists, stored transposed the same way.
+// for anything that fits an SM), and the edges of a node are a COMPILE-TIME stride apart: one address per node, the
+// rest are immediate offsets (with a run-time stride -- the class size -- address arithmetic was a third of all
+// instructions).  The variable side gathers through its slot lists, stored in the same tiled order.
 // A thread's nodes of a class are visited in a software-pipelined loop: the index-table entries (and the LLR / weight
 // they lead to) of the thread's NEXT node are requested before its current node is worked on, so the L2 round trips
 // of the tables -- 194 KB of messages leave no room for them in an SM -- overlap the shared-memory work.
@@ -96,6 +99,8 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                 constexpr int X = DC > 0 ? DC : 1;
                 const int D = DC > 0 ? DC : cl.deg;
                 const int m = cl.count;
+                const int lane = tid & 31;
+                auto node_off = [&](int c) { return (c - lane) * D + lane; };   // first edge of check c (c % 32 == lane)
                 const bool one_beta = has_beta && !p.beta_per_edge;
                 const int32_t* __restrict__ bx = (one_beta && p.bidx) ? p.bidx + cl.first_slot : nullptr;   // column of edge 0
                 float beta = 1.f, beta_next = 1.f;
@@ -104,26 +109,26 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                     if (!bx) {
                         beta = beta_next = __ldg(beta_t);
                     } else {
-                        if (tid < m) beta = __ldg(beta_t + __ldg(bx + tid));
-                        if (tid + nthr < m) col_next = __ldg(bx + tid + nthr);
+                        if (tid < m) beta = __ldg(beta_t + __ldg(bx + node_off(tid)));
+                        if (tid + nthr < m) col_next = __ldg(bx + node_off(tid + nthr));
                     }
                 }
                 for (int c = tid; c < m; c += nthr) {
                     int col_next2 = 0;
                     if (bx) {
                         if (c + nthr < m) beta_next = __ldg(beta_t + col_next);
-                        if (c + 2 * nthr < m) col_next2 = __ldg(bx + c + 2 * nthr);
+                        if (c + 2 * nthr < m) col_next2 = __ldg(bx + node_off(c + 2 * nthr));
                     }
-                    float* const io = msg + cl.first_slot + c;        // edge k at io[k * m]
-                    const int s0 = cl.first_slot + c;                 // physical slot of edge k: s0 + k * m
+                    const int s0 = cl.first_slot + node_off(c);       // physical slot of edge k: s0 + k * 32
+                    float* const io = msg + s0;                       // edge k at io[k * 32]
                     float x[X];
                     if constexpr (DC > 0) {
 #pragma unroll
-                        for (int k = 0; k < DC; ++k) x[k] = io[k * m];
+                        for (int k = 0; k < DC; ++k) x[k] = io[k * 32];
                     }
                     auto input = [&](int k) -> float {
                         if constexpr (DC > 0) return x[k];
-                        else return io[k * m];
+                        else return io[k * 32];
                     };
                     MinState<float, false> st;
                     st.init();
@@ -137,9 +142,9 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                             const float xk = input(k);
                             const bool is_min = fabsf(xk) == st.m1;
                             const bool zero_others = D > 1 && (st.m2 == 0.f || (st.m1 == 0.f && !is_min));
-                            const float b = (has_beta && p.beta_per_edge) ? __ldg(beta_t + __ldg(p.bidx + s0 + k * m)) : beta_check;
-                            const float alpha = alpha_t ? __ldg(alpha_t + (p.aidx_slot ? __ldg(p.aidx_slot + s0 + k * m) : 0)) : 0.f;
-                            io[k * m] = offset_value<float>(is_min ? st.m2 : st.m1, b, has_beta, alpha, alpha_t != nullptr,
+                            const float b = (has_beta && p.beta_per_edge) ? __ldg(beta_t + __ldg(p.bidx + s0 + k * 32)) : beta_check;
+                            const float alpha = alpha_t ? __ldg(alpha_t + (p.aidx_slot ? __ldg(p.aidx_slot + s0 + k * 32) : 0)) : 0.f;
+                            io[k * 32] = offset_value<float>(is_min ? st.m2 : st.m1, b, has_beta, alpha, alpha_t != nullptr,
                                                             st.par ^ __float_as_uint(xk), zero_others);
                         }
                     } else if (!p.beta_per_edge) {
@@ -149,18 +154,18 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                         for (int k = 0; k < D; ++k) {
                             const float xk = input(k);
                             const auto o = co.emit(fabsf(xk) == st.m1, __float_as_uint(xk));
-                            if constexpr (QUANT) io[k * m] = lutq[o];
-                            else io[k * m] = o;
+                            if constexpr (QUANT) io[k * 32] = lutq[o];
+                            else io[k * 32] = o;
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
                             const float xk = input(k);
                             const float raw = (fabsf(xk) == st.m1) ? st.m2 : st.m1;
-                            const auto o = cn_emit<float, QUANT, NTH>(raw, __ldg(beta_t + __ldg(p.bidx + s0 + k * m)),
+                            const auto o = cn_emit<float, QUANT, NTH>(raw, __ldg(beta_t + __ldg(p.bidx + s0 + k * 32)),
                                                                       st.par ^ __float_as_uint(xk), qz, p.bc);
-                            if constexpr (QUANT) io[k * m] = lutq[o];
-                            else io[k * m] = o;
+                            if constexpr (QUANT) io[k * 32] = lutq[o];
+                            else io[k * 32] = o;
                         }
                     }
                     beta = beta_next;
@@ -189,7 +194,10 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
             auto vn_class = [&](auto dv_tag, const WorkItem cl) {
                 constexpr int DV = decltype(dv_tag)::value;
                 const int m = cl.count;
-                const uint16_t* __restrict__ lists = p.vslots + cl.first_slot;   // entry d of variable i at lists[d * m + i]
+                const int lane = tid & 31;
+                const int dstride = DV >= 0 ? DV : cl.deg;
+                // entry d of variable i (i % 32 == lane) at lists[(i - lane) * deg + lane + d * 32]
+                const uint16_t* __restrict__ lists = p.vslots + cl.first_slot + lane;
                 const uint16_t* __restrict__ vp = p.vpos_var + cl.first_node;
                 const bool use_alpha = has_alpha && !last;
                 const int32_t* __restrict__ ax = (use_alpha && p.aidx) ? p.aidx + cl.first_node : nullptr;
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                     if (tid < m) {
                         j = __ldg(vp + tid);
 #pragma unroll
-                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + d * m + tid);
+                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + (tid - lane) * dstride + d * 32);
                     }
                     if (tid + nthr < m) {
                         j_next = __ldg(vp + tid + nthr);
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                         float L_next = 0.f, alpha_next = alpha_one;
                         if (i + nthr < m) {
 #pragma unroll
-                            for (int d = 0; d < DV; ++d) sl_next[d] = __ldg(lists + d * m + i + nthr);
+                            for (int d = 0; d < DV; ++d) sl_next[d] = __ldg(lists + (i + nthr - lane) * dstride + d * 32);
                             L_next = __ldg(llr + j_next);
                             if (ax) alpha_next = __ldg(alpha_t + acol_next);
                         }
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                         const int j = __ldg(vp + i);
                         int sl[DV];
 #pragma unroll
-                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + d * m + i);
+                        for (int d = 0; d < DV; ++d) sl[d] = __ldg(lists + (i - lane) * dstride + d * 32);
                         const float L = __ldg(llr + j);
                         const float alpha = ax ? __ldg(alpha_t + __ldg(ax + i)) : alpha_one;
                         float c[DV];
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                         int sl[kResMaxDv];
                         float c[kResMaxDv];
                         for (int d = 0; d < dvr; ++d) {
-                            sl[d] = __ldg(lists + d * m + i);
+                            sl[d] = __ldg(lists + (i - lane) * dstride + d * 32);
                             c[d] = msg[sl[d]];
                         }
                         const float tot = LibSum<float>::dyn([&](int k) { return c[k]; }, dvr);
@@ -324,15 +332,17 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                     constexpr int DC = decltype(dc_tag)::value;
                     constexpr int X = DC > 0 ? DC : 1;
                     const int m = cl.count;
-                    const uint16_t* __restrict__ sv = p.slot_var + cl.first_slot;
+                    const int lane = tid & 31;
+                    const int dstride = DC > 0 ? DC : cl.deg;
+                    const uint16_t* __restrict__ sv = p.slot_var + cl.first_slot + lane;   // edge k of check c at sv[(c - lane) * deg + k * 32]
                     if constexpr (DC > 0) {
                         for (int c = tid; c < m; c += 2 * nthr) {
                             const bool two = c + nthr < m;
                             int v0[X], v1[X];
 #pragma unroll
                             for (int k = 0; k < DC; ++k) {
-                                v0[k] = __ldg(sv + k * m + c);
-                                v1[k] = two ? __ldg(sv + k * m + c + nthr) : 0;
+                                v0[k] = __ldg(sv + (c - lane) * dstride + k * 32);
+                                v1[k] = two ? __ldg(sv + (c + nthr - lane) * dstride + k * 32) : 0;
                             }
                             uint32_t par0 = 0, par1 = 0;
 #pragma unroll
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(1024, 1) resident_decode_kernel(const Resident
                     } else {
                         for (int c = tid; c < m; c += nthr) {
                             uint32_t par = 0;
-                            for (int k = 0; k < cl.deg; ++k) par ^= hbit[__ldg(sv + k * m + c)];
+                            for (int k = 0; k < cl.deg; ++k) par ^= hbit[__ldg(sv + (c - lane) * dstride + k * 32)];
                             unsat |= (int)par;
                         }
                     }

@@ -26,6 +26,7 @@ namespace ldpc {
 namespace {
 
 constexpr int kSmallThreads = 128;
+constexpr int kSmallMaxDv = 64;   // run-time-degree variable nodes gather their inputs into a local array
 
 enum { SMALL_NORMALIZED = 0, SMALL_QUANT = 1, SMALL_OFFSET = 2 };
 
@@ -68,11 +69,15 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int E = p.E, n = p.n, nc = p.n_checks, nw = (n + 31) >> 5;
     // ---- shared-memory carve-up: per-frame columns first, then the tables ----
-    Real* const v2c = reinterpret_cast<Real*>(small_smem) + tid;                 // [E][threads]
-    Real* const c2v = v2c + (size_t)E * kSmallThreads;                           // [E][threads]
-    Real* const llr = c2v + (size_t)E * kSmallThreads;                           // [n][threads]
-    uint32_t* const hb = reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(small_smem) + (size_t)(2 * E + n) * kSmallThreads) + tid;   // [nw][threads]
-    int32_t* const tab = reinterpret_cast<int32_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(small_smem) + (size_t)(2 * E + n) * kSmallThreads) +
+    // messages in place: a slot holds v2c before the check-node pass and c2v after it (half the columns of a
+    // two-array layout: (7,4) float64 frames 268 -> 164 bytes, 6 -> 10 resident CTAs per SM)
+    const bool want_post = p.post_rows != nullptr || p.postT != nullptr;
+    const int ncol = E + n + (want_post ? n : 0);
+    Real* const msg = reinterpret_cast<Real*>(small_smem) + tid;                 // [E][threads]
+    Real* const llr = msg + (size_t)E * kSmallThreads;                           // [n][threads]
+    Real* const pcol = llr + (size_t)n * kSmallThreads;                          // [n][threads] posteriors (only if wanted)
+    uint32_t* const hb = reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(small_smem) + (size_t)ncol * kSmallThreads) + tid;   // [nw][threads]
+    int32_t* const tab = reinterpret_cast<int32_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(small_smem) + (size_t)ncol * kSmallThreads) +
                                                     (size_t)nw * kSmallThreads);
     SmallTables g;
     {
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
             const Real* __restrict__ gl = static_cast<const Real*>(p.llrT) + f;
             for (int j = 0; j < n; ++j) llr[j * S] = gl[(int64_t)j * p.Bp];
         }
-        for (int s = 0; s < E; ++s) v2c[s * S] = llr[g.svar[s] * S];   // ldpc_decoder.py:84-87
+        for (int s = 0; s < E; ++s) msg[s * S] = llr[g.svar[s] * S];   // ldpc_decoder.py:84-87
         const bool has_beta = p.beta != nullptr;
         const bool has_alpha = p.alpha != nullptr && KIND != SMALL_OFFSET;
         // hard decisions of the frame: in two registers while n <= 64, else in the frame's shared-memory words
@@ -176,8 +181,8 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
             auto cn_node = [&](auto dc_tag, const int deg, const int s0) {
                 constexpr int DC = decltype(dc_tag)::value;
                 const int D = DC > 0 ? DC : deg;
-                const Real* const in = v2c + s0 * S;
-                Real* const out = c2v + s0 * S;
+                const Real* const in = msg + s0 * S;
+                Real* const out = msg + s0 * S;    // in place: an output is written after its own input was read
                 Real x[DC > 0 ? DC : 1];
                 MinState<Real, false> st;
                 st.init();
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
 #pragma unroll
                     for (int i = 0; i < DV; ++i) {
                         off[i] = g.vslot[lb + i] * S;
-                        c[i] = c2v[off[i]];
+                        c[i] = msg[off[i]];
                     }
                     const Real tot = LibSum<Real>::template stat<DV>([&](int i) { return c[i]; });
                     post = DV > 0 ? Arith<Real>::add(L, tot) : L;
@@ -268,22 +273,25 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
                         for (int d = 0; d < DV; ++d) {
                             Real sd = LibSum<Real>::template stat<(DV > 0 ? DV - 1 : 0)>([&](int i) { return c[i < d ? i : i + 1]; });
                             if (has_alpha) sd = Arith<Real>::mul(alpha, sd);
-                            v2c[off[d]] = Arith<Real>::add(L, sd);
+                            msg[off[d]] = Arith<Real>::add(L, sd);
                         }
                     }
                 } else {
-                    const Real tot = LibSum<Real>::dyn([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dvr);
+                    Real c[kSmallMaxDv];   // in place: every input is read before the first output is written
+                    for (int i = 0; i < dvr; ++i) c[i] = msg[g.vslot[lb + i] * S];
+                    const Real tot = LibSum<Real>::dyn([&](int i) { return c[i]; }, dvr);
                     post = Arith<Real>::add(L, tot);
                     if (!last) {
                         Real alpha = Real(1);
                         if (has_alpha) alpha = alpha_t[g.aidx ? g.aidx[pos] : 0];
                         for (int d = 0; d < dvr; ++d) {
-                            Real sd = LibSum<Real>::dyn([&](int i) { return c2v[g.vslot[lb + (i < d ? i : i + 1)] * S]; }, dvr - 1);
+                            Real sd = LibSum<Real>::dyn([&](int i) { return c[i < d ? i : i + 1]; }, dvr - 1);
                             if (has_alpha) sd = Arith<Real>::mul(alpha, sd);
-                            v2c[g.vslot[lb + d] * S] = Arith<Real>::add(L, sd);
+                            msg[g.vslot[lb + d] * S] = Arith<Real>::add(L, sd);
                         }
                     }
                 }
+                if (want_post) pcol[j * S] = post;   // a frame that stops keeps the posterior of its last iteration
                 if (post < Real(0)) {
                     if (reg_bits) bits64 |= 1ull << j;
                     else hb[(j >> 5) * S] |= 1u << (j & 31);
@@ -340,20 +348,10 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
         if (p.success && active) p.success[f] = ok ? 1 : 0;
         if (p.packed_rows && active)   // the frame's decision words ARE its packed row
             for (int w = 0; w < nw; ++w) p.packed_rows[f * nw + w] = hb[w * S];
-        __syncthreads();   // every frame's v2c column is dead: the region becomes the byte stage of the decisions
+        __syncthreads();   // every frame's message columns are dead: the region becomes the byte stage of the decisions
         uint8_t* const stage = small_smem;
         if (p.bits_rows && active)
             for (int j = 0; j < n; ++j) stage[tid * n + j] = (uint8_t)((hb[(j >> 5) * S] >> (j & 31)) & 1u);
-        if (p.post_rows && active) {
-            // the check->variable messages of the frame's last iteration are still in place; the posterior of
-            // variable j replaces its LLR in the frame's column
-            for (int pos = 0; pos < n; ++pos) {
-                const int dv = g.vdeg[pos], lb = g.vbase[pos], j = g.vid[pos];
-                const Real L = llr[j * S];
-                const Real tot = lib_sum<Real>([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dv);
-                llr[j * S] = dv > 0 ? Arith<Real>::add(L, tot) : L;
-            }
-        }
         __syncthreads();
         const int total = cta_frames * n;
         if (p.bits_rows) {
@@ -367,7 +365,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
             Real* __restrict__ dst = static_cast<Real*>(p.post_rows) + cta_base * n;
             int fl = tid / n, j = tid % n;
             for (int e = tid; e < total; e += kSmallThreads) {
-                dst[e] = (llr - tid)[j * S + fl];
+                dst[e] = (pcol - tid)[j * S + fl];
                 j += r128;
                 fl += q128;
                 if (j >= n) { j -= n; ++fl; }
@@ -386,21 +384,16 @@ __global__ void __launch_bounds__(kSmallThreads) small_decode_kernel(const Small
     p.success[f] = ok ? 1 : 0;
     p.done[f] = 1;
     if (p.postT && active) {
-        // the check->variable messages of the frame's last iteration are still in place
         Real* __restrict__ gp = static_cast<Real*>(p.postT) + f;
-        for (int pos = 0; pos < n; ++pos) {
-            const int dv = g.vdeg[pos], lb = g.vbase[pos], j = g.vid[pos];
-            const Real L = llr[j * S];
-            const Real tot = lib_sum<Real>([&](int i) { return c2v[g.vslot[lb + i] * S]; }, dv);
-            gp[(int64_t)j * p.Bp] = dv > 0 ? Arith<Real>::add(L, tot) : L;
-        }
+        for (int j = 0; j < n; ++j) gp[(int64_t)j * p.Bp] = pcol[j * S];
     }
 }
 
 size_t small_smem_bytes(int dtype, const SmallLaunch& p) {
     const size_t rsz = dtype == 0 ? 4 : 8;
     const size_t nw = (size_t)(p.n + 31) / 32;
-    size_t b = ((size_t)(2 * p.E + p.n) * rsz + nw * 4) * kSmallThreads;
+    const bool want_post = p.post_rows != nullptr || p.postT != nullptr;
+    size_t b = ((size_t)(p.E + p.n + (want_post ? p.n : 0)) * rsz + nw * 4) * kSmallThreads;
     b += 4 * ((size_t)2 * p.n_checks + 2 * (size_t)p.E + 3 * (size_t)p.n + (p.bidx ? p.E : 0) + (p.aidx ? p.n : 0) + (p.aidx_slot ? p.E : 0));
     if (p.bc) b += 4 * ((size_t)p.n_quant * p.nth + ((size_t)p.n_quant << p.bc));
     return b;
@@ -420,9 +413,11 @@ cudaError_t launch_small_t(const SmallLaunch& p, size_t smem, cudaStream_t strea
 bool small_decode_fits(int dtype, const SmallLaunch& p) {
     if (p.E <= 0 || p.n <= 0) return false;
     const size_t rsz = dtype == 0 ? 4 : 8;
-    const size_t per_frame = (size_t)(2 * p.E + p.n) * rsz + 4 * (size_t)((p.n + 31) / 32);
-    // (row mode stages the decisions as n bytes per frame in the region of the v2c columns)
-    return per_frame <= 896 && (size_t)p.E * rsz >= (size_t)p.n && small_smem_bytes(dtype, p) <= (size_t)160 * 1024;
+    // (the posterior columns are counted whether or not a call wants them: which decodes go on chip must not depend on it)
+    const size_t per_frame = (size_t)(p.E + 2 * p.n) * rsz + 4 * (size_t)((p.n + 31) / 32);
+    // (row mode stages the decisions as n bytes per frame in the region of the message columns)
+    return per_frame <= 896 && p.max_dv <= kSmallMaxDv && (size_t)p.E * rsz >= (size_t)p.n &&
+           small_smem_bytes(dtype, p) <= (size_t)160 * 1024;
 }
 
 cudaError_t launch_small_decode(int dtype, const SmallLaunch& p, cudaStream_t stream) {
