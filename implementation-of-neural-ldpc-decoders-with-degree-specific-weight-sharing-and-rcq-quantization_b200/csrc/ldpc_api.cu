@@ -1003,13 +1003,13 @@ bool fill_resident(ldpc_decoder* d, int64_t B, ResidentLaunch& rp) {
     rp.sm_count = d->sm_count > 0 ? d->sm_count : 148;
     if (!resident_decode_fits(rp)) return false;
     if (d->use_resident == 1) return true;
-    // policy (tools/resident_latency_probe.py, profiles/r02t_resident_latency.jsonl): the resident decode is issue-bound
+    // policy (tools/resident_latency_probe.py, profiles/r02w_resident_latency.jsonl): the resident decode is issue-bound
     // (~400 G edge-iterations/s with every SM busy) where the per-iteration kernels are HBM-bound (16 bytes per edge and
     // iteration: ~400 G edge-iterations/s as well, 650 G with RCQ codes) -- but those need lanes-over-frames batches of
     // thousands of frames to fill the machine and ~4 launches per iteration, so a batch of a few WAVES (one thread block
     // per frame, as many blocks as the device holds) is faster resident: (16200,7200)-shaped 1 / 148 / 592 frames
-    // 237 / 239 / 937 us against 295 / 652 / 1239 us, QC shape 148 frames 176 against 1044 us, n = 504 1184 frames 58
-    // against 323 us; break-even at 4-8 waves with one block per SM, ~2 waves where an SM holds many small frames.
+    // 225 / 231 / 908 us against 292 / 645 / 1238 us, QC shape 148 frames 150 against 1011 us, n = 504 1184 frames 50
+    // against 318 us; break-even at 4-8 waves with one block per SM, ~2 waves where an SM holds many small frames.
     if (d->resident_wave_frames < 0) d->resident_wave_frames = resident_wave_frames(rp);
     const int64_t waves = d->resident_wave_frames <= rp.sm_count ? 4 : 2;
     const int64_t max_frames = d->resident_max_frames >= 0 ? d->resident_max_frames : waves * d->resident_wave_frames;
