@@ -630,7 +630,48 @@ def config_legs(rig, L, args):
     # C5: FER/BER Monte-Carlo sweep through LDPSimulator.simulate_decoder (simulation_framework.py:141-176) over the
     # SimulationConfig default grid 0..6 dB step 0.5, T = 50, frames sharded over the ranks (configs[4])
     legs.append(mc_sweep_leg(rig, L, args))
+    # one posterior-training step (forward with message history + backward kernels)
+    legs.append(training_leg(rig, L, args))
     return legs
+
+
+def training_leg(rig, L, args):
+    """Forward + backward of PosteriorJointTrainer's step (training_framework.py:108-165) through ldpc_train_forward /
+    ldpc_train_backward: N-2D-NMS type 2, 10 iterations, 8192 frames of the (16200,7200)-shaped code per GPU, loss =
+    binary_cross_entropy_with_logits(-posterior, 0).  Bytes: forward 16E + 4n per frame-iteration (the history slices ARE
+    the message arrays), backward 24E (v2c / c2v history read, gradient rows read and written)."""
+    torch = rig.torch
+    B, T = 8192, T_ITERS
+    code = make_code(L, "dvbs2", T)
+    E, n = code.graph.E, code.n
+    dec = build_decoder(L, code, "n2d2", T)
+    eng = dec._engine(rig.local_rank)
+    llr = L.awgn_llr(n, B, 2.0, seed=99, frame0=rig.rank * B, llr_sign=1, device=rig.local_rank)
+
+    def forward():
+        return eng.train_forward(llr)
+
+    def step():
+        _, post, _, _ = eng.train_forward(llr)
+        g = torch.sigmoid(-post) * (-1.0 / post.numel())     # d loss / d posterior
+        return eng.train_backward(g)
+
+    it = float(forward()[2].float().mean().item())
+    t_fwd, _ = rig.timed_device(forward, 5, 3)
+    t_step, _ = rig.timed_device(step, 5, 3)
+    peak, _ = peak_hbm()
+    fwd_gbs = (16 * E + 4 * n) * it * B / (t_fwd * 1e-3) / 1e9
+    bwd_gbs = 24 * E * it * B / (max(t_step - t_fwd, 1e-6) * 1e-3) / 1e9
+    leg = {"config": "TRAIN", "workload": f"posterior-training step (forward + backward), {DECODERS['n2d2']}, {SHAPES['dvbs2']}, "
+                                          f"AWGN 2.0 dB converging sign convention",
+           "frames_per_gpu": B, "steps": 5, "warmup": 3, "avg_iterations": it,
+           "frames_per_s": rig.world * B / (t_step * 1e-3), "ms_per_step": t_step, "forward_ms": t_fwd, "backward_ms": t_step - t_fwd,
+           "roofline": {"forward_frac": fwd_gbs / peak, "backward_frac": bwd_gbs / peak, "forward_gbs": fwd_gbs, "backward_gbs": bwd_gbs,
+                        "peak_gbs": peak}}
+    release(eng)
+    del dec, eng, llr
+    torch.cuda.empty_cache()
+    return leg
 
 
 def mc_sweep_leg(rig, L, args):

@@ -619,7 +619,8 @@ struct ldpc_decoder {
     int64_t compact_min_frames = 512;
     int compact_percent = 60;     // compact when at most this share of the level's lanes still runs
     int checkpoint_step = 1;      // iterations between checkpoints for batches of >= 16384 frames
-    int speculate = 0;            // LDPC_SPECULATE=1: keep a second span in flight while the host waits for a checkpoint (see DecodeJob)
+    int speculate = 0;            // LDPC_SPECULATE: 1 always / -1 while no frame has stopped yet / 0 (default) never keep a second
+                                  // span in flight while the host waits for a checkpoint (see job_top_up)
     int post_mode = 0;            // LDPC_POST_MODE: 0 adaptive, 1 posterior rows refreshed every iteration, 2 written on stop
     int64_t stat_compactions = 0, stat_early_exits = 0;
     // posterior training: the forward pass keeps every iteration's messages for the backward pass
@@ -630,6 +631,8 @@ struct ldpc_decoder {
         float* g_v2c = nullptr;      // [E][cap]
         float* g_c2v = nullptr;      // [E][cap]
         float* g_post = nullptr;     // [n][cap]
+        float* g_part = nullptr;     // spread copies of the weight gradients (ldpc_train_backward)
+        size_t part_cap = 0;         // floats
         int64_t cap = 0;
         int64_t B = 0, Bp = 0;       // of the last forward pass (0: none yet)
     } train;
@@ -1176,9 +1179,15 @@ int job_enqueue(DecodeJob& j) {
     return LDPC_OK;
 }
 
-// keep up to two spans (one when speculation is off) in flight
+// Keep one span in flight, or two.  A second span hides the host round trip of a checkpoint (the GPU idles for it: tens
+// of microseconds per iteration at large batches), but a decision taken one span late runs that span at the old level
+// size.  Measured (65 536 frames of the (16200,7200)-shaped code, tools/r02_probe.py / mc_knob_probe.py, r02ab): no frame
+// ever stops, T = 10: 87.6 ms with one span, 88.7 with two; 3 dB, T = 50: 76.5 ms with one, 80.7 with two while nobody
+// has stopped (LDPC_SPECULATE=-1), 88.7 with two throughout (=1).  The round trip is already down to a mapped-memory
+// read behind an event, so one span stays the default.
 int job_top_up(DecodeJob& j) {
-    const uint32_t depth = j.d->speculate ? 2u : 1u;
+    const bool nobody_stopped = j.level == 0 && j.last_pending >= j.curB;   // (child levels exist because frames stop)
+    const uint32_t depth = (j.d->speculate > 0 || (j.d->speculate < 0 && nobody_stopped)) ? 2u : 1u;
     while (!j.finished && j.cp_issued - j.cp_done < depth) {
         int rc = job_enqueue(j);
         if (rc) return rc;
@@ -1523,7 +1532,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* gr = getenv("LDPC_GRAPHS")) d->use_graphs = atoi(gr) != 0;
     if (const char* cf = getenv("LDPC_COMPACT_PERCENT")) d->compact_percent = std::min(95, std::max(5, atoi(cf)));
     if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
-    if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp) != 0;
+    if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp);
     if (const char* sm = getenv("LDPC_SMALL")) d->use_small = atoi(sm) != 0;
     if (const char* rs = getenv("LDPC_RESIDENT")) d->use_resident = atoi(rs) != 0;
     if (const char* pm = getenv("LDPC_POST_MODE")) d->post_mode = std::min(2, std::max(0, atoi(pm)));
@@ -1665,6 +1674,7 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder* d) {
     cudaFree(d->train.g_v2c);
     cudaFree(d->train.g_c2v);
     cudaFree(d->train.g_post);
+    cudaFree(d->train.g_part);
     cudaFree(d->d_bidx);
     cudaFree(d->d_aidx);
     cudaFree(d->d_aidx_slot);
@@ -2003,8 +2013,24 @@ extern "C" int ldpc_train_backward(ldpc_decoder* d, const float* grad_posterior,
     const size_t E = (size_t)std::max<int64_t>(g->E, 1);
     const size_t slice = E * (size_t)Bp;
     LAUNCH(K_OTHER, launch_pack(LDPC_F32, grad_posterior, tc.g_post, B, Bp, g->n, nullptr, nullptr, nullptr, d->T, stream));
-    if (grad_beta) CU(cudaMemsetAsync(grad_beta, 0, (size_t)d->T * d->n_beta * sizeof(float), stream));
-    if (grad_alpha) CU(cudaMemsetAsync(grad_alpha, 0, (size_t)d->T * d->n_alpha * sizeof(float), stream));
+    // weight gradients: tables of a few columns (degree-shared weights) are accumulated in `kParts` spread copies and
+    // folded at the end -- every warp adding to the same few addresses serialises in L2 (TrainBwd in ldpc_internal.h)
+    constexpr int kParts = 64;
+    auto parts_for = [&](int cols) { return (cols > 0 && cols <= 4096) ? kParts : 1; };
+    const int beta_parts = grad_beta ? parts_for(d->n_beta) : 1, alpha_parts = grad_alpha ? parts_for(d->n_alpha) : 1;
+    const size_t beta_count = (size_t)d->T * d->n_beta, alpha_count = (size_t)d->T * d->n_alpha;
+    const size_t part_floats = (beta_parts > 1 ? beta_parts * beta_count : 0) + (alpha_parts > 1 ? alpha_parts * alpha_count : 0);
+    if (part_floats > tc.part_cap) {
+        cudaFree(tc.g_part);
+        tc.g_part = nullptr;
+        tc.part_cap = 0;
+        CU(cudaMalloc((void**)&tc.g_part, part_floats * sizeof(float)));
+        tc.part_cap = part_floats;
+    }
+    float* const beta_acc = beta_parts > 1 ? tc.g_part : grad_beta;
+    float* const alpha_acc = alpha_parts > 1 ? tc.g_part + (beta_parts > 1 ? beta_parts * beta_count : 0) : grad_alpha;
+    if (grad_beta) CU(cudaMemsetAsync(beta_acc, 0, (size_t)beta_parts * beta_count * sizeof(float), stream));
+    if (grad_alpha) CU(cudaMemsetAsync(alpha_acc, 0, (size_t)alpha_parts * alpha_count * sizeof(float), stream));
     TrainBwd p{};
     p.B = B;
     p.Bp = Bp;
@@ -2028,14 +2054,19 @@ extern "C" int ldpc_train_backward(ldpc_decoder* d, const float* grad_posterior,
     p.g_post = tc.g_post;
     p.g_v2c = tc.g_v2c;
     p.g_c2v = tc.g_c2v;
-    p.g_beta = grad_beta;
-    p.g_alpha = grad_alpha;
+    p.g_beta = grad_beta ? beta_acc : nullptr;
+    p.g_alpha = grad_alpha ? alpha_acc : nullptr;
+    p.beta_parts = beta_parts;
+    p.alpha_parts = alpha_parts;
+    p.T = d->T;
     for (int t = d->T - 1; t >= 0; --t) {
         p.v2c_t = tc.v2c_hist + (size_t)t * slice;
         p.c2v_t = tc.c2v_hist + (size_t)t * slice;
         LAUNCH(K_OTHER, launch_train_bwd_vn(p, t, stream));
         LAUNCH(K_OTHER, launch_train_bwd_cn(p, t, stream));
     }
+    if (grad_beta && beta_parts > 1) LAUNCH(K_OTHER, launch_train_fold(beta_acc, grad_beta, beta_parts, (int64_t)beta_count, stream));
+    if (grad_alpha && alpha_parts > 1) LAUNCH(K_OTHER, launch_train_fold(alpha_acc, grad_alpha, alpha_parts, (int64_t)alpha_count, stream));
     return LDPC_OK;
 }
 

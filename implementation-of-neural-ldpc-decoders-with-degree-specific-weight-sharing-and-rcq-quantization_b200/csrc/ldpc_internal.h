@@ -192,9 +192,15 @@ struct TrainBwd {
     const float* g_post;        // [n][Bp] gradient of the loss with respect to the posteriors
     float* g_v2c;               // [E][Bp] in: g v2c_{t+1};  out (check side): g v2c_t
     float* g_c2v;               // [E][Bp] g c2v_t
-    float* g_beta;              // [T][n_beta] accumulated, or nullptr
-    float* g_alpha;             // [T][n_alpha] accumulated, or nullptr
+    float* g_beta;              // [beta_parts][T][n_beta] accumulated, or nullptr
+    float* g_alpha;             // [alpha_parts][T][n_alpha] accumulated, or nullptr
+    // Degree-shared weights have a handful of columns: every warp of the grid adding to the same few addresses
+    // serialises in L2 (2.1 TB/s instead of 4.3 for the backward pass of a type-2 decoder).  The sums are therefore
+    // spread over `parts` copies (a power of two; block b adds to copy b & (parts - 1)) that a last kernel folds.
+    int beta_parts, alpha_parts;
+    int T;
 };
+cudaError_t launch_train_fold(const float* parts, float* out, int n_parts, int64_t count, cudaStream_t stream);
 cudaError_t launch_train_bwd_vn(const TrainBwd& p, int t, cudaStream_t stream);
 cudaError_t launch_train_bwd_cn(const TrainBwd& p, int t, cudaStream_t stream);
 

@@ -16,7 +16,9 @@
 //     v2c_{t+1}[e] = llr_j + alpha_t[j] * sum_{e' != e} c2v_t[e']
 //                   g alpha_t[col(j)] += g v2c_{t+1}[e] * sum_{e' != e} c2v_t[e']
 //                   g c2v_t[e']       += alpha_t[j] * (G - g v2c_{t+1}[e']),  G = sum_e g v2c_{t+1}[e]
-// Lanes over frames like every other kernel here; weight gradients are reduced over the warp and added atomically.
+// Lanes over frames like every other kernel here; weight gradients are reduced over the warp, accumulated over the nodes
+// of a work item that share a column, and added atomically to one of `parts` spread copies (folded at the end).
+// (Degree-templated bodies with the rows of a node held in registers were tried: 96-128 registers, 22 -> 33 ms.)
 #include "ldpc_cn_common.cuh"
 
 namespace ldpc {
@@ -46,6 +48,15 @@ __global__ void __launch_bounds__(kTrainThreads) train_bwd_vn_kernel(const Train
     const int dv = it.deg;
     const float* alpha_t = p.alpha ? p.alpha + (size_t)t * p.n_alpha : nullptr;
     const int lane = threadIdx.x & 31;
+    float* const g_alpha = p.g_alpha ? p.g_alpha + ((size_t)(blockIdx.x & (unsigned)(p.alpha_parts - 1)) * p.T + t) * p.n_alpha : nullptr;
+    float acc = 0.f;
+    int acc_col = -1;
+    auto flush_alpha = [&]() {
+        if (acc_col < 0) return;
+        const float s = warp_sum(acc);
+        if (lane == 0 && s != 0.f) atomicAdd(g_alpha + acc_col, s);
+        acc = 0.f;
+    };
     for (int c = 0; c < it.count; ++c) {
         const int pos = it.first_node + c;
         const int64_t lbase = (int64_t)it.first_slot + (int64_t)c * dv;
@@ -87,10 +98,15 @@ __global__ void __launch_bounds__(kTrainThreads) train_bwd_vn_kernel(const Train
             float ga = 0.f;
 #pragma unroll
             for (int v = 0; v < V; ++v) ga += (t < tstar[v]) ? (G[v] * C[v] - GC[v]) : 0.f;
-            ga = warp_sum(ga);
-            if (lane == 0 && ga != 0.f) atomicAdd(p.g_alpha + (size_t)t * p.n_alpha + acol, ga);
+            // consecutive variables of an item mostly share their column (one degree class): one atomic per run
+            if (acol != acc_col) {
+                flush_alpha();
+                acc_col = acol;
+            }
+            acc += ga;
         }
     }
+    flush_alpha();
 }
 
 // Check side of iteration t: g_v2c_t and the beta gradients from g_c2v_t.
@@ -108,6 +124,15 @@ __global__ void __launch_bounds__(kTrainThreads) train_bwd_cn_kernel(const Train
     const float* beta_t = p.beta ? p.beta + (size_t)t * p.n_beta : nullptr;
     const float* src = (t == 0) ? p.llrT : p.v2c_t;
     const int lane = threadIdx.x & 31;
+    float* const g_beta = p.g_beta ? p.g_beta + ((size_t)(blockIdx.x & (unsigned)(p.beta_parts - 1)) * p.T + t) * p.n_beta : nullptr;
+    float acc = 0.f;      // one-beta-per-check weights: the checks of an item mostly share their column
+    int acc_col = -1;
+    auto flush_beta = [&]() {
+        if (acc_col < 0) return;
+        const float s = warp_sum(acc);
+        if (lane == 0 && s != 0.f) atomicAdd(g_beta + acc_col, s);
+        acc = 0.f;
+    };
     for (int c = 0; c < it.count; ++c) {
         const int64_t slot0 = (int64_t)it.first_slot + (int64_t)c * dc;
         auto row = [&](int k) -> int64_t { return (t == 0) ? (int64_t)p.slot_var[slot0 + k] : slot0 + k; };
@@ -171,16 +196,19 @@ __global__ void __launch_bounds__(kTrainThreads) train_bwd_cn_kernel(const Train
             if (p.g_beta && beta_t) {
                 if (p.beta_per_edge) {
                     gb = warp_sum(gb);
-                    if (lane == 0 && gb != 0.f) atomicAdd(p.g_beta + (size_t)t * p.n_beta + bcol, gb);
+                    if (lane == 0 && gb != 0.f) atomicAdd(g_beta + bcol, gb);
                 } else {
                     gb_check += gb;
                 }
             }
         }
         if (p.g_beta && beta_t && !p.beta_per_edge) {
-            gb_check = warp_sum(gb_check);
             const int bcol = p.bidx ? p.bidx[slot0] : 0;
-            if (lane == 0 && gb_check != 0.f) atomicAdd(p.g_beta + (size_t)t * p.n_beta + bcol, gb_check);
+            if (bcol != acc_col) {
+                flush_beta();
+                acc_col = bcol;
+            }
+            acc += gb_check;
         }
         if (t == 0) continue;   // g_v2c_0 would be the gradient with respect to the LLRs: not needed
         // pass 2: g_v2c_t
@@ -198,9 +226,25 @@ __global__ void __launch_bounds__(kTrainThreads) train_bwd_cn_kernel(const Train
             *reinterpret_cast<Pack<float, V>*>(p.g_v2c + (slot0 + k) * p.Bp + f0) = out;
         }
     }
+    flush_beta();
+}
+
+// out[i] = sum over the copies of parts[copy][i]
+__global__ void train_fold_kernel(const float* __restrict__ parts, float* __restrict__ out, const int n_parts, const int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int k = 0; k < n_parts; ++k) s += parts[(size_t)k * count + i];
+    out[i] = s;
 }
 
 }  // namespace
+
+cudaError_t launch_train_fold(const float* parts, float* out, int n_parts, int64_t count, cudaStream_t stream) {
+    if (count < 1) return cudaSuccess;
+    train_fold_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(parts, out, n_parts, count);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_train_bwd_vn(const TrainBwd& p, int t, cudaStream_t stream) {
     if (p.n_vn_items == 0) return cudaSuccess;

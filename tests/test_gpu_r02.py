@@ -29,7 +29,8 @@ def _mixed_llr(rng, B, n, snrs):
 
 
 @pytest.mark.parametrize("post_mode,speculate,compact", [("1", "0", "1"), ("2", "0", "1"), ("0", "1", "1"), ("2", "1", "1"),
-                                                          ("1", "1", "1"), ("2", "0", "0"), ("0", "0", "1")])
+                                                          ("1", "1", "1"), ("2", "0", "0"), ("0", "0", "1"), ("0", "-1", "1"),
+                                                          ("2", "-1", "1")])
 def test_posterior_modes_and_speculation_are_result_neutral(built_lib, monkeypatch, post_mode, speculate, compact):
     from oracle import capi as O
     from oracle.restatement import MODE_WRCQ, quantizer_schedule

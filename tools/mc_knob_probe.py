@@ -24,9 +24,8 @@ def timed(fn, reps=3):
     return e0.elapsed_time(e1) / reps, out
 
 
-envs = [{}, {"LDPC_COMPACT_PERCENT": "50"}, {"LDPC_COMPACT_PERCENT": "70"}, {"LDPC_COMPACT_PERCENT": "80"}, {"LDPC_COMPACT_PERCENT": "90"},
-        {"LDPC_SPECULATE": "1"}, {"LDPC_SPECULATE": "0"}, {"LDPC_CHECKPOINT_STEP": "2"}, {"LDPC_COMPACT_MIN_FRAMES": "1024"},
-        {"LDPC_COMPACT_MIN_FRAMES": "8192"}]
+envs = [{}, {"LDPC_COMPACT_PERCENT": "70"},
+        {"LDPC_SPECULATE": "1"}, {"LDPC_SPECULATE": "0"}, {"LDPC_CHECKPOINT_STEP": "2"}]
 for snr in (2.0, 3.0):
     llr = L.awgn_llr(code.n, B, snr, seed=1, llr_sign=1)
     for env in envs:
