@@ -496,6 +496,8 @@ __device__ __forceinline__ void cn_wide_check(const CnLaunch& p, RowRing<Real>& 
         Real beta_check = Real(0);
         if (p.beta_t && !p.beta_per_edge) beta_check = __ldg(static_cast<const Real*>(p.beta_t) + (p.bidx ? __ldg(p.bidx + slot0) : 0));
         Real* __restrict__ orow = static_cast<Real*>(p.dst) + slot0 * p.Bp + f0;
+        // (unrolled: the weight lookups of an edge are two dependent loads; four edges' worth go out together)
+#pragma unroll 4
         for (int k = 0; k < dc; ++k, orow += p.Bp) {
             Real beta, alpha;
             offset_weights<Real>(p, slot0 + k, beta_check, beta, alpha);
