@@ -65,7 +65,7 @@ def built_lib():
     return ldpc_b200
 
 
-FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4"]
+FULLSIZE_CASES = ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4", "rcq_layered_qc"]
 
 
 def load_fullsize(case):

@@ -221,7 +221,7 @@ def test_batch_equals_single_frames_and_host_equals_device(built_lib):
         assert torch.equal(b, B[f]) and torch.equal(p, P[f]) and i == int(I[f])
 
 
-@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4"])
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4", "rcq_layered_qc"])
 def test_fullsize_reference_vectors(built_lib, case):
     """The CUDA path against frames decoded by the LIVE reference at BASELINE's full code sizes."""
     from conftest import fullsize_tables, load_fullsize
@@ -236,7 +236,8 @@ def test_fullsize_reference_vectors(built_lib, case):
         assert np.array_equal(p.cpu().numpy(), z["posterior"])
     elif case.startswith("rcq"):
         dec = L.RCQMinSumDecoder(code, 3, 8, [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)], max_iterations=T,
-                                 layered=case.startswith("rcq_layered"))   # layered: the software-pipelined walk
+                                 layered=case.startswith("rcq_layered"))   # layered: the software-pipelined walk on the chain
+                                                                           # code, the level-parallel kernel on the QC code
         b, s, i = dec.decode(x)
         assert np.array_equal(s.cpu().numpy().astype(bool), z["success"])
     else:

@@ -197,7 +197,7 @@ def test_next_rows_match_live_reference(stem, case, impl):
         assert np.array_equal(res.success, g["success"])
 
 
-@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4"])
+@pytest.mark.parametrize("case", ["n2d2_dvbs2", "rcq_dvbs2", "wrcq1_qc", "rcq_layered_dvbs2_s4", "rcq_layered_qc"])
 def test_oracle_reproduces_fullsize_reference_vectors(case):
     """BASELINE's full code sizes: frames decoded by the LIVE reference (minutes per frame,
     tests/golden/make_golden_fullsize.py) against the C port -- bits, iterations, success, posteriors bit for bit."""
