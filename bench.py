@@ -456,6 +456,8 @@ def kernel_roofline(prof, ab, Bp, steps, T, step_ms, kind, code_name):
         "vn_kernel": {"gbs": vn_gbs, "frac": vn_gbs / peak, "ms_total": prof["vn_ms"], "launches": prof["vn_launches"]},
         "cn_kernel": {"gbs": cn_gbs, "frac": cn_gbs / peak, "ms_total": prof["cn_ms"], "launches": prof["cn_launches"]},
         "other_ms_total": prof["other_ms"],
+        # device time of a step not covered by any of this library's kernels (host round trips, launch gaps)
+        "uncovered_ms_per_step": step_ms - (prof["vn_ms"] + prof["cn_ms"] + prof["other_ms"]) / steps,
         "whole_step": {"gbs": step_bytes / (step_ms * 1e-3) / 1e9, "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
                        "bytes_per_frame_iter": ab["frame_iter"]},
     }
@@ -614,7 +616,8 @@ def config_legs(rig, L, args):
                "avg_iterations": rec["avg_iterations"],
                "roofline": {"cn_frac": r["cn_kernel"]["frac"], "vn_frac": r["vn_kernel"]["frac"],
                             "whole_step_frac": r["whole_step"]["frac"], "bytes_per_frame_iter": r["whole_step"]["bytes_per_frame_iter"],
-                            "peak_gbs": r["peak"]}}
+                            "other_kernels_ms_per_step": r["other_ms_total"] / rec["steps"],
+                            "uncovered_ms_per_step": r.get("uncovered_ms_per_step"), "peak_gbs": r["peak"]}}
         del llr, out
         release(eng)
         del dec, eng
