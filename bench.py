@@ -207,22 +207,49 @@ def cpu_leg(code, kind, seconds, threads, posterior):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polling every 200 ms (the profiling recipe's clocks line) in a child process.  Its START-UP stalls the
+    GPU once for 10-100 ms (measured: a 90 ms step took 97-189 ms right after the process came up,
+    profiles/r02aj_sampler_effect.log), so it is started well before the timed region and only the samples taken between
+    `mark()` and `stop()` -- the timed region -- are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
         self.idx = gpu_index
+        self.t_mark = None
 
     def start(self):
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "200", "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def wait_first_sample(self, timeout=8.0):
+        """Block until the child has written a sample: its start-up (and the GPU stall that comes with it) is over."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout and os.path.getsize(self.tmp.name) == 0 and self.proc.poll() is None:
+            time.sleep(0.05)
+
+    def mark(self):
+        self.t_mark = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
+        t_end = time.time()
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.proc is None:
             return out
@@ -233,19 +260,26 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.tmp.read().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+        lines = self.tmp.read().splitlines()
+        for windowed in (True, False):     # (no sample inside the window -- clock skew, a very short region: use them all)
+            sm, mx, reasons, power = [], [], set(), []
+            for line in lines:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 10:
+                    continue
+                ts = self._stamp(f[0])
+                if windowed and self.t_mark is not None and ts is not None and not (self.t_mark - 0.2 <= ts <= t_end + 0.2):
+                    continue
+                try:
+                    sm.append(float(f[2])); mx.append(float(f[3])); power.append(float(f[4]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                break
         os.unlink(self.tmp.name)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
@@ -473,6 +507,8 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     torch = rig.torch
     g = code.graph
     gc.collect()                       # (buffers of an earlier leg freed inside the timed region would stall it)
+    if sampler is not None:
+        sampler.start()                # its start-up stalls the GPU once: long before the timed region
     dec = build_decoder(L, code, kind)
     eng = dec._engine(rig.local_rank)
     eng.reserve(B)
@@ -484,6 +520,8 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     def step():
         return eng.decode_device(llr, want_posterior=posterior)
 
+    if sampler is not None:
+        sampler.wait_first_sample()
     for _ in range(warmup):
         out = step()
     if min_timed_ms > 0:
@@ -502,7 +540,7 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     # per-launch CUDA events for the check / variable node kernels (a one-launch on-chip decode has nothing to split)
     eng.profile_mode(0 if on_chip else 1)
     if sampler is not None:
-        sampler.start()
+        sampler.mark()
     ms, out = rig.timed_device(step, steps, 0)
     clocks = sampler.stop() if sampler is not None else None
     prof = eng.profile_read(reset=True)

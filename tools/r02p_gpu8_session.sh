@@ -1,3 +1,3 @@
 # 8-GPU bench (device-resident, e2e through one host, Monte-Carlo sweep + parity)
 set -x
-( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02p_bench_8gpu.json 2> gpurun_out/r02p_bench_8gpu.err ) 2> gpurun_out/r02p_bench_8gpu.time; tail -3 gpurun_out/r02p_bench_8gpu.time; tail -5 gpurun_out/r02p_bench_8gpu.err
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29651 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02ah_bench_8gpu.json 2> gpurun_out/r02ah_bench_8gpu.err ) 2> gpurun_out/r02ah_bench_8gpu.time; tail -3 gpurun_out/r02ah_bench_8gpu.time; tail -5 gpurun_out/r02ah_bench_8gpu.err
