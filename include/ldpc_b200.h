@@ -140,6 +140,11 @@ int ldpc_decoder_reserve(ldpc_decoder *d, int64_t frames);
  * _host:   all pointers are host pointers (pinned for full speed); the call copies in, decodes and
  *          copies out through an internal chunked double-buffered pipeline and returns when the
  *          outputs are valid.
+ * Which kernels run is the library's business and never changes a result: codes of a few hundred bytes of state per
+ * frame decode in ONE launch with their messages in shared memory (ldpc_small.cu); float32 batches of at most a few
+ * waves of thread blocks decode one block per frame, messages in that block's shared memory (ldpc_resident.cu) -- both
+ * only enqueue, with or without early_stop; everything else runs one kernel per half iteration with the messages in
+ * HBM (ldpc_cn.cu / ldpc_vn.cu).  ldpc_decoder_profile_read says which path the calls took.
  */
 int ldpc_decode_device(ldpc_decoder *d, const void *llr, int64_t B, uint8_t *bits, void *posterior,
                        int32_t *iterations, uint8_t *success, void *stream);
