@@ -1,6 +1,8 @@
 // Check-node half iteration: cn_kernel (degree <= 8 unrolled in registers, > 64 streaming), cn_wide_kernel
 // (degree 9..64, bulk-async shared-memory row ring), cn_offset_kernel (offset min-sum rule) and the layered RCQ
 // schedule.  Layout and conventions: ldpc_kernel_common.cuh / DESIGN.md sections 3-4.
+#include <algorithm>
+
 #include "ldpc_cn_common.cuh"
 
 namespace ldpc {
@@ -1095,6 +1097,82 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
     }
 }
 
+
+// The level-parallel kernel with the check's posteriors STAGED in shared memory: a thread copies the dc row segments of
+// its four frames with per-thread cp.async (16 bytes each, all dc in flight at once, no register staging) into its own
+// column of the stage -- no barrier: a column belongs to one thread -- and both passes (min / parity, then the outputs)
+// read shared memory, so every posterior is read from global memory ONCE and written once: the `8 * E` bytes per
+// frame-iteration the schedule needs.  (The kernel above reads every row twice, eight and four rows in flight: 0.56
+// of that roofline on the (9472,8192)-shaped QC code, dc = 29 / 30; this one 0.65 at 32 768 frames and 0.71 at 131 072 --
+// bound by occupancy: a warp's stage is dc x 512 bytes, 12 warps per SM.)  Check degrees up to kLevelStageMaxDeg.
+constexpr int kLevelStageThreads = 128;
+constexpr int kLevelStageMaxDeg = 64;
+__global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel(float* __restrict__ P, const int64_t* __restrict__ chk_ptr,
+                                                                               const int32_t* __restrict__ chk_var,
+                                                                               const int32_t* __restrict__ level_chk, int n_checks,
+                                                                               const float* __restrict__ thr, int nth, int mono,
+                                                                               const uint8_t* __restrict__ done, int64_t Bp, int nfb) {
+    constexpr int V = 4;
+    extern __shared__ __align__(16) unsigned char level_stage[];   // [max dc][threads] 16-byte segments
+    __shared__ float s_thr[kMaxQuantLevels];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
+    __syncthreads();
+    const int fb = blockIdx.x % nfb;
+    const int group = blockIdx.x / nfb;
+    const int64_t f0 = ((int64_t)fb * blockDim.x + threadIdx.x) * V;
+    if (f0 >= Bp) return;
+    const uint32_t dmask = load_done_mask<V>(done, f0);
+    if (dmask == ((1u << V) - 1u)) return;   // (per lane: the stage needs no warp or block agreement)
+    Quantizer<0> qz;
+    qz.load(s_thr, nth, mono != 0);
+    const uint32_t stride = (uint32_t)Bp * (uint32_t)sizeof(float);
+    float* __restrict__ P0 = P + f0;
+    unsigned char* const col = level_stage + threadIdx.x * 16;
+    constexpr uint32_t kRow = kLevelStageThreads * 16;
+    for (int c = group * kLayerChunk; c < min(n_checks, (group + 1) * kLayerChunk); ++c) {
+        const int32_t i = __ldg(level_chk + c);
+        const int64_t e0 = __ldg(chk_ptr + i), e1 = __ldg(chk_ptr + i + 1);
+        const int dc = (int)(e1 - e0);
+        for (int k = 0; k < dc; ++k)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(col + k * kRow)),
+                         "l"(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride))
+                         : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        MinState<float, false> st[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].init();
+#pragma unroll 4
+        for (int k = 0; k < dc; ++k) {
+            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(col + k * kRow);
+#pragma unroll
+            for (int v = 0; v < V; ++v) st[v].push(x.v[v], k);
+        }
+        float va[V], vb[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (dc == 1) st[v].m2 = st[v].m1;
+            va[v] = s_thr[qz.index(st[v].m1)];
+            vb[v] = s_thr[qz.index(st[v].m2)];
+        }
+#pragma unroll 4
+        for (int k = 0; k < dc; ++k) {
+            const Pack<float, V> x = *reinterpret_cast<const Pack<float, V>*>(col + k * kRow);
+            Pack<float, V> out;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const bool is_min = fabsf(x.v[v]) == st[v].m1;
+                const float raw = is_min ? st[v].m2 : st[v].m1;
+                const float mag = is_min ? vb[v] : va[v];
+                // code sign bit = (sp * raw < 0): a negative product of the other signs AND a non-zero magnitude
+                const bool neg = (((st[v].par ^ __float_as_uint(x.v[v])) >> 31) != 0u) && (raw != 0.f);
+                // stopped frames keep their posteriors: the staged value is written back unchanged
+                out.v[v] = ((dmask >> v) & 1u) ? x.v[v] : __fadd_rn(x.v[v], neg ? -mag : mag);
+            }
+            *reinterpret_cast<Pack<float, V>*>(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride)) = out;
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1193,8 +1271,19 @@ cudaError_t launch_cn_offset(int dtype, const CnLaunch& p, cudaStream_t stream) 
 
 cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t* chk_var, const int32_t* level_chk,
                                  int n_checks, const float* thr, int nth, int mono, const uint8_t* done, int64_t Bp,
-                                 cudaStream_t stream) {
+                                 int max_dc, int staged, cudaStream_t stream) {
     if (n_checks <= 0) return cudaSuccess;
+    if (staged && max_dc <= kLevelStageMaxDeg) {
+        const size_t smem = (size_t)std::max(max_dc, 1) * kLevelStageThreads * 16;
+        cudaError_t e = cudaFuncSetAttribute(layered_level_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int64_t nfb = (Bp / 4 + kLevelStageThreads - 1) / kLevelStageThreads;
+        const int64_t grid = nfb * ((n_checks + kLayerChunk - 1) / kLayerChunk);
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        layered_level_stage_kernel<<<(unsigned)grid, kLevelStageThreads, smem, stream>>>(P, chk_ptr, chk_var, level_chk, n_checks, thr, nth,
+                                                                                          mono, done, Bp, (int)nfb);
+        return cudaGetLastError();
+    }
     const int threads = threads_for(Bp, 4);
     const int64_t nfb = (Bp / 4 + threads - 1) / threads;
     const int64_t grid = nfb * ((n_checks + kLayerChunk - 1) / kLayerChunk);

@@ -215,7 +215,7 @@ cudaError_t launch_layered_iter(float* P, const int64_t* chk_ptr, const int32_t*
 // the checks level_chk[0..n_checks) of ONE dependency level of that schedule, concurrently (they share no variable)
 cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t* chk_var, const int32_t* level_chk,
                                  int n_checks, const float* thr, int nth, int mono, const uint8_t* done, int64_t Bp,
-                                 cudaStream_t stream);
+                                 int max_dc, int staged, cudaStream_t stream);
 // the whole iteration in index order, software-pipelined (see layered_pipe_kernel): one record per NON-EMPTY check.
 // desc[k] bits 6..0: (distance << 3 | position) of the next reader this edge's new value is forwarded to, 0 = none;
 // ahead_mask bit k: input k is copied ahead from its posterior row (nobody forwards it).  Positions >= dc hold 0.
