@@ -750,7 +750,7 @@ int run_layered(ldpc_decoder* d, Workspace& ws, int64_t B, int64_t Bp, bool want
                                                   g->d_level_chk + g->level_ptr[(size_t)l],
                                                   g->level_ptr[(size_t)l + 1] - g->level_ptr[(size_t)l],
                                                   d->d_thr + (size_t)q * d->nth, d->nth, d->mono[q], ws.done, Bp, g->max_dc,
-                                                  (d->layered_stage && Bp >= 16384) ? 1 : 0, stream));   // (8192 frames: 955 K staged, 1035 K not)
+                                                  (d->layered_stage && Bp >= 16384) ? d->layered_stage : 0, stream));   // (8192 frames: 955 K staged, 1035 K not)
         } else if (d->layered_pipe && !g->lay_recs.empty()) {
             // chain-structured codes: one thread per frame walks the checks, inputs prefetched / forwarded on chip
             LAUNCH(K_CN, launch_layered_pipe(static_cast<float*>(ws.llrT), g->d_lay_recs, (int)g->lay_recs.size(),
@@ -1528,7 +1528,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* lp = getenv("LDPC_LAYERED_PIPE")) d->layered_pipe = atoi(lp) != 0;
     if (const char* lv = getenv("LDPC_LAYERED_V2_FRAMES")) d->layered_v2_frames = atoll(lv);
     if (const char* ll = getenv("LDPC_LAYERED_LEVELS")) d->layered_levels = atoi(ll) != 0;
-    if (const char* ls = getenv("LDPC_LAYERED_STAGE")) d->layered_stage = atoi(ls) != 0;  // tuning knob: frames per pipeline chunk
+    if (const char* ls = getenv("LDPC_LAYERED_STAGE")) d->layered_stage = std::min(2, std::max(0, atoi(ls)));  // tuning knob: frames per pipeline chunk
     if (const char* wr = getenv("LDPC_WIDE_RING")) d->wide_ring = atoi(wr) != 0; // A/B switch for the wide-check kernel
     if (const char* cp = getenv("LDPC_COMPACT")) d->compact = atoi(cp) != 0;      // A/B switch for frame compaction
     if (const char* fi = getenv("LDPC_FINE_ITEMS_MAX_FRAMES")) d->fine_items_max_frames = atoll(fi);

@@ -1107,13 +1107,15 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
 // bound by occupancy: a warp's stage is dc x 512 bytes, 12 warps per SM.)  Check degrees up to kLevelStageMaxDeg.
 constexpr int kLevelStageThreads = 128;
 constexpr int kLevelStageMaxDeg = 64;
+template <int V>
 __global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel(float* __restrict__ P, const int64_t* __restrict__ chk_ptr,
                                                                                const int32_t* __restrict__ chk_var,
                                                                                const int32_t* __restrict__ level_chk, int n_checks,
                                                                                const float* __restrict__ thr, int nth, int mono,
                                                                                const uint8_t* __restrict__ done, int64_t Bp, int nfb) {
-    constexpr int V = 4;
-    extern __shared__ __align__(16) unsigned char level_stage[];   // [max dc][threads] 16-byte segments
+    static_assert(V == 2 || V == 4, "frames per lane");
+    constexpr int SEG = 4 * V;                                     // bytes of a lane's row segment
+    extern __shared__ __align__(16) unsigned char level_stage[];   // [max dc][threads] segments
     __shared__ float s_thr[kMaxQuantLevels];
     for (int i = threadIdx.x; i < nth; i += blockDim.x) s_thr[i] = thr[i];
     __syncthreads();
@@ -1127,16 +1129,19 @@ __global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel
     qz.load(s_thr, nth, mono != 0);
     const uint32_t stride = (uint32_t)Bp * (uint32_t)sizeof(float);
     float* __restrict__ P0 = P + f0;
-    unsigned char* const col = level_stage + threadIdx.x * 16;
-    constexpr uint32_t kRow = kLevelStageThreads * 16;
+    unsigned char* const col = level_stage + threadIdx.x * SEG;
+    constexpr uint32_t kRow = kLevelStageThreads * SEG;
     for (int c = group * kLayerChunk; c < min(n_checks, (group + 1) * kLayerChunk); ++c) {
         const int32_t i = __ldg(level_chk + c);
         const int64_t e0 = __ldg(chk_ptr + i), e1 = __ldg(chk_ptr + i + 1);
         const int dc = (int)(e1 - e0);
-        for (int k = 0; k < dc; ++k)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(col + k * kRow)),
-                         "l"(row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride))
-                         : "memory");
+        for (int k = 0; k < dc; ++k) {
+            const float* src = row_at(P0, (uint32_t)__ldg(chk_var + e0 + k), stride);
+            if constexpr (V == 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(col + k * kRow)), "l"(src) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(col + k * kRow)), "l"(src) : "memory");
+        }
         asm volatile("cp.async.wait_all;" ::: "memory");
         MinState<float, false> st[V];
 #pragma unroll
@@ -1274,14 +1279,17 @@ cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t
                                  int max_dc, int staged, cudaStream_t stream) {
     if (n_checks <= 0) return cudaSuccess;
     if (staged && max_dc <= kLevelStageMaxDeg) {
-        const size_t smem = (size_t)std::max(max_dc, 1) * kLevelStageThreads * 16;
-        cudaError_t e = cudaFuncSetAttribute(layered_level_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // staged == 2 (LDPC_LAYERED_STAGE=2, tuning): two frames per lane -- half the stage per warp, twice the warps per SM;
+        // measured slower (131 072 frames: 1.40 M frames/s against 1.55 M), so occupancy is not what bounds the kernel
+        const int V = staged == 2 ? 2 : 4;
+        const size_t smem = (size_t)std::max(max_dc, 1) * kLevelStageThreads * 4 * V;
+        auto kern = V == 2 ? layered_level_stage_kernel<2> : layered_level_stage_kernel<4>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        const int64_t nfb = (Bp / 4 + kLevelStageThreads - 1) / kLevelStageThreads;
+        const int64_t nfb = (Bp / V + kLevelStageThreads - 1) / kLevelStageThreads;
         const int64_t grid = nfb * ((n_checks + kLayerChunk - 1) / kLayerChunk);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        layered_level_stage_kernel<<<(unsigned)grid, kLevelStageThreads, smem, stream>>>(P, chk_ptr, chk_var, level_chk, n_checks, thr, nth,
-                                                                                          mono, done, Bp, (int)nfb);
+        kern<<<(unsigned)grid, kLevelStageThreads, smem, stream>>>(P, chk_ptr, chk_var, level_chk, n_checks, thr, nth, mono, done, Bp, (int)nfb);
         return cudaGetLastError();
     }
     const int threads = threads_for(Bp, 4);

@@ -8,7 +8,7 @@ code = L.codes.qc_shaped(max_iterations=10)
 E = code.graph.E
 for B in (8192, 32768, 131072):
     llr = L.awgn_llr(code.n, B, 2.0, seed=1, llr_sign=-1)
-    for stage in ("0", "1"):
+    for stage in ("0", "1", "2"):
         os.environ["LDPC_LAYERED_STAGE"] = stage
         dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=10, layered=True)
         for _ in range(2):
