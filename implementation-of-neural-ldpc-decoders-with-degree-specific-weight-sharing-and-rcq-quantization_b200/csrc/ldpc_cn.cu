@@ -922,7 +922,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
-    static_assert(BYTES == 4 || BYTES == 8, "cp.async.ca size");
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async.ca size");
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
 }
 
@@ -1103,8 +1103,8 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
 // column of the stage -- no barrier: a column belongs to one thread -- and both passes (min / parity, then the outputs)
 // read shared memory, so every posterior is read from global memory ONCE and written once: the `8 * E` bytes per
 // frame-iteration the schedule needs.  (The kernel above reads every row twice, eight and four rows in flight: 0.56
-// of that roofline on the (9472,8192)-shaped QC code, dc = 29 / 30; this one 0.65 at 32 768 frames and 0.71 at 131 072 --
-// bound by occupancy: a warp's stage is dc x 512 bytes, 12 warps per SM.)  Check degrees up to kLevelStageMaxDeg.
+// of that roofline on the (9472,8192)-shaped QC code, dc = 29 / 30; this one 0.65 at 32 768 frames and 0.73 at 131 072.)
+// Check degrees up to kLevelStageMaxDeg.
 constexpr int kLevelStageThreads = 128;
 constexpr int kLevelStageMaxDeg = 64;
 template <int V>
@@ -1314,11 +1314,12 @@ cudaError_t launch_layered_pipe_v(float* P, const LayerRec* recs, int n_checks, 
 }
 }  // namespace
 
-// frames_per_thread: 1 or 2 (Bp must be a multiple of kLayerThreads, which the workspace padding guarantees)
+// frames_per_thread: 1, 2 or 4 (Bp must be a multiple of kLayerThreads, which the workspace padding guarantees)
 cudaError_t launch_layered_pipe(float* P, const LayerRec* recs, int n_checks, const float* thr, int nth, int mono,
                                 const uint8_t* done, int64_t Bp, int frames_per_thread, cudaStream_t stream) {
     if (n_checks <= 0) return cudaSuccess;
     if (Bp % kLayerThreads != 0) return cudaErrorInvalidValue;
+    if (frames_per_thread == 4) return launch_layered_pipe_v<4>(P, recs, n_checks, thr, nth, mono, done, Bp, stream);
     return frames_per_thread == 2 ? launch_layered_pipe_v<2>(P, recs, n_checks, thr, nth, mono, done, Bp, stream)
                                   : launch_layered_pipe_v<1>(P, recs, n_checks, thr, nth, mono, done, Bp, stream);
 }
