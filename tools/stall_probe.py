@@ -17,8 +17,9 @@ stop = False
 
 def spawner():
     while not stop:
-        subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        time.sleep(0.25)
+        subprocess.run(["nvidia-smi", "--query-gpu=index,clocks.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.sw_power_cap",
+                        "--format=csv,noheader"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        time.sleep(0.4)
 
 
 for early in (True, False):
