@@ -18,7 +18,9 @@
 //                   g c2v_t[e']       += alpha_t[j] * (G - g v2c_{t+1}[e']),  G = sum_e g v2c_{t+1}[e]
 // Lanes over frames like every other kernel here; weight gradients are reduced over the warp, accumulated over the nodes
 // of a work item that share a column, and added atomically to one of `parts` spread copies (folded at the end).
-// (Degree-templated bodies with the rows of a node held in registers were tried: 96-128 registers, 22 -> 33 ms.)
+// (Degree-templated bodies were tried twice -- rows of a node held in registers: 96-128 registers, 22 -> 33 ms; rows re-read
+// from L1 in every pass, unrolled, with and without a register cap: 30-35 ms.  ncu on the run-time-degree kernels below: the
+// variable side runs at the HBM roofline (6.5 TB/s), the check side is issue-bound (74 % of issue slots, 3.1 TB/s).)
 #include "ldpc_cn_common.cuh"
 
 namespace ldpc {
