@@ -439,6 +439,23 @@ class Rig:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed_device_steps(self, fn, steps):
+        """`steps` calls with a CUDA event between consecutive calls: (median, mean) device time per step in ms, each the
+        max over ranks, and the last result.  The median is what a step costs; the mean also carries whatever stalled
+        the GPU from outside during the region (measurement hygiene)."""
+        torch = self.torch
+        self.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        out = None
+        for k in range(steps):
+            out = fn()
+            ev[k + 1].record()
+        self.barrier()
+        per = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(steps))
+        median = per[len(per) // 2] if len(per) % 2 else 0.5 * (per[len(per) // 2 - 1] + per[len(per) // 2])
+        return self.max_over_ranks(median), self.max_over_ranks(ev[0].elapsed_time(ev[steps]) / steps), out
+
     def timed_device(self, fn, steps, warmup):
         """W warm-ups, then K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over
         ranks.  Returns (ms per step, last result)."""
@@ -541,14 +558,21 @@ def device_leg(rig, L, code, code_name, kind, B, steps, warmup, posterior, sampl
     eng.profile_mode(0 if on_chip else 1)
     if sampler is not None:
         sampler.mark()
-    ms, out = rig.timed_device(step, steps, 0)
+    ms_mean = None
+    if min_timed_ms > 0:     # configuration legs: per-step events, the median is reported (the headline: exactly K steps, mean)
+        ms, ms_mean, out = rig.timed_device_steps(step, steps)
+    else:
+        ms, out = rig.timed_device(step, steps, 0)
     clocks = sampler.stop() if sampler is not None else None
     prof = eng.profile_read(reset=True)
     eng.profile_mode(0)
     fps = rig.world * B * steps / (ms * steps / 1e3)
     ab = algorithmic_bytes(code, kind, posterior)
     roof = kernel_roofline(prof, ab, prof["frames_padded"], steps, T_ITERS, ms, kind, code_name)
-    rec = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "avg_iterations": avg_iters, "steps": steps,
+    if ms_mean is not None and "uncovered_ms_per_step" in roof:   # of the whole region, stalls included
+        roof["uncovered_ms_per_step"] = ms_mean - (prof["vn_ms"] + prof["cn_ms"] + prof["other_ms"]) / steps
+    rec = {"frames_per_s": fps, "info_gbps": fps * code.k / 1e9, "ms_per_step": ms, "ms_per_step_mean": ms_mean,
+           "avg_iterations": avg_iters, "steps": steps,
            "edge_msgs_per_s": fps * T_ITERS * 2 * g.E, "launches": int(prof["launches"]), "roofline": roof}
     return rec, dec, eng, llr, out, clocks
 
@@ -651,7 +675,9 @@ def config_legs(rig, L, args):
         leg = {"config": tag, "workload": workload_name(kind, code_name), "frames_per_gpu": B,
                "call": "forward()" if posterior else "decode()", "steps": rec["steps"], "warmup": warmup,
                "frames_per_s": rec["frames_per_s"], "info_gbps": rec["info_gbps"], "ms_per_step": rec["ms_per_step"],
-               "avg_iterations": rec["avg_iterations"],
+               "timing": "median of per-step CUDA-event times, max over ranks (ms_per_step_mean: the whole region / steps, "
+                         "which also carries stalls from outside the process)",
+               "ms_per_step_mean": rec["ms_per_step_mean"], "avg_iterations": rec["avg_iterations"],
                "roofline": {"cn_frac": r["cn_kernel"]["frac"], "vn_frac": r["vn_kernel"]["frac"],
                             "whole_step_frac": r["whole_step"]["frac"], "bytes_per_frame_iter": r["whole_step"]["bytes_per_frame_iter"],
                             "other_kernels_ms_per_step": r["other_ms_total"] / rec["steps"],
