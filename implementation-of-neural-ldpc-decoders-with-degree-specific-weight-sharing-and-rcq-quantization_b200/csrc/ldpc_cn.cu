@@ -1104,7 +1104,9 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
 // read shared memory, so every posterior is read from global memory ONCE and written once: the `8 * E` bytes per
 // frame-iteration the schedule needs.  (The kernel above reads every row twice, eight and four rows in flight: 0.56
 // of that roofline on the (9472,8192)-shaped QC code, dc = 29 / 30; this one 0.65 at 32 768 frames and 0.73 at 131 072.)
-// Check degrees up to kLevelStageMaxDeg.
+// Check degrees up to kLevelStageMaxDeg.  (Packing the hard decisions of the written posteriors here as well -- to save the
+// pass over all n rows per iteration -- was tried and lost, 1.41 -> 1.17 M frames/s: four 16-byte partial-sector stores
+// per edge and warp, dv times per variable, cost more than one 4n-byte pass.)
 constexpr int kLevelStageThreads = 128;
 constexpr int kLevelStageMaxDeg = 64;
 template <int V>
