@@ -141,3 +141,113 @@ def test_backward_needs_its_own_forward(built_lib):
     _, p3, _ = dec(x)
     p3.sum().backward()
     assert not dec._beta_table.grad[2:].any() and dec._beta_table.grad[:2].any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The backward kernels against torch.autograd on a plain-PyTorch restatement of the reference's forward pass
+# (neural_2d_decoder.py:133-225, neural_minsum_decoder.py:58-150: the same torch ops -- sign, abs, argmin, the
+# inf-masked torch.min, prod of the other signs, sum -- on sparse neighbour lists), one frame at a time on the CPU.
+# Inputs on a coarse grid, so exact zeros (three-valued sign), ties of both minima and a degree-1 check all occur:
+# the cases the three-pass check-side kernel hands to its general form.
+# ---------------------------------------------------------------------------------------------------------------
+def _autograd_forward(H, llr, weights, kind, T):
+    m, n = H.shape
+    rows = [np.nonzero(H[i])[0] for i in range(m)]
+    cols = [np.nonzero(H[:, j])[0] for j in range(n)]
+    dcs, dvs = H.sum(1), H.sum(0)
+    Hf = torch.tensor(H, dtype=torch.float32)
+
+    def beta(t, i, j):
+        if kind == "nnms":
+            return weights[f"beta_weights.iter_{t}_c{i}_v{j}"]
+        if kind == "n2d1":
+            return weights[f"beta_weights.iter_{t}_dc{dcs[i]}_dv{dvs[j]}"]
+        if kind in ("n2d2", "n2d3"):
+            return weights[f"beta_weights.iter_{t}_dc{dcs[i]}"]
+        return torch.tensor(0.7)
+
+    def alpha(t, j):
+        if kind in ("n2d2", "n2d4"):
+            return weights[f"alpha_weights.iter_{t}_dv{dvs[j]}"]
+        return torch.tensor(1.0)
+
+    v2c = {(j, i): llr[j] for j in range(n) for i in cols[j]}
+    for t in range(T):
+        c2v = {}
+        for i in range(m):
+            nb = rows[i]
+            if len(nb) == 0:
+                continue
+            inc = torch.stack([v2c[(j, i)] for j in nb])
+            signs, mags = torch.sign(inc), torch.abs(inc)
+            k0 = torch.argmin(mags)
+            mn = mags[k0]
+            if len(nb) > 1:
+                tmp = mags.clone()
+                tmp[k0] = float("inf")
+                mn2 = torch.min(tmp)
+            else:
+                mn2 = mn
+            for k, j in enumerate(nb):
+                sp = torch.prod(signs[torch.arange(len(nb)) != k])
+                c2v[(i, j)] = beta(t, i, j) * (mn2 if k == int(k0) else mn) * sp
+        for j in range(n):
+            for i in cols[j]:
+                others = [c2v[(i2, j)] for i2 in cols[j] if i2 != i]
+                s = torch.sum(torch.stack(others)) if others else torch.tensor(0.0)
+                v2c[(j, i)] = llr[j] + alpha(t, j) * s
+        post = torch.stack([llr[j] + (torch.sum(torch.stack([c2v[(i, j)] for i in cols[j]])) if len(cols[j]) else 0.0)
+                            for j in range(n)])
+        bits = (post < 0).float()
+        if float(torch.sum(torch.matmul(Hf, bits) % 2)) == 0:
+            return post, t + 1
+    return post, T
+
+
+def _grid_case(seed):
+    rng = np.random.default_rng(seed)
+    m, n = 10, 20
+    H = np.zeros((m, n), dtype=np.int64)
+    H[0, 3] = 1                                            # a degree-1 check
+    H[1, rng.choice(n, 11, replace=False)] = 1             # a wide one
+    for i in range(2, m):
+        H[i, rng.choice(n, int(rng.integers(2, 7)), replace=False)] = 1
+    for j in range(n):                                     # no isolated variables
+        if not H[:, j].any():
+            H[int(rng.integers(1, m)), j] = 1
+    llr = (rng.integers(0, 9, size=(24, n)) * 0.5).astype(np.float32)    # zeros and equal magnitudes everywhere
+    llr *= np.where(rng.random((24, n)) < 0.12, -1.0, 1.0).astype(np.float32)   # a few wrong signs: frames stop at different iterations
+    return H, llr
+
+
+@pytest.mark.parametrize("kind", ["n2d2", "n2d1", "n2d3", "n2d4", "nnms"])
+def test_backward_against_torch_autograd_with_zeros_and_ties(built_lib, kind):
+    L = built_lib
+    T = 4
+    H, llr_np = _grid_case(11)
+    code = L.LDPCCode(H.shape[1], H.shape[1] - H.shape[0], H, max_iterations=T)
+    dec = L.NeuralMinSumDecoder(code, T) if kind == "nnms" else L.Neural2DMinSumDecoder(code, int(kind[-1]), T)
+    g = torch.Generator().manual_seed(5)
+    sd = {k: (0.4 + 0.6 * torch.rand(1, generator=g)) * (-1.0 if i % 7 == 3 else 1.0) for i, k in enumerate(dec.state_dict())}
+    dec.load_state_dict(sd)
+    dec.differentiable = True
+    keys = list(sd)
+    # plain PyTorch, frame by frame
+    weights = {k: v.clone().squeeze(0).requires_grad_(True) for k, v in sd.items()}
+    posts, its = [], []
+    for f in range(llr_np.shape[0]):
+        p, it = _autograd_forward(H, torch.from_numpy(llr_np[f]), weights, kind, T)
+        posts.append(p)
+        its.append(it)
+    want_post = torch.stack(posts)
+    F.binary_cross_entropy_with_logits(-want_post, torch.zeros_like(want_post)).backward()
+    want = np.array([0.0 if weights[k].grad is None else float(weights[k].grad) for k in keys], dtype=np.float32)
+    assert len(set(its)) > 1 and np.abs(want).max() > 1e-3
+    # the kernels
+    _, post, iters = dec(torch.from_numpy(llr_np).cuda())
+    assert iters.cpu().tolist() == its
+    np.testing.assert_allclose(post.detach().cpu().numpy(), want_post.detach().numpy(), rtol=1e-6, atol=1e-6)
+    F.binary_cross_entropy_with_logits(-post, torch.zeros_like(post)).backward()
+    got = _by_key(dec, keys, {"beta_weights": dec._beta_table.grad if dec._beta_table is not None else None,
+                              "alpha_weights": dec._alpha_table.grad if dec._alpha_table is not None else None})
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
