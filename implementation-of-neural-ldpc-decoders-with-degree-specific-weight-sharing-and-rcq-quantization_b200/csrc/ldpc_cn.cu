@@ -895,17 +895,12 @@ __device__ __forceinline__ void layer_step(const LayerRecRegs& r, float* __restr
         for (int v = 0; v < V; ++v) {
             const bool is_min = fabsf(x[k].v[v]) == st[v].m1;
             const uint32_t rec = (is_min ? a2[v] : a1[v]) ^ ((st[v].par ^ __float_as_uint(x[k].v[v])) & (is_min ? g2[v] : g1[v]));
-            out.v[v] = __fadd_rn(x[k].v[v], __uint_as_float(rec));
+            // stopped frames keep their posteriors: the value they came in with goes back out (V > 1: one vector store
+            // per edge whatever the mix of running and stopped frames in the lane, no per-frame store branches)
+            out.v[v] = (V == 1 || ((live >> v) & 1u)) ? __fadd_rn(x[k].v[v], __uint_as_float(rec)) : x[k].v[v];
         }
-        // stopped frames keep their posteriors
         float* row = row_at(Pf, r.var(k), stride);
-        if (V == 1 || live == (1u << V) - 1u) {
-            if (live) *reinterpret_cast<Pack<float, V>*>(row) = out;
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if ((live >> v) & 1u) row[v] = out.v[v];
-        }
+        if (live) *reinterpret_cast<Pack<float, V>*>(row) = out;
         const uint32_t fwd = r.fwd(k);   // next reader within the ring: (distance << 3) | position
         if (fwd) *reinterpret_cast<Pack<float, V>*>(col + ((sbase + (fwd << 9)) & (kLayerRingBytes - 1))) = out;
     }
@@ -1109,6 +1104,13 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
 // per edge and warp, dv times per variable, cost more than one 4n-byte pass.)
 constexpr int kLevelStageThreads = 128;
 constexpr int kLevelStageMaxDeg = 64;
+#ifndef LDPC_LEVEL_CHUNK
+#define LDPC_LEVEL_CHUNK 4      // checks of a level per CTA of the staged kernel (8 and 16 measured slower, with or without the prefetch)
+#endif
+#ifndef LDPC_LEVEL_PREFETCH
+#define LDPC_LEVEL_PREFETCH 1   // the rows of the CTA's next check are asked into L2 while the current one is staged (+2-6 %)
+#endif
+constexpr int kLevelStageChunk = LDPC_LEVEL_CHUNK;
 template <int V>
 __global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel(float* __restrict__ P, const int64_t* __restrict__ chk_ptr,
                                                                                const int32_t* __restrict__ chk_var,
@@ -1133,7 +1135,8 @@ __global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel
     float* __restrict__ P0 = P + f0;
     unsigned char* const col = level_stage + threadIdx.x * SEG;
     constexpr uint32_t kRow = kLevelStageThreads * SEG;
-    for (int c = group * kLayerChunk; c < min(n_checks, (group + 1) * kLayerChunk); ++c) {
+    const int c_end = min(n_checks, (group + 1) * kLevelStageChunk);
+    for (int c = group * kLevelStageChunk; c < c_end; ++c) {
         const int32_t i = __ldg(level_chk + c);
         const int64_t e0 = __ldg(chk_ptr + i), e1 = __ldg(chk_ptr + i + 1);
         const int dc = (int)(e1 - e0);
@@ -1144,6 +1147,14 @@ __global__ void __launch_bounds__(kLevelStageThreads) layered_level_stage_kernel
             else
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(col + k * kRow)), "l"(src) : "memory");
         }
+#if LDPC_LEVEL_PREFETCH
+        if (c + 1 < c_end) {   // (checks of a level touch disjoint variables: nothing writes these rows in between)
+            const int32_t i2 = __ldg(level_chk + c + 1);
+            const int64_t n0 = __ldg(chk_ptr + i2), n1 = __ldg(chk_ptr + i2 + 1);
+            for (int64_t e = n0; e < n1; ++e)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row_at(P0, (uint32_t)__ldg(chk_var + e), stride)));
+        }
+#endif
         asm volatile("cp.async.wait_all;" ::: "memory");
         MinState<float, false> st[V];
 #pragma unroll
@@ -1289,7 +1300,7 @@ cudaError_t launch_layered_level(float* P, const int64_t* chk_ptr, const int32_t
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int64_t nfb = (Bp / V + kLevelStageThreads - 1) / kLevelStageThreads;
-        const int64_t grid = nfb * ((n_checks + kLayerChunk - 1) / kLayerChunk);
+        const int64_t grid = nfb * ((n_checks + kLevelStageChunk - 1) / kLevelStageChunk);
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         kern<<<(unsigned)grid, kLevelStageThreads, smem, stream>>>(P, chk_ptr, chk_var, level_chk, n_checks, thr, nth, mono, done, Bp, (int)nfb);
         return cudaGetLastError();

@@ -1,14 +1,16 @@
 """Level-parallel layered RCQ on the (9472,8192)-shaped QC code: staged in shared memory against the unstaged kernel.
-    python tools/layered_qc_probe.py"""
+    python tools/layered_qc_probe.py [sizes,comma-separated [stages]]"""
 import os, sys, torch
 sys.path.insert(0, ".")
 import ldpc_b200 as L
 qp = [(3.0, 1.3), (5.0, 1.3), (7.0, 1.3)]
 code = L.codes.qc_shaped(max_iterations=10)
 E = code.graph.E
-for B in (8192, 32768, 131072):
+SIZES = tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (8192, 32768, 131072)
+STAGES = tuple(sys.argv[2].split(",")) if len(sys.argv) > 2 else ("0", "1", "2")
+for B in SIZES:
     llr = L.awgn_llr(code.n, B, 2.0, seed=1, llr_sign=-1)
-    for stage in ("0", "1", "2"):
+    for stage in STAGES:
         os.environ["LDPC_LAYERED_STAGE"] = stage
         dec = L.RCQMinSumDecoder(code, 3, 8, qp, max_iterations=10, layered=True)
         for _ in range(2):
