@@ -625,6 +625,7 @@ struct ldpc_decoder {
     int speculate = 0;            // LDPC_SPECULATE: 1 always / -1 while no frame has stopped yet / 0 (default) never keep a second
                                   // span in flight while the host waits for a checkpoint (see job_top_up)
     int post_mode = 0;            // LDPC_POST_MODE: 0 adaptive, 1 posterior rows refreshed every iteration, 2 written on stop
+    int train_general = 0;        // LDPC_TRAIN_GENERAL=1: every check takes the general four-pass backward form (A/B of the three-pass one)
     int64_t stat_compactions = 0, stat_early_exits = 0;
     // posterior training: the forward pass keeps every iteration's messages for the backward pass
     struct TrainCtx {
@@ -1540,6 +1541,7 @@ extern "C" int ldpc_decoder_create(ldpc_graph* g, const ldpc_decoder_config* cfg
     if (const char* cf = getenv("LDPC_COMPACT_PERCENT")) d->compact_percent = std::min(95, std::max(5, atoi(cf)));
     if (const char* cs = getenv("LDPC_CHECKPOINT_STEP")) d->checkpoint_step = std::max(1, atoi(cs));
     if (const char* sp = getenv("LDPC_SPECULATE")) d->speculate = atoi(sp);
+    if (const char* tg = getenv("LDPC_TRAIN_GENERAL")) d->train_general = atoi(tg) != 0;
     if (const char* sm = getenv("LDPC_SMALL")) d->use_small = atoi(sm) != 0;
     if (const char* rs = getenv("LDPC_RESIDENT")) d->use_resident = atoi(rs) != 0;
     if (const char* pm = getenv("LDPC_POST_MODE")) d->post_mode = std::min(2, std::max(0, atoi(pm)));
@@ -2066,6 +2068,7 @@ extern "C" int ldpc_train_backward(ldpc_decoder* d, const float* grad_posterior,
     p.beta_parts = beta_parts;
     p.alpha_parts = alpha_parts;
     p.T = d->T;
+    p.force_general = d->train_general;
     for (int t = d->T - 1; t >= 0; --t) {
         p.v2c_t = tc.v2c_hist + (size_t)t * slice;
         p.c2v_t = tc.c2v_hist + (size_t)t * slice;

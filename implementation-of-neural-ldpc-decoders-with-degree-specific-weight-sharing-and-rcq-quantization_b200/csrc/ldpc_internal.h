@@ -199,6 +199,7 @@ struct TrainBwd {
     // spread over `parts` copies (a power of two; block b adds to copy b & (parts - 1)) that a last kernel folds.
     int beta_parts, alpha_parts;
     int T;
+    int force_general;          // tuning / test knob: the check side runs its general four-pass form for every check
 };
 cudaError_t launch_train_fold(const float* parts, float* out, int n_parts, int64_t count, cudaStream_t stream);
 cudaError_t launch_train_bwd_vn(const TrainBwd& p, int t, cudaStream_t stream);

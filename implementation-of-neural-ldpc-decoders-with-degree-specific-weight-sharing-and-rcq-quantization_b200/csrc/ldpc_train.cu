@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kTrainThreads, LDPC_TRAIN_CN_MINCTAS) train_bw
     const size_t check_step = (size_t)dc * row_step;
     for (int c = 0; c < it.count; ++c, off0 += check_step) {
         const int64_t slot0 = (int64_t)it.first_slot + (int64_t)c * dc;
-        if (dc < 2) {
+        if (dc < 2 || p.force_general) {
             add_check(slot0, cn_bwd_check_general(p, t, src, slot0, dc, f0, on_mask, beta_t, g_beta, lane));
             continue;
         }

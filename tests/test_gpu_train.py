@@ -251,3 +251,34 @@ def test_backward_against_torch_autograd_with_zeros_and_ties(built_lib, kind):
     got = _by_key(dec, keys, {"beta_weights": dec._beta_table.grad if dec._beta_table is not None else None,
                               "alpha_weights": dec._alpha_table.grad if dec._alpha_table is not None else None})
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("kind", ["n2d2", "n2d1", "nnms"])
+def test_three_pass_check_backward_equals_general_form_at_full_size(built_lib, monkeypatch, kind):
+    """The (16200,7200)-shaped code, early stop on, 256 frames at 6 dB and 256 at 2 dB (frames stop at different
+    iterations, many run to the end): weight gradients of the three-pass check-side kernel against the general four-pass form taken for
+    every check (LDPC_TRAIN_GENERAL=1), which is the form the golden gradients of the live reference pinned first."""
+    L = built_lib
+    T = 8
+    code = L.codes.dvbs2_shaped(max_iterations=T)
+    llr = torch.cat([L.awgn_llr(code.n, 256, 6.0, seed=3, llr_sign=1), L.awgn_llr(code.n, 256, 2.0, seed=4, llr_sign=1)])
+    grads = []
+    for general in ("0", "1"):
+        monkeypatch.setenv("LDPC_TRAIN_GENERAL", general)
+        torch.manual_seed(1)
+        dec = L.NeuralMinSumDecoder(code, T) if kind == "nnms" else L.Neural2DMinSumDecoder(code, int(kind[-1]), T)
+        with torch.no_grad():
+            for p in dec.parameters():
+                p.uniform_(0.55, 0.95)
+        dec.differentiable = True
+        _, post, iters = dec(llr)
+        F.binary_cross_entropy_with_logits(-post, torch.zeros_like(post)).backward()
+        grads.append([None if p.grad is None else p.grad.detach().cpu().numpy().copy() for p in dec.parameters()])
+        if general == "0":
+            assert len(set(iters.cpu().tolist())) > 1
+        dec._engine(0).close()
+    assert any(g is not None and np.abs(g).max() > 1e-6 for g in grads[0])
+    for a, b in zip(*grads):
+        assert (a is None) == (b is None)
+        if a is not None:
+            np.testing.assert_allclose(a, b, rtol=2e-4, atol=1e-7 + 2e-4 * np.abs(b).max())
