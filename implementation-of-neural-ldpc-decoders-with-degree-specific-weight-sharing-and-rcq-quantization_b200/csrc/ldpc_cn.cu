@@ -1101,7 +1101,10 @@ __global__ void __launch_bounds__(kThreads) layered_level_kernel(float* __restri
 // of that roofline on the (9472,8192)-shaped QC code, dc = 29 / 30; this one 0.65 at 32 768 frames and 0.73 at 131 072.)
 // Check degrees up to kLevelStageMaxDeg.  (Packing the hard decisions of the written posteriors here as well -- to save the
 // pass over all n rows per iteration -- was tried and lost, 1.41 -> 1.17 M frames/s: four 16-byte partial-sector stores
-// per edge and warp, dv times per variable, cost more than one 4n-byte pass.)
+// per edge and warp, dv times per variable, cost more than one 4n-byte pass.  Tried again with a host-made flag on the ONE
+// edge per variable that enters its last level, so each decision word is written once per iteration and only iteration 0
+// keeps the separate pass: 1.59 -> 1.46 M frames/s at 131 072 frames, 1.49 -> 1.29 M at 32 768 -- the ballots need whole
+// warps and the extra predicates / registers slow the unfused path of the same kernel by 6 % as well.)
 constexpr int kLevelStageThreads = 128;
 constexpr int kLevelStageMaxDeg = 64;
 #ifndef LDPC_LEVEL_CHUNK
