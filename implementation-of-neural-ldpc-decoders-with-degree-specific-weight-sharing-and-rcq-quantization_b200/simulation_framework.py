@@ -25,6 +25,7 @@ from typing import Callable, Dict, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
+from . import _plotting
 from .ldpc_decoder import BasicMinSumDecoder, LDPCCode
 from .neural_2d_decoder import Neural2DMinSumDecoder, Neural2DOffsetMinSumDecoder
 from .neural_minsum_decoder import NeuralMinSumDecoder, NeuralOffsetMinSumDecoder
@@ -234,6 +235,19 @@ class LDPSimulator:
     def simulate_multiple_decoders(self, decoders: Dict[str, Union[Callable, torch.nn.Module]],
                                    code: LDPCCode) -> Dict[str, SimulationResult]:
         return {name: self.simulate_decoder(dec, code, name) for name, dec in decoders.items()}
+
+    # simulation_framework.py:218-336 -- the four figures (matplotlib imported on demand, see _plotting.py)
+    def plot_fer_curves(self, results: Dict[str, SimulationResult], save_path: Optional[str] = None, log_scale: bool = True):
+        _plotting.curves(results, "fer", save_path, log_scale)
+
+    def plot_ber_curves(self, results: Dict[str, SimulationResult], save_path: Optional[str] = None, log_scale: bool = True):
+        _plotting.curves(results, "ber", save_path, log_scale)
+
+    def plot_iteration_curves(self, results: Dict[str, SimulationResult], save_path: Optional[str] = None):
+        _plotting.curves(results, "iterations", save_path)
+
+    def plot_comprehensive_comparison(self, results: Dict[str, SimulationResult], save_path: Optional[str] = None):
+        _plotting.comparison(results, save_path)
 
     # simulation_framework.py:338-382 -- same JSON schema
     def save_results(self, results: Dict[str, SimulationResult], filename: str):

@@ -157,7 +157,9 @@ class PosteriorJointTrainer:
                 'gradient_norms': self.gradient_norms}
 
     def plot_training_history(self, save_path=None):
-        raise NotImplementedError("plotting is outside this package (matplotlib); the history lists hold the data")
+        from . import _plotting
+        _plotting.series([("Training Loss", "Loss", self.train_losses), ("Training Accuracy", "Accuracy", self.train_accuracies),
+                          ("Gradient Norm", "Gradient Norm", self.gradient_norms)], save_path)
 
 
 class GradientExplosionAnalyzer:
@@ -185,7 +187,8 @@ class GradientExplosionAnalyzer:
                 'max_gradient': np.max(gradient_magnitudes)}
 
     def plot_gradient_analysis(self, results, save_path=None):
-        raise NotImplementedError("plotting is outside this package (matplotlib); `results` holds the data")
+        from . import _plotting
+        _plotting.gradient_analysis(results, save_path)
 
 
 def create_dvbs2_code() -> LDPCCode:

@@ -207,3 +207,67 @@ def test_host_pipeline_chunk_plan(built_lib):
         if B > 4 * lim and lim >= 1024:
             assert p[-1] >= lim // 2, (B, chunk, p)                   # no small un-overlapped tail
             assert p[0] <= max(lim // 8, 128 * 8), (B, chunk, p)        # the kernels start early
+
+
+def test_figures_go_through_matplotlib_when_it_is_there(built_lib, monkeypatch):
+    """The plot methods of the simulator / trainer / analyzer (simulation_framework.py:218-336, training_framework.py:266-295,
+    354-377) import matplotlib on demand: a recording stand-in sees one curve per decoder and panel, the file name and
+    show(); without matplotlib the call is an ImportError, never a silent no-op."""
+    import sys
+    import types
+    L = built_lib
+    from ldpc_b200.training_framework import GradientExplosionAnalyzer, PosteriorJointTrainer, TrainingConfig
+    calls = []
+
+    class Axis:
+        def __getattr__(self, name):
+            return lambda *a, **k: calls.append((name, a, k))
+
+    plt = types.ModuleType("matplotlib.pyplot")
+
+    def subplots(rows=1, cols=1, **kw):
+        calls.append(("subplots", (rows, cols), kw))
+        grid = [[Axis() for _ in range(cols)] for _ in range(rows)]
+        return object(), (grid[0][0] if rows * cols == 1 else grid[0] if rows == 1 else grid)
+
+    plt.subplots = subplots
+    for fn in ("tight_layout", "savefig", "show"):
+        setattr(plt, fn, (lambda n: lambda *a, **k: calls.append((n, a, k)))(fn))
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+
+    res = {}
+    for name in ("A", "B"):
+        r = L.SimulationResult(name, [0.0, 1.0, 2.0])
+        for i in range(3):
+            r.add_result(i, 0.1 / (i + 1), 0.01 / (i + 1), 5.0 - i, 0.2, 100, 10 - i)
+        res[name] = r
+    sim = L.LDPSimulator(L.SimulationConfig(save_results=False))
+    sim.plot_fer_curves(res, save_path="fer.png")
+    assert [c[0] for c in calls].count("semilogy") == 2 and ("savefig", ("fer.png",), {"dpi": 300, "bbox_inches": "tight"}) in calls
+    assert calls[-1][0] == "show"
+    calls.clear()
+    sim.plot_ber_curves(res, log_scale=False)
+    sim.plot_iteration_curves(res)
+    assert [c[0] for c in calls].count("plot") == 4 and not any(c[0] in ("semilogy", "savefig") for c in calls)
+    calls.clear()
+    sim.plot_comprehensive_comparison(res)
+    names = [c[0] for c in calls]
+    assert names.count("semilogy") == 4 and names.count("plot") == 4 and names.count("set_title") == 4
+    assert {c[1][0] for c in calls if c[0] == "set_ylabel"} == {"Frame Error Rate (FER)", "Bit Error Rate (BER)", "Average Iterations",
+                                                                "Simulation Time (s)"}
+    calls.clear()
+    tr = PosteriorJointTrainer.__new__(PosteriorJointTrainer)
+    tr.train_losses, tr.train_accuracies, tr.gradient_norms = [1.0, 0.5], [0.6, 0.8], [2.0, 1.0]
+    tr.plot_training_history()
+    assert [c[1][0] for c in calls if c[0] == "set_title"] == ["Training Loss", "Training Accuracy", "Gradient Norm"]
+    calls.clear()
+    GradientExplosionAnalyzer.plot_gradient_analysis(None, {"gradient_magnitudes": [1.0, 2.0], "iteration_counts": [3, 4]}, save_path="g.png")
+    assert [c[0] for c in calls].count("hist") == 1 and [c[0] for c in calls].count("scatter") == 1
+    # no matplotlib: a clear error
+    monkeypatch.setitem(sys.modules, "matplotlib", None)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", None)
+    with pytest.raises(ImportError):
+        sim.plot_fer_curves(res)
